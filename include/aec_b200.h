@@ -1,0 +1,150 @@
+/*
+ * aec_b200.h -- C ABI of the B200 AEC device layer.
+ *
+ * This is the thin boundary the C host code (libaec.h / szlib.h entry points in
+ * libaec_b200/csrc/libaec_api.c and sz_api.c) uses to reach the CUDA kernels,
+ * and the boundary a foreign-language binding (ctypes, cgo, JNI ...) would bind
+ * for the hot path.  Plain pointers and sizes only.
+ *
+ * What each entry point replaces in the reference (/root/reference/src):
+ *   aecb200_encode_host    the work of aec_buffer_encode  (encode.c:950-963) = aec_encode_init
+ *                          (:773-907) + aec_encode(AEC_FLUSH) (:909-936) + aec_encode_end (:938-948)
+ *   aecb200_decode_host    the work of aec_buffer_decode  (decode.c:843-854)
+ *   aecb200_encode_device / aecb200_decode_device
+ *                          the same on buffers already resident in HBM (no reference
+ *                          counterpart: the reference only knows host pointers)
+ *   aecb200_scan_offsets_* RSI boundary discovery; the reference discovers boundaries
+ *                          implicitly by decoding sequentially (decode.c:402-421 m_id)
+ *
+ * Return values are the libaec codes (libaec.h): 0 AEC_OK, -1 AEC_CONF_ERROR,
+ * -2 AEC_STREAM_ERROR, -3 AEC_DATA_ERROR, -4 AEC_MEM_ERROR; -100 = CUDA failure
+ * (see aecb200_last_error).  There is no CPU fallback: without a usable CUDA
+ * device every call fails with -100.
+ */
+#ifndef AEC_B200_H
+#define AEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AECB200_CUDA_ERROR (-100)
+
+typedef struct aecb200_ctx aecb200_ctx;
+
+/* same four fields as struct aec_stream's coding parameters (libaec.h:84-97) */
+typedef struct {
+    uint32_t bits_per_sample;
+    uint32_t block_size;
+    uint32_t rsi;
+    uint32_t flags;
+} aecb200_params;
+
+/* Carry between consecutive encode launches of one stream (AEC_NO_FLUSH
+ * streaming, multi-GPU shards): where the next bit goes, the bits already in
+ * the partially filled 32-bit word there, and the split position k of the last
+ * coded block (the reference keeps both in struct internal_state:
+ * encode.h:128-133 `bits`, :145 `k`). */
+typedef struct {
+    uint64_t bits;      /* bit offset of the next free bit in the output buffer */
+    uint32_t k;
+    uint32_t word;      /* big-endian content of the 32-bit word containing `bits` */
+} aecb200_carry;
+
+int  aecb200_device_count(void);
+/* device < 0: current device.  One context = one CUDA stream + workspace;
+ * use one context per thread. */
+int  aecb200_ctx_create(aecb200_ctx **ctx, int device);
+void aecb200_ctx_destroy(aecb200_ctx *ctx);
+/* Run all work of this context on an existing CUDA stream (cudaStream_t). */
+int  aecb200_ctx_set_stream(aecb200_ctx *ctx, void *cuda_stream);
+const char *aecb200_last_error(aecb200_ctx *ctx);
+/* Honour AEC_PAD_RSI when encoding (the reference does so only when built with
+ * -DENABLE_RSI_PADDING, encode.c:499-505; default off like the stock build). */
+void aecb200_ctx_set_encode_padding(aecb200_ctx *ctx, int on);
+/* Number of kernels this context has launched so far. */
+uint64_t aecb200_ctx_launches(aecb200_ctx *ctx);
+
+/* Upper bound of the compressed size of in_bytes of input. */
+size_t aecb200_encode_bound(const aecb200_params *p, size_t in_bytes);
+/* Device workspace the context will hold for an input of in_bytes. */
+
+/* ---- device-resident buffers ------------------------------------------- */
+
+/* Enqueue the encode of d_in[0..in_bytes) into d_out starting at carry->bits.
+ * d_out must be 4-byte aligned; d_in should be 16-byte aligned (unaligned input
+ * takes a slower bytewise load path).  d_rsi_offsets (optional, device,
+ * ceil(samples / (rsi*block_size)) entries) receives the start bit of every RSI.
+ * Asynchronous: results are collected by aecb200_encode_finish. */
+int aecb200_encode_device(aecb200_ctx *ctx, const aecb200_params *p,
+                          const void *d_in, size_t in_bytes,
+                          void *d_out, size_t out_cap,
+                          const aecb200_carry *carry,
+                          uint64_t *d_rsi_offsets);
+/* Wait for the last enqueued encode; returns the carry after it (end bit, k;
+ * `word` is not filled).  AEC_STREAM_ERROR when the stream did not fit out_cap. */
+int aecb200_encode_finish(aecb200_ctx *ctx, aecb200_carry *end);
+
+/* Enqueue the decode of out_bytes/bytes_per_sample samples from the stream at
+ * d_in using the RSI start offsets d_rsi_offsets[0..nrsi).  Asynchronous. */
+int aecb200_decode_device(aecb200_ctx *ctx, const aecb200_params *p,
+                          const void *d_in, size_t in_bytes,
+                          const uint64_t *d_rsi_offsets, size_t nrsi,
+                          void *d_out, size_t out_bytes);
+/* Wait for the last enqueued decode; *out_written = bytes of samples delivered. */
+int aecb200_decode_finish(aecb200_ctx *ctx, size_t *out_written);
+
+/* Sequentially discover the RSI start offsets of a stream without an index.
+ * d_rsi_offsets must hold max_rsi entries.  Synchronous. */
+int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
+                                const void *d_in, size_t in_bytes, uint64_t start_bit,
+                                uint64_t *d_rsi_offsets, size_t max_rsi, size_t *found);
+
+/* ---- host buffers (what the libaec.h entry points call) ------------------ */
+
+/* Whole-buffer encode: stage to HBM, encode, copy back.  *out_len = bytes
+ * produced (<= out_cap), *in_consumed = bytes of whole samples consumed.
+ * rsi_offsets (optional, host) receives up to offsets_cap RSI start bits. */
+int aecb200_encode_host(aecb200_ctx *ctx, const aecb200_params *p,
+                        const void *in, size_t in_bytes,
+                        void *out, size_t out_cap, size_t *out_len, size_t *in_consumed,
+                        uint64_t *rsi_offsets, size_t offsets_cap, size_t *n_offsets);
+/* Streaming piece: codes the whole RSIs in `in` (everything, including a short
+ * last RSI and the final byte padding, when `final`), continuing the stream
+ * described by *carry (bits in 0..7: how many bits of the stream's last byte
+ * are already in use; word: that byte in the top 8 bits; k).  out[0] is the
+ * byte that contains the carried bits.  *out_len = complete bytes produced
+ * (all bytes when final); *carry is updated for the next piece.  RSI offsets
+ * are relative to bit 0 of out[0]. */
+int aecb200_encode_host_piece(aecb200_ctx *ctx, const aecb200_params *p,
+                              const void *in, size_t in_bytes, int final,
+                              void *out, size_t out_cap, size_t *out_len, size_t *in_consumed,
+                              aecb200_carry *carry,
+                              uint64_t *rsi_offsets, size_t offsets_cap, size_t *n_offsets);
+
+/* Whole-buffer decode.  rsi_offsets == NULL: discover RSI boundaries on the
+ * device first (sequential, slow).  *out_len = bytes delivered. */
+int aecb200_decode_host(aecb200_ctx *ctx, const aecb200_params *p,
+                        const void *in, size_t in_bytes,
+                        const uint64_t *rsi_offsets, size_t n_offsets,
+                        void *out, size_t out_cap, size_t *out_len);
+
+/* Streaming form of the above: decode starts at `start_bit`, which must be the
+ * first bit of an RSI, and drops the first skip_samples samples of that RSI
+ * (already delivered earlier).  On return *resume_bit / *resume_delivered tell
+ * where the next call has to start: the first bit of the RSI holding the next
+ * undelivered sample and how many of its samples were delivered so far. */
+int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
+                               const void *in, size_t in_bytes,
+                               const uint64_t *rsi_offsets, size_t n_offsets,
+                               uint64_t start_bit, size_t skip_samples,
+                               void *out, size_t out_cap, size_t *out_len,
+                               uint64_t *resume_bit, size_t *resume_delivered);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AEC_B200_H */

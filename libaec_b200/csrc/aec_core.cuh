@@ -1,0 +1,537 @@
+/*
+ * aec_core.cuh -- per-block and per-RSI building blocks of the B200 AEC coder.
+ *
+ * Everything here is `__host__ __device__` so the very same code runs inside
+ * the CUDA kernels (aec_encode.cu / aec_decode.cu) and inside the CPU model
+ * harness (cpu_model.cpp) that tests/ uses to check the block logic against
+ * the oracle without a GPU.  No reference code is used; citations point at the
+ * reference lines whose *results* each function has to reproduce
+ * (/root/reference/src/...).
+ */
+#ifndef AEC_CORE_CUH
+#define AEC_CORE_CUH
+
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define AEC_HD __host__ __device__ __forceinline__
+#define AEC_HDM __host__ __device__ __forceinline__      /* member functions */
+#else
+#define AEC_HD static inline
+#define AEC_HDM inline
+#endif
+
+/* flag bits: same values as include/libaec.h */
+#define AECF_SIGNED     1u
+#define AECF_3BYTE      2u
+#define AECF_MSB        4u
+#define AECF_PREPROCESS 8u
+#define AECF_RESTRICTED 16u
+#define AECF_PAD_RSI    32u
+#define AECF_NOT_ENFORCE 64u
+
+#define AEC_MAX_J 64
+
+/* code options of one block */
+enum { OPT_ZERO = 0, OPT_SE = 1, OPT_SPLIT = 2, OPT_UNCOMP = 3, OPT_NONE = 4 };
+
+/* Coding configuration derived once per stream (host) and passed by value. */
+struct AecCfg {
+    uint32_t n;       /* bits per sample 1..32 */
+    uint32_t J;       /* block size (even, <= 64) */
+    uint32_t rsi;     /* blocks per RSI */
+    uint32_t flags;
+    uint32_t B;       /* storage bytes per sample 1..4 */
+    uint32_t idl;     /* id length */
+    uint32_t kmax;    /* 2^idl - 3 */
+    uint32_t pp;      /* preprocessing on */
+    uint32_t msb;     /* MSB-first sample storage */
+    uint32_t pad;     /* byte-align every RSI (AEC_PAD_RSI honoured) */
+    uint32_t mask;    /* 2^n - 1 */
+    uint32_t sflip;   /* 2^(n-1) for signed+pp, else 0: u = raw ^ sflip maps [xmin,xmax] -> [0,mask] */
+    uint32_t sext;    /* signed: decoder sign-extends outputs (decode.c:78-84) */
+    uint32_t R;       /* samples per RSI = rsi*J */
+};
+
+/* Validation + derivation shared by encoder and decoder
+ * (results of encode.c:777-872 and decode.c:699-763). enc!=0 applies the
+ * encoder-only checks. Returns 0 or AEC_CONF_ERROR (-1). */
+AEC_HD int aec_cfg_init(AecCfg *c, uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags,
+                        int enc, int honour_pad)
+{
+    c->n = n; c->J = J; c->rsi = rsi; c->flags = flags;
+    if (n == 0 || n > 32) return -1;
+    if (enc) {
+        if (flags & AECF_NOT_ENFORCE) { if (J & 1u) return -1; }
+        else if (J != 8 && J != 16 && J != 32 && J != 64) return -1;
+        if (rsi > 4096) return -1;
+    }
+    if (n > 16) { c->idl = 5; c->B = (n <= 24 && (flags & AECF_3BYTE)) ? 3 : 4; }
+    else if (n > 8) { c->idl = 4; c->B = 2; }
+    else {
+        if (flags & AECF_RESTRICTED) {
+            if (n <= 2) c->idl = 1; else if (n <= 4) c->idl = 2; else return -1;
+        } else c->idl = 3;
+        c->B = 1;
+    }
+    c->kmax = c->idl > 1 ? (1u << c->idl) - 3u : 0u;   /* no split option when idl <= 1 (encode.c:595-598) */
+    c->pp = (flags & AECF_PREPROCESS) ? 1u : 0u;
+    c->msb = (flags & AECF_MSB) ? 1u : 0u;
+    c->pad = (honour_pad && (flags & AECF_PAD_RSI)) ? 1u : 0u;
+    c->mask = (n == 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+    uint32_t sg = (flags & AECF_SIGNED) ? 1u : 0u;
+    c->sflip = (sg && c->pp) ? (1u << (n - 1)) : 0u;
+    c->sext = sg;
+    c->R = rsi * J;
+    return 0;
+}
+
+/* ---- small bit helpers with host equivalents ---- */
+AEC_HD int aec_clz32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+AEC_HD int aec_clz64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+AEC_HD uint32_t aec_bswap32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, 0, 0x0123);
+#else
+    return __builtin_bswap32(x);
+#endif
+}
+/* 32 bits starting `sh` bits into the 64-bit big-endian pair (hi:lo) */
+AEC_HD uint32_t aec_funnel(uint32_t hi, uint32_t lo, uint32_t sh)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, sh);
+#else
+    sh &= 31u;
+    return sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+#endif
+}
+
+/* One sample from `B` storage bytes (results of encode_accessors.c:61-143). */
+AEC_HD uint32_t aec_load_sample(const uint8_t *p, uint32_t B, uint32_t msb)
+{
+    uint32_t v = 0;
+    if (msb) { for (uint32_t i = 0; i < B; i++) v = (v << 8) | p[i]; }
+    else     { for (uint32_t i = 0; i < B; i++) v |= (uint32_t)p[i] << (8u * i); }
+    return v;
+}
+
+/* CCSDS mapper for one sample given the previous one, both already normalised
+ * to u = x - xmin in [0, M] (results of encode.c:255-269 / :294-309; the two
+ * signedness variants collapse to this single unsigned form). */
+AEC_HD uint32_t aec_map_delta(uint32_t u0, uint32_t u1, uint32_t M)
+{
+    uint32_t ge = u1 >= u0;
+    uint32_t D = ge ? (u1 - u0) : (u0 - u1);
+    uint32_t th = (u0 < M - u0) ? u0 : (M - u0);
+    return (D <= th) ? (2u * D - (ge ? 0u : 1u)) : (th + D);
+}
+
+/* Inverse of aec_map_delta (results of decode.c:89-135). */
+AEC_HD uint32_t aec_unmap_delta(uint32_t u0, uint32_t d, uint32_t M)
+{
+    uint32_t h = (d >> 1) + (d & 1u);
+    uint32_t mu = M - u0;
+    uint32_t th = (u0 < mu) ? u0 : mu;
+    uint32_t step = (d & 1u) ? (u0 - h) : (u0 + h);
+    uint32_t clip = (u0 <= mu) ? d : (M - d);
+    return (h <= th) ? step : clip;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Encoder: per-block analysis                                                */
+/* ------------------------------------------------------------------------- */
+
+struct BlockInfo {
+    uint32_t opt;     /* OPT_* (OPT_ZERO = all-zero block, length decided by the run logic) */
+    uint32_t klo, khi;/* argmin plateau of the split length (identity 0..kmax when unused) */
+    uint32_t len;     /* CDS bits for SE/SPLIT/UNCOMP incl. id and reference sample */
+};
+
+/* Sum of d[i] >> k over the block. */
+template <int JT>
+AEC_HD uint32_t aec_sum_shift(const uint32_t *d, uint32_t J, uint32_t k)
+{
+    uint32_t s = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t i = 0; i < (JT ? (uint32_t)JT : J); i++) s += d[i] >> k;
+    return s;
+}
+
+/*
+ * Analyse one non-trivial block: pick the code option exactly as the
+ * reference does (encode.c:585-612) and report the k plateau [klo,khi]
+ * (encode.c:329-410 returns clamp(k_prev, klo, khi)).
+ *   d[0..J)   mapped samples (d[0] == 0 in a reference block)
+ *   ref       1 when the block carries the reference sample
+ * Returns opt == OPT_ZERO when every sample is zero (caller runs the zero-run
+ * logic); then klo/khi are the identity.
+ */
+template <int JT>
+AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t ref)
+{
+    const uint32_t J = JT ? (uint32_t)JT : c.J;
+    BlockInfo bi;
+    bi.klo = 0; bi.khi = c.kmax; bi.len = 0; bi.opt = OPT_ZERO;
+
+    uint32_t orv = 0;
+    uint64_t S0 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t i = 0; i < J; i++) { orv |= d[i]; S0 += d[i]; }
+    if (orv == 0) return bi;
+
+    const uint32_t thisbs = J - ref;
+    const uint32_t unc = thisbs * c.n;                 /* encode.c:270, :746 */
+
+    /* ---- split option: T(k) = S(k) - S(k+1) = sum ceil((d>>k)/2) is
+     * non-increasing; klo = first k < kmax with T(k) <= thisbs, khi = first
+     * k < kmax with T(k) < thisbs, both kmax when none. ---- */
+    uint32_t split = 0xFFFFFFFFu;
+    if (c.idl > 1) {
+        /* guess: smallest k with (S0 >> (k+1)) <= thisbs */
+        uint64_t q = S0 >> 1;
+        int kg = 0;
+        if (q > thisbs) {
+            /* bits(q) - bits(thisbs) is within one of the answer */
+            kg = (64 - aec_clz64(q)) - (32 - aec_clz32(thisbs));
+            if (kg < 0) kg = 0;
+            while (kg > 0 && (q >> (kg - 1)) <= thisbs) kg--;
+            while ((q >> kg) > thisbs) kg++;
+        }
+        uint32_t kmax = c.kmax;
+        uint32_t kb = (uint32_t)kg > kmax ? kmax : (uint32_t)kg;
+        kb = kb > 0 ? kb - 1 : 0;                       /* window base */
+        if (kb + 1 > kmax) kb = kmax > 0 ? kmax - 1 : 0;
+        /* S at kb..kb+4 (values beyond kmax are never consulted) */
+        uint32_t S[5];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 5; j++) S[j] = 0;
+        if (S0 >> kb <= 0xFFFFFFFFull / 2) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (uint32_t i = 0; i < J; i++) {
+                uint32_t v = d[i] >> kb;
+                S[0] += v; S[1] += v >> 1; S[2] += v >> 2; S[3] += v >> 3; S[4] += v >> 4;
+            }
+        } else {
+            kb = 0xFFFFFFFFu;                           /* force the exact path */
+        }
+        bool done = false;
+        uint32_t lo = 0, hi = 0, slo = 0;
+        if (kb != 0xFFFFFFFFu) {
+            /* T_j for k = kb+j, j = 0..3, only meaningful while kb+j < kmax */
+            int jlo = -1, jhi = -1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int j = 0; j < 4; j++) {
+                uint32_t k = kb + (uint32_t)j;
+                bool valid = k < kmax;
+                uint32_t T = S[j] - S[j + 1];
+                if (valid && jlo < 0 && T <= thisbs) jlo = j;
+                if (valid && jhi < 0 && T < thisbs) jhi = j;
+            }
+            /* low side resolved when the first T<=thisbs is not at the window's
+             * left edge (or the window starts at k = 0) */
+            bool lo_ok, hi_ok;
+            if (jlo >= 0) { lo = kb + (uint32_t)jlo; lo_ok = (jlo > 0) || (kb == 0); }
+            else { lo = kmax; lo_ok = (kb + 4 >= kmax); }
+            if (jhi >= 0) { hi = kb + (uint32_t)jhi; hi_ok = true; }
+            else { hi = kmax; hi_ok = (kb + 4 >= kmax); }
+            if (lo_ok && hi_ok) {
+                done = true;
+                slo = (lo - kb <= 4) ? S[lo - kb] : 0;
+                if (lo - kb > 4) done = false;
+            }
+        }
+        if (!done) {
+            /* exact scan over every k (rare) */
+            lo = kmax; hi = kmax;
+            bool flo = false, fhi = false;
+            uint64_t prev = S0;
+            for (uint32_t k = 0; k < kmax; k++) {
+                uint64_t nxt = 0;
+                for (uint32_t i = 0; i < J; i++) nxt += d[i] >> (k + 1);
+                uint64_t T = prev - nxt;
+                if (!flo && T <= thisbs) { lo = k; flo = true; }
+                if (!fhi && T < thisbs) { hi = k; fhi = true; }
+                prev = nxt;
+                if (fhi) break;
+            }
+            uint64_t s = 0;
+            for (uint32_t i = 0; i < J; i++) s += d[i] >> lo;
+            slo = (uint32_t)s;
+        }
+        bi.klo = lo; bi.khi = hi;
+        split = slo + thisbs * (lo + 1);
+    }
+
+    /* ---- second extension (encode.c:412-434) ---- */
+    uint32_t se = 0xFFFFFFFFu;
+    if (S0 <= unc) {       /* se >= 1 + J/2 + S0, so larger S0 can never win */
+        uint64_t len = 1;
+        bool inf = false;
+        for (uint32_t i = 0; i < J; i += 2) {
+            uint64_t s = (uint64_t)d[i] + (uint64_t)d[i + 1];
+            len += s * (s + 1) / 2 + d[i + 1] + 1;
+            if (len > unc) { inf = true; break; }
+        }
+        if (!inf) se = (uint32_t)len;
+    } else if (orv >= 0x80000000u) {
+        /* the reference adds in u64 with wrap-around: only
+         * reachable when a pair sum reaches 2^32; replicate exactly */
+        uint64_t len = 1;
+        bool inf = false;
+        for (uint32_t i = 0; i < J; i += 2) {
+            uint64_t s = (uint64_t)d[i] + (uint64_t)d[i + 1];
+            len += s * (s + 1) / 2 + d[i + 1] + 1;
+            if (len > unc) { inf = true; break; }
+        }
+        if (!inf) se = (uint32_t)len;
+    }
+
+    /* ---- selection with the reference's tie-breaks (encode.c:600-611) ---- */
+    uint32_t opt, body;
+    if (split < unc) {
+        if (split < se) { opt = OPT_SPLIT; body = split; }
+        else            { opt = OPT_SE;    body = se; }
+    } else {
+        if (unc <= se)  { opt = OPT_UNCOMP; body = unc; }
+        else            { opt = OPT_SE;     body = se; }
+    }
+    bi.opt = opt;
+    /* the SE cost already counts the extra selector bit (its sum starts at 1, encode.c:424) */
+    if (opt == OPT_SE || opt == OPT_SPLIT) bi.len = c.idl + ref * c.n + body;
+    else                        bi.len = c.idl + J * c.n;       /* reference replaces sample 0 */
+    return bi;
+}
+
+/* Zero-run bookkeeping for the block at position p of its 64-block segment.
+ *   segmask  bit i set <=> block i of the segment is a valid all-zero block
+ *   V        valid blocks in this segment (1..64)
+ *   b        block index inside the RSI (p == b % 64)
+ * Returns the CDS bit length this block owns (0 when it is not the last block
+ * of its run) and fills *fs_code / *zref.  Results of encode.c:614-659 and
+ * :565-583. */
+AEC_HD uint32_t aec_zero_run(const AecCfg &c, uint64_t segmask, uint32_t V, uint32_t b,
+                             uint32_t *fs_code, uint32_t *zref)
+{
+    uint32_t p = b & 63u;
+    bool last = (p + 1 == V);
+    bool next_zero = !last && ((segmask >> (p + 1)) & 1ull);
+    if (next_zero) return 0;                           /* run continues */
+    /* run length: consecutive ones ending at bit p */
+    uint64_t sh = segmask << (63u - p);
+    uint32_t L = (uint32_t)aec_clz64(~sh);
+    if (L > p + 1) L = p + 1;
+    uint32_t code;
+    if (last && L > 4) code = 4;                       /* ROS */
+    else if (L >= 5)   code = L;
+    else               code = L - 1;
+    *fs_code = code;
+    *zref = (c.pp && (b + 1 == L)) ? 1u : 0u;          /* run starts at block 0 of the RSI */
+    return c.idl + 1 + (*zref ? c.n : 0) + code + 1;
+}
+
+/* clamp-map composition for the k chain: apply X then Y. */
+AEC_HD uint32_t aec_clampu(uint32_t v, uint32_t lo, uint32_t hi)
+{
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+AEC_HD uint32_t aec_kpair(uint32_t lo, uint32_t hi) { return lo | (hi << 8); }
+AEC_HD uint32_t aec_kcompose(uint32_t x, uint32_t y)
+{
+    uint32_t ylo = y & 0xFFu, yhi = y >> 8;
+    return aec_kpair(aec_clampu(x & 0xFFu, ylo, yhi), aec_clampu(x >> 8, ylo, yhi));
+}
+
+/* Position monoid for AEC_PAD_RSI: f(p) = has_end ? roundup8(p + a) + rest : p + a. */
+struct PosFn { uint32_t has_end; uint64_t a; uint64_t rest; };
+AEC_HD uint64_t aec_up8(uint64_t x) { return (x + 7ull) & ~7ull; }
+AEC_HD PosFn aec_pcompose(const PosFn &x, const PosFn &y)
+{
+    PosFn r;
+    if (!y.has_end) {
+        if (x.has_end) { r.has_end = 1; r.a = x.a; r.rest = x.rest + y.a; }
+        else           { r.has_end = 0; r.a = x.a + y.a; r.rest = 0; }
+    } else {
+        if (x.has_end) { r.has_end = 1; r.a = x.a; r.rest = aec_up8(x.rest + y.a) + y.rest; }
+        else           { r.has_end = 1; r.a = x.a + y.a; r.rest = y.rest; }
+    }
+    return r;
+}
+AEC_HD uint64_t aec_papply(const PosFn &f, uint64_t p)
+{
+    return f.has_end ? aec_up8(p + f.a) + f.rest : p + f.a;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Encoder: bit packer writing one CDS into a zero-initialised word buffer    */
+/* ------------------------------------------------------------------------- */
+
+/* The buffer holds big-endian-bit-order 32-bit words (bit 31 of word 0 is the
+ * first stream bit).  A CDS shares its first and last word with its
+ * neighbours, so those two are merged with OR (atomic on the GPU, where the
+ * buffer is shared memory written by 256 threads); interior words are owned
+ * exclusively and stored plainly. */
+struct BitPack {
+    uint32_t *buf;
+    uint32_t cur;     /* bits accumulated for word widx, MSB first */
+    uint32_t fill;    /* bits of cur in use (may reach 32 transiently) */
+    uint32_t widx;
+    uint32_t first;   /* next flush is the shared first word */
+
+    AEC_HDM void merge(uint32_t idx, uint32_t v)
+    {
+#if defined(__CUDA_ARCH__)
+        if (v) atomicOr(&buf[idx], v);
+#else
+        buf[idx] |= v;
+#endif
+    }
+    AEC_HDM void init(uint32_t *b, uint64_t bitpos)
+    {
+        buf = b; cur = 0; fill = (uint32_t)(bitpos & 31u); widx = (uint32_t)(bitpos >> 5);
+        first = 1;
+    }
+    AEC_HDM void flush_word()
+    {
+        if (first) { merge(widx, cur); first = 0; }
+        else buf[widx] = cur;
+        cur = 0;
+    }
+    /* append len (1..32) bits of v (v < 2^len) */
+    AEC_HDM void put(uint32_t v, uint32_t len)
+    {
+        if (fill >= 32) { flush_word(); widx += fill >> 5; fill &= 31u; }
+        uint32_t space = 32u - fill;
+        if (len < space) {
+            cur |= v << (space - len);
+            fill += len;
+        } else {
+            uint32_t rem = len - space;
+            cur |= v >> rem;
+            flush_word();
+            widx++;
+            cur = rem ? (v << (32u - rem)) : 0u;
+            fill = rem;
+        }
+    }
+    /* fundamental sequence: fs zeros then a one */
+    AEC_HDM void put_fs(uint32_t fs)
+    {
+        fill += fs;
+        if (fill >= 32) { flush_word(); widx += fill >> 5; fill &= 31u; }
+        cur |= 0x80000000u >> fill;
+        fill++;
+    }
+    AEC_HDM void finish()
+    {
+        if (cur) merge(widx, cur);
+    }
+};
+
+/*
+ * Emit the CDS of one non-zero block (results of encode.c:520-563).
+ *   d      mapped samples; refs: raw reference sample when ref
+ *   k      split position (already clamp(k_prev, klo, khi))
+ */
+template <int JT>
+AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint32_t opt,
+                           uint32_t k, uint32_t ref, uint32_t refs)
+{
+    const uint32_t J = JT ? (uint32_t)JT : c.J;
+    if (opt == OPT_SPLIT) {
+        bp.put(k + 1, c.idl);
+        if (ref) bp.put(refs, c.n);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t i = 0; i < J; i++)
+            if (i >= ref) bp.put_fs(d[i] >> k);
+        if (k) {
+            uint32_t m = (1u << k) - 1u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (uint32_t i = 0; i < J; i++)
+                if (i >= ref) bp.put(d[i] & m, k);
+        }
+    } else if (opt == OPT_SE) {
+        bp.put(1, c.idl + 1);
+        if (ref) bp.put(refs, c.n);
+        for (uint32_t i = 0; i < J; i += 2) {
+            uint32_t s = d[i] + d[i + 1];
+            bp.put_fs(s * (s + 1) / 2 + d[i + 1]);      /* u32 like encode.c:558-559 */
+        }
+    } else { /* OPT_UNCOMP */
+        bp.put((1u << c.idl) - 1u, c.idl);
+        bp.put(ref ? refs : d[0], c.n);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t i = 1; i < J; i++) bp.put(d[i], c.n);
+    }
+}
+
+/* Zero-run CDS (results of encode.c:565-583). */
+AEC_HD void aec_pack_zero(const AecCfg &c, BitPack &bp, uint32_t fs_code, uint32_t zref, uint32_t refs)
+{
+    bp.put(0, c.idl + 1);
+    if (zref) bp.put(refs, c.n);
+    bp.put_fs(fs_code);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Decoder: big-endian bit reader over 32-bit words                           */
+/* ------------------------------------------------------------------------- */
+
+struct BitRd {
+    const uint32_t *w;   /* 4-byte aligned, raw (byte order as stored) */
+    uint64_t nwords;     /* words that may be read; beyond that zeros */
+    uint64_t nbits;      /* valid stream bits */
+    uint64_t ci;         /* index of cached word pair */
+    uint32_t c0, c1;
+
+    AEC_HDM uint32_t word(uint64_t i) const { return i < nwords ? aec_bswap32(w[i]) : 0u; }
+    AEC_HDM void init(const uint32_t *base, uint64_t nw, uint64_t nb)
+    {
+        w = base; nwords = nw; nbits = nb; ci = 0xFFFFFFFFFFFFFFF0ull; c0 = c1 = 0;
+    }
+    /* 32 stream bits starting at bit position pos (zeros past the end) */
+    AEC_HDM uint32_t peek(uint64_t pos)
+    {
+        uint64_t i = pos >> 5;
+        if (i != ci) {
+            if (i == ci + 1) { c0 = c1; c1 = word(i + 1); }
+            else { c0 = word(i); c1 = word(i + 1); }
+            ci = i;
+        }
+        return aec_funnel(c0, c1, (uint32_t)(pos & 31u));
+    }
+};
+
+#endif /* AEC_CORE_CUH */

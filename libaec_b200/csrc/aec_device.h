@@ -1,0 +1,64 @@
+/*
+ * aec_device.h -- internal interface between the host runtime (aec_runtime.cu)
+ * and the CUDA kernels.  Not installed; the public C ABI is include/aec_b200.h.
+ */
+#ifndef AEC_DEVICE_H
+#define AEC_DEVICE_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "aec_core.cuh"
+
+/* Arguments of one encode launch (passed by value). */
+struct AecEncArgs {
+    AecCfg cfg;
+    const uint8_t *in;          /* raw samples, device */
+    uint64_t nsamples;          /* whole samples in `in` */
+    uint64_t nrsi;              /* RSIs to code (last may be short) */
+    uint32_t last_nblk;         /* coded blocks of the last RSI */
+    uint32_t RP;                /* block slots per RSI (power of two <= TB, or multiple of TB) */
+    uint64_t ntiles;
+    uint32_t aligned;           /* `in` is 16-byte aligned */
+    uint32_t staging_words;     /* dynamic shared memory in words */
+    uint32_t *out_words;        /* output stream, 4-byte aligned, device */
+    uint64_t out_cap_words;     /* floor(capacity / 4) */
+    uint64_t out_cap_bytes;
+    uint64_t seed_bits;         /* bit offset in out where this launch starts */
+    uint32_t seed_k;            /* k carried in from the stream so far */
+    uint32_t seed_word;         /* content of the partial word at seed_bits (bits already there) */
+    /* workspace, device */
+    uint64_t *desc;             /* [ntiles], zeroed */
+    uint32_t *ticket;           /* zeroed */
+    uint32_t *head_c, *tail_c;  /* [ntiles] partial boundary words */
+    uint64_t *tile_end;         /* [ntiles] absolute end bit of each tile */
+    uint64_t *rsi_offsets;      /* optional [nrsi] absolute start bit of each RSI */
+    uint64_t *result;           /* [0] end bit, [1] k after the last block */
+};
+
+/* Arguments of one decode launch. */
+struct AecDecArgs {
+    AecCfg cfg;
+    const uint32_t *in_words;   /* compressed stream, 4-byte aligned, device */
+    uint64_t in_bytes;
+    const uint64_t *rsi_offsets;/* [nrsi] start bit of each RSI */
+    uint64_t nrsi;
+    uint8_t *out;               /* decoded samples, device */
+    uint64_t out_samples;       /* samples wanted in total */
+    uint32_t out_aligned;       /* out is 16-byte aligned */
+    uint64_t *result;           /* [0] samples delivered (contiguous prefix), [1] status flags */
+    uint32_t *rsi_count;        /* [nrsi] samples each RSI delivered */
+};
+
+uint32_t aec_encode_tile_blocks(uint32_t J);
+uint32_t aec_encode_staging_words(const AecCfg &c);
+cudaError_t aec_encode_launch(const AecEncArgs &a, int num_sms, cudaStream_t st);
+
+cudaError_t aec_decode_launch(const AecDecArgs &a, int num_sms, cudaStream_t st);
+/* Sequential RSI-boundary scan for streams without an offset index:
+ * fills offsets[0..max_rsi) and result[0] = RSIs found, result[1] = status. */
+cudaError_t aec_scan_offsets_launch(const AecCfg &c, const uint32_t *in_words, uint64_t in_bytes,
+                                    uint64_t start_bit, uint64_t *offsets, uint64_t max_rsi,
+                                    uint64_t *result, cudaStream_t st);
+
+#endif

@@ -1,0 +1,506 @@
+/*
+ * aec_encode.cu -- single-pass CCSDS 121.0-B-2 encoder for sm_100a.
+ *
+ * Replaces the hot loop of the reference's encoder state machine
+ * (/root/reference/src/encode.c:614-754 m_get_block / m_check_zero_block /
+ * m_select_code_option / m_encode_*, :235-311 preprocess_*, :313-434 option
+ * costs, :61-233 bit emission, src/encode_accessors.c) with one persistent
+ * kernel:
+ *
+ *   thread  = one block of J samples (loaded with 16-byte vector loads,
+ *             mapped and costed in registers),
+ *   warp    = ballots give the zero-run structure of a 64-block segment,
+ *             shuffles give the exclusive scan of CDS bit lengths and of the
+ *             k clamp chain,
+ *   CTA     = one tile of TB consecutive block slots; tiles are handed out in
+ *             order by an atomic ticket, publish their aggregate
+ *             (bits, clamp pair) in a 64-bit descriptor and obtain their
+ *             absolute bit offset / incoming k with a decoupled look-back,
+ *   output  = each thread packs its CDS into a shared-memory staging area
+ *             laid out at the tile's final bit phase; the tile then streams
+ *             whole 32-bit words to global memory.  Words shared between two
+ *             tiles are resolved afterwards by a tiny fix-up kernel, so the
+ *             output needs neither atomics nor pre-zeroing.
+ *
+ * Input is read exactly once and output written exactly once.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "aec_core.cuh"
+#include "aec_device.h"
+
+namespace {
+
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+/* ---- descriptor encoding (one 64-bit word, written/read with single
+ * volatile accesses) ------------------------------------------------------ */
+constexpr uint64_t ST_AGG = 1, ST_PREFIX = 2;
+
+__device__ __forceinline__ uint64_t desc_pack_agg(const PosFn &f, uint32_t kp)
+{
+    return ST_AGG | ((uint64_t)(kp & 0x1Fu) << 2) | ((uint64_t)((kp >> 8) & 0x1Fu) << 7) |
+           ((uint64_t)(f.has_end & 1u) << 12) | ((f.a & 0x1FFFFFull) << 13) | ((f.rest & 0x1FFFFFull) << 34);
+}
+__device__ __forceinline__ uint64_t desc_pack_prefix(uint64_t bits, uint32_t k)
+{
+    return ST_PREFIX | ((uint64_t)(k & 0x1Fu) << 2) | (bits << 12);
+}
+__device__ __forceinline__ void desc_unpack(uint64_t d, PosFn &f, uint32_t &kp)
+{
+    if ((d & 3) == ST_PREFIX) {
+        uint32_t k = (uint32_t)(d >> 2) & 0x1Fu;
+        kp = aec_kpair(k, k);
+        f.has_end = 0; f.a = d >> 12; f.rest = 0;
+    } else {
+        kp = aec_kpair((uint32_t)(d >> 2) & 0x1Fu, (uint32_t)(d >> 7) & 0x1Fu);
+        f.has_end = (uint32_t)(d >> 12) & 1u;
+        f.a = (d >> 13) & 0x1FFFFFull;
+        f.rest = (d >> 34) & 0x1FFFFFull;
+    }
+}
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p)
+{
+    return *reinterpret_cast<const volatile uint64_t *>(p);
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t *p, uint64_t v)
+{
+    *reinterpret_cast<volatile uint64_t *>(p) = v;
+}
+
+__device__ __forceinline__ PosFn shfl_posfn(const PosFn &v, int src)
+{
+    PosFn r;
+    r.has_end = __shfl_sync(FULL, v.has_end, src);
+    r.a = __shfl_sync(FULL, (unsigned long long)v.a, src);
+    r.rest = __shfl_sync(FULL, (unsigned long long)v.rest, src);
+    return r;
+}
+
+/* ---- sample loading ------------------------------------------------------ */
+
+/* Sample i of a block whose bytes sit in the word array w (little-endian
+ * words as loaded). Compile-time i after unrolling -> a couple of PRMT/SHF. */
+template <int B>
+__device__ __forceinline__ uint32_t extract_sample(const uint32_t *w, int i, uint32_t msb)
+{
+    if (B == 4) return msb ? __byte_perm(w[i], 0, 0x0123) : w[i];
+    if (B == 2) {
+        uint32_t x = w[i >> 1];
+        if (i & 1) return msb ? __byte_perm(x, 0, 0x4423) : (x >> 16);
+        return msb ? __byte_perm(x, 0, 0x4401) : (x & 0xFFFFu);
+    }
+    if (B == 1) return (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+    /* B == 3 */
+    int o = i * 3;
+    uint32_t lo = w[o >> 2];
+    uint32_t hi = ((o & 3) > 1) ? w[(o >> 2) + 1] : 0u;
+    uint32_t v = __funnelshift_r(lo, hi, 8 * (o & 3)) & 0xFFFFFFu;
+    return msb ? __byte_perm(v, 0, 0x4012) : v;
+}
+
+/* Load the J raw samples of one block.  fast: the whole block is inside the
+ * input and the base pointer is 16-byte aligned. */
+template <int JT, int B>
+__device__ __forceinline__ void load_block(const AecCfg &c, const uint8_t *in, uint64_t first,
+                                           uint64_t nsamples, bool fast, uint32_t *x)
+{
+    const uint32_t J = JT ? (uint32_t)JT : c.J;
+    if (JT != 0 && fast) {
+        constexpr int BB = (JT ? JT : 2) * B;               /* bytes per block */
+        constexpr int VW = (BB % 16 == 0) ? 16 : ((BB % 8 == 0) ? 8 : ((BB % 4 == 0) ? 4 : 2));
+        constexpr int NW = (BB + 3) / 4;
+        uint32_t w[NW + 1];
+        const uint8_t *p = in + first * B;
+        if (VW == 16) {
+#pragma unroll
+            for (int j = 0; j < BB / 16; j++) {
+                uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + j);
+                w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
+            }
+        } else if (VW == 8) {
+#pragma unroll
+            for (int j = 0; j < BB / 8; j++) {
+                uint2 q = __ldg(reinterpret_cast<const uint2 *>(p) + j);
+                w[2 * j] = q.x; w[2 * j + 1] = q.y;
+            }
+        } else if (VW == 4) {
+#pragma unroll
+            for (int j = 0; j < BB / 4; j++) w[j] = __ldg(reinterpret_cast<const uint32_t *>(p) + j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NW; j++) {
+                uint32_t a = __ldg(reinterpret_cast<const uint16_t *>(p) + 2 * j);
+                uint32_t b = (4 * j + 2 < BB) ? __ldg(reinterpret_cast<const uint16_t *>(p) + 2 * j + 1) : 0u;
+                w[j] = a | (b << 16);
+            }
+        }
+        w[NW] = 0;
+#pragma unroll
+        for (int i = 0; i < JT; i++) x[i] = extract_sample<B>(w, i, c.msb);
+    } else {
+        /* generic: bytewise, index clamped to the last sample (encode.c:681-684) */
+        for (uint32_t i = 0; i < J; i++) {
+            uint64_t idx = first + i;
+            if (idx >= nsamples) idx = nsamples - 1;
+            x[i] = aec_load_sample(in + idx * c.B, c.B, c.msb);
+        }
+    }
+}
+
+/* ---- the kernel ----------------------------------------------------------- */
+
+template <int JT>
+struct TileCfg {
+    static constexpr int TB = (JT == 0 || JT == 64) ? 128 : 256;
+    static constexpr int NWARP = TB / 32;
+    static constexpr int JMAX = JT ? JT : AEC_MAX_J;
+};
+
+template <int JT, int B>
+__global__ void __launch_bounds__(TileCfg<JT>::TB)
+aec_encode_kernel(const AecEncArgs a)
+{
+    constexpr int TB = TileCfg<JT>::TB;
+    constexpr int NWARP = TileCfg<JT>::NWARP;
+    constexpr int JMAX = TileCfg<JT>::JMAX;
+    const AecCfg &c = a.cfg;
+    const uint32_t J = JT ? (uint32_t)JT : c.J;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    extern __shared__ uint32_t staging[];
+    __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_zb[NWARP + 1];
+    __shared__ uint32_t s_wlen[NWARP];       /* per-warp sums (no-pad mode) */
+    __shared__ uint32_t s_wend[NWARP], s_wa[NWARP], s_wrest[NWARP];   /* per-warp PosFn (pad mode) */
+    __shared__ uint32_t s_wk[NWARP];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_kin;
+
+    for (;;) {
+        if (tid == 0) s_ticket = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const uint64_t tile = s_ticket;
+        if (tile >= a.ntiles) break;
+
+        /* ---- which block is mine ---- */
+        uint64_t rsi_idx; uint32_t b;
+        if (a.RP >= (uint32_t)TB) {
+            uint32_t tpr = a.RP / TB;
+            rsi_idx = tile / tpr;
+            b = (uint32_t)(tile % tpr) * TB + tid;
+        } else {
+            rsi_idx = tile * (TB / a.RP) + tid / a.RP;
+            b = tid % a.RP;
+        }
+        uint32_t nblk = 0;
+        if (rsi_idx + 1 < a.nrsi) nblk = c.rsi;
+        else if (rsi_idx + 1 == a.nrsi) nblk = a.last_nblk;
+        const bool valid = b < nblk;
+        const uint32_t ref = (valid && c.pp && b == 0) ? 1u : 0u;
+
+        /* ---- load, map ---- */
+        uint32_t d[JMAX];
+        uint32_t refs = 0;
+        BlockInfo bi; bi.opt = OPT_NONE; bi.klo = 0; bi.khi = c.kmax; bi.len = 0;
+        if (valid) {
+            const uint64_t first = rsi_idx * (uint64_t)c.R + (uint64_t)b * J;
+            const bool fast = a.aligned && (first + J <= a.nsamples);
+            load_block<JT, B>(c, a.in, first, a.nsamples, fast, d);
+            if (c.pp) {
+                uint32_t prev;
+                if (b == 0) { refs = d[0]; prev = d[0] ^ c.sflip; }
+                else {
+                    uint64_t pi = first - 1;
+                    if (pi >= a.nsamples) pi = a.nsamples - 1;
+                    prev = aec_load_sample(a.in + pi * c.B, c.B, c.msb) ^ c.sflip;
+                }
+#pragma unroll
+                for (uint32_t i = 0; i < (JT ? (uint32_t)JT : J); i++) {
+                    uint32_t u = d[i] ^ c.sflip;
+                    d[i] = aec_map_delta(prev, u, c.mask);
+                    prev = u;
+                }
+                if (b == 0) d[0] = 0;
+            }
+            bi = aec_analyze_block<JT>(c, d, ref);
+        }
+        const bool is_zero = valid && bi.opt == OPT_ZERO;
+
+        /* ---- zero-run structure of my 64-block segment ---- */
+        uint32_t ball = __ballot_sync(FULL, is_zero);
+        if (lane == 0) s_zb[warp] = ball;
+        __syncthreads();
+        uint32_t len = bi.len, zcode = 0, zref = 0;
+        if (is_zero) {
+            uint64_t m64 = (uint64_t)s_zb[warp & ~1u] | ((uint64_t)((warp | 1u) < NWARP ? s_zb[warp | 1u] : 0u) << 32);
+            uint32_t q = tid & 63u;                       /* position in the aligned 64-slot group */
+            uint32_t g0 = q - (b & 63u);                  /* where my segment starts in the group */
+            uint32_t seg = b >> 6;
+            uint32_t V = nblk - seg * 64u; if (V > 64u) V = 64u;
+            uint64_t segmask = (m64 >> g0);
+            if (V < 64u) segmask &= ((1ull << V) - 1ull);
+            len = aec_zero_run(c, segmask, V, b, &zcode, &zref);
+        }
+        if (zref) {   /* run owner needs the reference sample of block 0 of the RSI */
+            uint64_t f0 = rsi_idx * (uint64_t)c.R;
+            refs = aec_load_sample(a.in + f0 * c.B, c.B, c.msb);
+        }
+        const bool rsi_end = valid && (b + 1 == nblk);
+
+        /* ---- intra-tile exclusive scans: bit offsets and k clamp chain ---- */
+        uint32_t kp = aec_kpair(bi.klo, bi.khi);          /* identity for zero/invalid/idl<=1 */
+        uint32_t kinc = kp;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t o = __shfl_up_sync(FULL, kinc, off);
+            if (lane >= (uint32_t)off) kinc = aec_kcompose(o, kinc);
+        }
+        uint32_t kexc = __shfl_up_sync(FULL, kinc, 1);
+        if (lane == 0) kexc = aec_kpair(0, c.kmax);
+
+        PosFn pinc; pinc.has_end = 0; pinc.a = 0; pinc.rest = 0;   /* pad mode */
+        uint32_t linc = len;                                      /* no-pad mode */
+        if (c.pad) {
+            pinc.has_end = rsi_end ? 1u : 0u; pinc.a = len; pinc.rest = 0;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                PosFn o = shfl_posfn(pinc, (int)lane - off);
+                if (lane >= (uint32_t)off) pinc = aec_pcompose(o, pinc);
+            }
+        } else {
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t o = __shfl_up_sync(FULL, linc, off);
+                if (lane >= (uint32_t)off) linc += o;
+            }
+        }
+        if (lane == 31) {
+            s_wk[warp] = kinc;
+            s_wlen[warp] = linc;
+            s_wend[warp] = pinc.has_end; s_wa[warp] = (uint32_t)pinc.a; s_wrest[warp] = (uint32_t)pinc.rest;
+        }
+        __syncthreads();
+
+        /* function of everything before me in the tile */
+        PosFn pexc; pexc.has_end = 0; pexc.a = 0; pexc.rest = 0;
+        uint32_t kbefore = aec_kpair(0, c.kmax);
+        PosFn ptile = pexc; uint32_t ktile = kbefore;
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) {
+            PosFn f;
+            if (c.pad) { f.has_end = s_wend[w]; f.a = s_wa[w]; f.rest = s_wrest[w]; }
+            else { f.has_end = 0; f.a = s_wlen[w]; f.rest = 0; }
+            if ((uint32_t)w < warp) { pexc = aec_pcompose(pexc, f); kbefore = aec_kcompose(kbefore, s_wk[w]); }
+            ptile = aec_pcompose(ptile, f); ktile = aec_kcompose(ktile, s_wk[w]);
+        }
+        {   /* add the lanes before me in my own warp */
+            PosFn f;
+            if (c.pad) {
+                f = shfl_posfn(pinc, (int)lane - 1);
+            } else {
+                f.has_end = 0; f.a = __shfl_up_sync(FULL, linc, 1); f.rest = 0;
+            }
+            if (lane > 0) pexc = aec_pcompose(pexc, f);
+            kbefore = aec_kcompose(kbefore, kexc);
+        }
+
+        /* ---- zero the staging area (upper bound on the tile's bits) ---- */
+        {
+            uint32_t ub = (uint32_t)(ptile.a + ptile.rest) + (c.pad ? 8u * TB : 0u);
+            uint32_t nz = (31u + ub + 31u) / 32u + 1u;
+            if (nz > a.staging_words) nz = a.staging_words;
+            for (uint32_t i = tid; i < nz; i += TB) staging[i] = 0;
+        }
+
+        /* ---- publish aggregate, decoupled look-back (warp 0) ---- */
+        if (warp == 0) {
+            if (lane == 0) st_volatile_u64(&a.desc[tile], desc_pack_agg(ptile, ktile));
+            PosFn accp; accp.has_end = 0; accp.a = 0; accp.rest = 0;
+            uint32_t acck = aec_kpair(0, c.kmax);
+            int64_t pred = (int64_t)tile - 1;
+            for (;;) {
+                int64_t idx = pred - (int64_t)lane;
+                uint64_t dv = 0;
+                if (idx >= 0) {
+                    do { dv = ld_volatile_u64(&a.desc[idx]); } while ((dv & 3) == 0);
+                } else if (idx == -1) {
+                    dv = desc_pack_prefix(a.seed_bits, a.seed_k);
+                } else {
+                    dv = ST_AGG | ((uint64_t)c.kmax << 7);      /* identity, never reached */
+                }
+                __syncwarp();
+                uint32_t pm = __ballot_sync(FULL, (dv & 3) == ST_PREFIX);
+                int firstp = pm ? (__ffs((int)pm) - 1) : 32;
+                PosFn f; uint32_t k;
+                desc_unpack(dv, f, k);
+                if ((int)lane > firstp) { f.has_end = 0; f.a = 0; f.rest = 0; k = aec_kpair(0, c.kmax); }
+                /* ordered reduction: higher lane = earlier tile */
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    PosFn o = shfl_posfn(f, (int)lane + off);
+                    uint32_t ok = __shfl_down_sync(FULL, k, off);
+                    if (lane + off < 32u) { f = aec_pcompose(o, f); k = aec_kcompose(ok, k); }
+                }
+                f = shfl_posfn(f, 0); k = __shfl_sync(FULL, k, 0);
+                accp = aec_pcompose(f, accp); acck = aec_kcompose(k, acck);
+                if (pm) break;
+                pred -= 32;
+            }
+            if (lane == 0) {
+                uint64_t base = aec_papply(accp, 0);
+                uint32_t kin = acck & 0xFFu;              /* constant map: lo == hi */
+                uint64_t end = aec_papply(ptile, base);
+                uint32_t kout = aec_clampu(kin, ktile & 0xFFu, ktile >> 8);
+                st_volatile_u64(&a.desc[tile], desc_pack_prefix(end, kout));
+                s_base = base; s_kin = kin;
+                a.tile_end[tile] = end;
+                if (tile + 1 == a.ntiles) { a.result[0] = end; a.result[1] = kout; }
+            }
+        }
+        __syncthreads();
+
+        /* ---- pack my CDS into the staging area ---- */
+        const uint64_t base = s_base;
+        const uint64_t w0 = base >> 5;
+        const uint64_t myoff = aec_papply(pexc, base);
+        if (valid && b == 0 && a.rsi_offsets) a.rsi_offsets[rsi_idx] = myoff;
+        if (valid && len) {
+            BitPack bp;
+            bp.init(staging, myoff - (w0 << 5));
+            if (is_zero) {
+                aec_pack_zero(c, bp, zcode, zref, refs);
+            } else {
+                uint32_t kprev = aec_clampu(s_kin, kbefore & 0xFFu, kbefore >> 8);
+                uint32_t k = aec_clampu(kprev, bi.klo, bi.khi);
+                aec_pack_block<JT>(c, bp, d, bi.opt, k, ref, refs);
+            }
+            bp.finish();
+        }
+        __syncthreads();
+
+        /* ---- stream the tile's words out ---- */
+        {
+            const uint64_t end = aec_papply(ptile, base);
+            const uint64_t we = end >> 5;
+            const uint32_t nw = (uint32_t)(we - w0) + ((end & 31u) ? 1u : 0u);
+            const bool head_partial = (base & 31u) != 0;
+            const bool tail_partial = (end & 31u) != 0 && (we > w0 || !head_partial);
+            for (uint32_t i = tid; i < nw; i += TB) {
+                uint32_t v = staging[i];
+                uint64_t wi = w0 + i;
+                if (i == 0 && head_partial) continue;
+                if (wi == we) continue;                   /* partial tail word */
+                if (wi < a.out_cap_words) a.out_words[wi] = __byte_perm(v, 0, 0x0123);
+            }
+            if (tid == 0) {
+                a.head_c[tile] = (head_partial && end > base) ? staging[0] : 0u;
+                a.tail_c[tile] = tail_partial ? staging[(uint32_t)(we - w0)] : 0u;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* Resolve the words shared between tiles (and with the bits a previous call
+ * left in the stream's last partial word): one thread per tile boundary. */
+__global__ void aec_encode_fixup_kernel(const AecEncArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - 1;   /* -1 = the seed */
+    if (i >= (int64_t)a.ntiles) return;
+    const uint64_t total = a.tile_end[a.ntiles - 1];
+    uint64_t bi = (i <= 0) ? a.seed_bits : a.tile_end[i - 1];
+    uint64_t ei = (i < 0) ? a.seed_bits : a.tile_end[i];
+    uint32_t v;
+    if (i < 0) {
+        if ((ei & 31u) == 0) return;
+        v = a.seed_word;
+    } else {
+        if ((ei & 31u) == 0) return;
+        bool head_partial = (bi & 31u) != 0;
+        if (!((ei >> 5) > (bi >> 5) || !head_partial)) return;   /* no tail contribution of its own */
+        v = a.tail_c[i];
+    }
+    const uint64_t word = ei >> 5;
+    for (int64_t j = i + 1; j < (int64_t)a.ntiles; j++) {
+        uint64_t ej = a.tile_end[j];
+        v |= a.head_c[j];
+        if ((ej >> 5) > word) break;
+    }
+    /* bytewise store: only bytes that belong to the stream and fit the buffer */
+    uint64_t limit = (total + 7) >> 3;
+    if (limit > a.out_cap_bytes) limit = a.out_cap_bytes;
+    uint8_t *o = reinterpret_cast<uint8_t *>(a.out_words);
+    for (int bq = 0; bq < 4; bq++) {
+        uint64_t bidx = word * 4 + bq;
+        if (bidx < limit) o[bidx] = (uint8_t)(v >> (24 - 8 * bq));
+    }
+}
+
+template <int JT, int B>
+cudaError_t launch_variant(const AecEncArgs &a, uint32_t smem_bytes, int num_sms, cudaStream_t st)
+{
+    auto kern = aec_encode_kernel<JT, B>;
+    static uint32_t attr_smem = 48 * 1024;      /* opt in to large dynamic shared memory once */
+    cudaError_t e;
+    if (smem_bytes > attr_smem) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        attr_smem = smem_bytes;
+    }
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TileCfg<JT>::TB, smem_bytes);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    uint64_t grid = (uint64_t)occ * (uint64_t)num_sms;
+    if (grid > a.ntiles) grid = a.ntiles;
+    if (grid == 0) return cudaSuccess;
+    kern<<<(unsigned)grid, TileCfg<JT>::TB, smem_bytes, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int JT>
+cudaError_t launch_j(const AecEncArgs &a, uint32_t smem, int sms, cudaStream_t st)
+{
+    switch (a.cfg.B) {
+    case 1: return launch_variant<JT, 1>(a, smem, sms, st);
+    case 2: return launch_variant<JT, 2>(a, smem, sms, st);
+    case 3: return launch_variant<JT, 3>(a, smem, sms, st);
+    default: return launch_variant<JT, 4>(a, smem, sms, st);
+    }
+}
+
+} // namespace
+
+uint32_t aec_encode_tile_blocks(uint32_t J)
+{
+    return (J == 8 || J == 16 || J == 32) ? 256u : 128u;
+}
+
+uint32_t aec_encode_staging_words(const AecCfg &c)
+{
+    uint32_t TB = aec_encode_tile_blocks(c.J);
+    /* every CDS is at most idl + 1 + n + J*n bits, plus RSI padding */
+    uint64_t bits = 31ull + (uint64_t)TB * (c.idl + 1ull + (uint64_t)c.J * c.n + c.n + 8ull) + 64ull;
+    return (uint32_t)(bits / 32ull + 4ull);
+}
+
+cudaError_t aec_encode_launch(const AecEncArgs &a, int num_sms, cudaStream_t st)
+{
+    uint32_t smem = a.staging_words * 4u;
+    cudaError_t e;
+    switch (a.cfg.J) {
+    case 8:  e = launch_j<8>(a, smem, num_sms, st); break;
+    case 16: e = launch_j<16>(a, smem, num_sms, st); break;
+    case 32: e = launch_j<32>(a, smem, num_sms, st); break;
+    case 64: e = launch_j<64>(a, smem, num_sms, st); break;
+    default: e = launch_j<0>(a, smem, num_sms, st); break;
+    }
+    if (e != cudaSuccess) return e;
+    unsigned nthreads = (unsigned)(a.ntiles + 1);
+    aec_encode_fixup_kernel<<<(nthreads + 255) / 256, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}

@@ -1,0 +1,293 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libaec.h entry
+points and the aec_b200.h device layer), against the CPU oracle on the same
+seeded inputs, against the committed golden vectors, and -- at sizes the oracle
+cannot reach in seconds -- through round-trip properties.
+
+Bar: byte-exact compressed streams, bit-exact decoded samples.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import libaec_b200 as L
+from cases import random_case, reference_test_patterns
+from libaec_b200 import datagen
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def P(p):
+    return L.Params(p.bits_per_sample, p.block_size, p.rsi, p.flags)
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+# ---------------------------------------------------------------- libaec.h API
+
+def test_buffer_encode_decode_random_cases():
+    """aec_buffer_encode / aec_buffer_decode vs oracle: every n in 1..32, all
+    flag sets, standard and NOT_ENFORCE block sizes, short last RSIs."""
+    for seed in range(500):
+        p, raw = random_case(seed)
+        want = po.orc_encode(p, raw, want_offsets=True)
+        got = L.buffer_encode(P(p), raw, want_offsets=True)
+        assert got["status"] == want["status"], (seed, p)
+        assert got["total_in"] == want["total_in"], (seed, p)
+        assert np.array_equal(got["out"], want["out"]), (seed, p)
+        if want["offsets"].size:
+            assert np.array_equal(got["offsets"], want["offsets"]), (seed, p)
+        B = p.bytes_per_sample
+        ns = len(raw) // B
+        for size in (ns * B, (ns // 2) * B, ns * B + 40 * B + 1):
+            ref = po.orc_decode(p, want["out"], size)
+            dec = L.buffer_decode(P(p), want["out"], size)
+            assert dec["status"] == ref["status"], (seed, p, size)
+            if ref["status"] == 0:
+                assert np.array_equal(dec["out"], ref["out"]), (seed, p, size)
+        if want["offsets"].size:
+            dec = L.buffer_decode(P(p), want["out"], ns * B, offsets=want["offsets"])
+            ref = po.orc_decode(p, want["out"], ns * B)
+            assert dec["status"] == ref["status"] and np.array_equal(dec["out"], ref["out"]), (seed, p)
+
+
+def test_pad_rsi_encode_matches_padding_build():
+    """AEC_PAD_RSI honoured (== reference built with -DENABLE_RSI_PADDING)."""
+    codec = L.DeviceCodec(encode_padding=True)
+    for seed in range(250):
+        p, raw = random_case(seed, allow_pad=True)
+        want = po.orc_encode(p, raw, pad_rsi_build=True)
+        src = np.ascontiguousarray(raw)
+        cap = L.encode_bound(P(p), src.size) + 16
+        out = np.zeros(cap, np.uint8)
+        st, n, _ = codec.encode_host(P(p), src.ctypes.data, src.size, out.ctypes.data, cap)
+        assert st == want["status"], (seed, p)
+        assert np.array_equal(out[:n], want["out"]), (seed, p)
+        # the decoder always honours the flag (decode.c:406-408)
+        B = p.bytes_per_sample
+        ns = len(raw) // B
+        dec = L.buffer_decode(P(p), want["out"], ns * B)
+        ref = po.orc_decode(p, want["out"], ns * B)
+        assert dec["status"] == ref["status"] and np.array_equal(dec["out"], ref["out"]), (seed, p)
+    codec.close()
+
+
+def test_golden_typical_rz_both_directions():
+    rz = np.fromfile(os.path.join(ROOT, "tests", "golden", "typical.rz"), dtype=np.uint8)
+    p = L.Params(16, 64, 256, L.AEC_DATA_MSB | L.AEC_DATA_PREPROCESS)
+    dec = L.buffer_decode(p, rz, 1 << 20)
+    assert dec["status"] == 0 and dec["out"].size == 1 << 20
+    assert hashlib.sha256(dec["out"].tobytes()).hexdigest() == \
+        "e6e1bf684916d765320bc1064c20c5801202e3a6c595c9caca0928e1fe6df896"
+    enc = L.buffer_encode(p, dec["out"])
+    assert enc["status"] == 0 and np.array_equal(enc["out"], rz)
+
+
+def test_committed_reference_vectors(golden):
+    for seed, row in enumerate(golden["meta"]):
+        n, J, rsi, flags, pad_build, est, tin, s0, s1, s2, d0, d1, d2 = (int(x) for x in row)
+        if pad_build:
+            continue      # covered by test_pad_rsi_encode_matches_padding_build
+        p = L.Params(n, J, rsi, flags)
+        enc = L.buffer_encode(p, golden[f"raw{seed}"])
+        assert enc["status"] == est and enc["total_in"] == tin, (seed, p)
+        assert np.array_equal(enc["out"], golden[f"enc{seed}"]), (seed, p)
+        for j, (size, dst) in enumerate(((s0, d0), (s1, d1), (s2, d2))):
+            dec = L.buffer_decode(p, golden[f"enc{seed}"], size)
+            assert dec["status"] == dst, (seed, p, size)
+            if dst == 0:
+                assert np.array_equal(dec["out"], golden[f"dec{seed}_{j}"]), (seed, p, size)
+
+
+def test_reference_option_patterns_first_id():
+    """The per-option buffers and first-ID assertion of the reference's
+    check_code_options.c (large-buffer pass) for all five flag orderings."""
+    flagsets = [0, L.AEC_DATA_PREPROCESS, L.AEC_DATA_PREPROCESS | L.AEC_DATA_SIGNED,
+                L.AEC_DATA_PREPROCESS | L.AEC_DATA_MSB,
+                L.AEC_DATA_PREPROCESS | L.AEC_DATA_MSB | L.AEC_DATA_SIGNED]
+    for flags in flagsets:
+        for n in (8, 16, 24, 32):
+            f = flags | (L.AEC_DATA_3BYTE if n == 24 else 0)
+            for J in (8, 16, 32, 64):
+                for rsi in (1, 3, 48):
+                    op = po.Params(n, J, rsi, f)
+                    if 3072 // (J * op.bytes_per_sample) < rsi:
+                        continue
+                    for name, want_id, idbits, raw in reference_test_patterns(op, 3072):
+                        enc = L.buffer_encode(P(op), raw)
+                        want = po.orc_encode(op, raw)
+                        assert enc["status"] == 0
+                        assert np.array_equal(enc["out"], want["out"]), (name, op)
+                        assert enc["out"][0] >> (8 - idbits) == want_id, (name, op)
+                        dec = L.buffer_decode(P(op), enc["out"], raw.size)
+                        ref = po.orc_decode(op, enc["out"], raw.size)
+                        assert dec["status"] == 0 and np.array_equal(dec["out"], ref["out"]), (name, op)
+
+
+def test_buffer_sizes_and_long_fs():
+    """check_buffer_sizes.c (short last block is padded, decoder returns it whole)
+    and check_long_fs.c (FS runs longer than any refill window)."""
+    p = L.Params(32, 8, 0, L.AEC_DATA_PREPROCESS)
+    buf_len = 3072
+    pattern = np.tile(np.array([0xFFFFFFFF, 0], dtype="<u4"), buf_len // 8).view(np.uint8)
+    for J in (8, 16, 32, 64):
+        q = L.Params(32, J, buf_len // (J * 4), L.AEC_DATA_PREPROCESS)
+        for ibuf_len in (buf_len, buf_len - 2 * J + 4):
+            enc = L.buffer_encode(q, pattern[:ibuf_len], out_cap=2 * buf_len)
+            assert enc["status"] == 0
+            dec = L.buffer_decode(q, enc["out"], buf_len)
+            assert dec["status"] == 0
+            assert dec["out"].size == buf_len                       # check_buffer_sizes.c:38-43
+            assert np.array_equal(dec["out"][:ibuf_len], pattern[:ibuf_len])
+    q = L.Params(16, 64, 1, L.AEC_DATA_PREPROCESS)
+    vals = np.array([0] * 32 + [65000] * 32, dtype="<u2").view(np.uint8)
+    enc = L.buffer_encode(q, vals, out_cap=512)
+    want = po.orc_encode(po.Params(16, 64, 1, po.AEC_DATA_PREPROCESS), vals)
+    assert enc["status"] == 0 and np.array_equal(enc["out"], want["out"])
+    dec = L.buffer_decode(q, enc["out"], vals.size)
+    assert dec["status"] == 0 and np.array_equal(dec["out"], vals)
+    del p
+
+
+def test_error_codes():
+    p = L.Params(32, 16, 128, L.AEC_DATA_SIGNED | L.AEC_DATA_PREPROCESS)
+    empty = L.buffer_encode(p, np.zeros(0, np.uint8))
+    assert empty["status"] == 0 and empty["out"].tolist() == [0]        # encode.c:686-695
+    raw = np.arange(4096, dtype="<u4").view(np.uint8)
+    full = L.buffer_encode(p, raw)
+    short = L.buffer_encode(p, raw, out_cap=full["out"].size - 1)
+    assert short["status"] == L.AEC_STREAM_ERROR                          # encode.c:944-945
+    assert short["out"].size == full["out"].size - 1
+    assert np.array_equal(short["out"], full["out"][:-1])
+    trunc = L.buffer_decode(p, full["out"][: full["out"].size // 2], raw.size)
+    ref = po.orc_decode(po.Params(32, 16, 128, 9), full["out"][: full["out"].size // 2], raw.size)
+    assert trunc["status"] == 0 and np.array_equal(trunc["out"], ref["out"])
+    odd = L.buffer_decode(p, full["out"], raw.size + 2)                   # decode.c:821-823
+    assert odd["status"] == L.AEC_MEM_ERROR
+
+
+def test_streaming_windows_concatenate_to_the_same_stream():
+    """AEC_NO_FLUSH streaming with arbitrary windows (the way src/aec.c calls
+    the library): the concatenation equals the whole-buffer stream."""
+    rng = np.random.default_rng(3)
+    for seed in range(60):
+        p, raw = random_case(2000 + seed, max_samples=20000)
+        want = po.orc_encode(p, raw)
+        in_chunk = int(rng.integers(1, 5000))
+        in_chunk -= in_chunk % p.bytes_per_sample
+        in_chunk = max(in_chunk, p.bytes_per_sample)
+        out_chunk = int(rng.integers(1, 4000))
+        enc = L.Encoder(P(p))
+        assert enc.status == 0
+        whole_samples = (len(raw) // p.bytes_per_sample) * p.bytes_per_sample
+        got = enc.run(raw[:whole_samples], in_chunk, out_chunk, want["out"].size + 64)
+        assert enc.close() == 0, (seed, p)
+        assert np.array_equal(got, want["out"]), (seed, p, in_chunk, out_chunk)
+        # and back, with different windows
+        ns = whole_samples
+        dec = L.Decoder(P(p))
+        in_chunk = int(rng.integers(1, 3000))
+        out_chunk = max(p.bytes_per_sample, int(rng.integers(1, 6000)) // p.bytes_per_sample * p.bytes_per_sample)
+        back = dec.run(want["out"], in_chunk, out_chunk, ns, flush_at_end=True)
+        dec.close()
+        ref = po.orc_decode(p, want["out"], ns)
+        assert np.array_equal(back, ref["out"]), (seed, p, in_chunk, out_chunk)
+
+
+def test_sz_shim():
+    rng = np.random.default_rng(11)
+    for bpp, ppb, pps, mask in [(8, 32, 4096, 16 | 32 | 128 | 1), (8, 16, 1000, 32 | 128),
+                                (16, 8, 200, 16 | 32), (32, 8, 1024, 16 | 32 | 128),
+                                (64, 8, 1024, 16 | 32 | 128), (12, 10, 77, 32), (24, 32, 300, 16)]:
+        nbytes = int(rng.integers(30000, 200000))
+        px = 4 if bpp > 16 else (2 if bpp > 8 else 1)
+        if bpp in (32, 64):
+            src = np.cumsum(rng.integers(-2, 3, size=nbytes)).astype(np.uint8)
+            src = src[: (nbytes // (bpp // 8)) * (bpp // 8)]
+        else:
+            vals = (np.cumsum(rng.integers(-3, 4, size=nbytes // px)) + (1 << (bpp - 1))) & ((1 << bpp) - 1)
+            dt = np.dtype({1: np.uint8, 2: np.uint16, 4: np.uint32}[px])
+            if mask & 16:
+                dt = dt.newbyteorder(">")
+            src = vals.astype(dt).view(np.uint8)
+        want = po.orc_sz_compress(src, src.size * 2 + 1000, mask, bpp, ppb, pps)
+        got = L.sz_compress(src, src.size * 2 + 1000, mask, bpp, ppb, pps)
+        assert got["status"] == want["status"] == 0
+        assert np.array_equal(got["out"], want["out"]), (bpp, ppb, pps)
+        back = L.sz_decompress(got["out"], src.size, mask, bpp, ppb, pps)
+        ref = po.orc_sz_decompress(got["out"], src.size, mask, bpp, ppb, pps)
+        assert back["status"] == 0 and np.array_equal(back["out"], ref["out"]), (bpp, ppb, pps)
+        assert np.array_equal(back["out"], src)
+    small = L.sz_compress(np.arange(100000, dtype=np.uint8), 10, 32 | 128, 8, 16, 256)
+    assert small["status"] == 2                                           # SZ_OUTBUFF_FULL
+
+
+# ---------------------------------------------------------------- device ABI
+
+def _device_roundtrip(torch, codec, name, nsamples, check_oracle):
+    p, _ = datagen.CONFIGS[name]
+    raw = datagen.generate(name, nsamples)
+    d_in = torch.from_numpy(raw).cuda()
+    cap = (L.encode_bound(p, raw.size) + 64 + 3) // 4 * 4
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    R = p.rsi * p.block_size
+    nrsi = (nsamples + R - 1) // R
+    d_offs = torch.empty(nrsi, dtype=torch.int64, device="cuda")
+    assert codec.encode_enqueue(p, d_in, raw.size, d_out, d_offs) == 0
+    st, bits, _ = codec.encode_finish()
+    assert st == 0
+    nbytes = (bits + 7) // 8
+    comp = d_out[:nbytes].cpu().numpy()
+    if check_oracle:
+        want = po.orc_encode(po.Params(p.bits_per_sample, p.block_size, p.rsi, p.flags), raw, want_offsets=True)
+        assert np.array_equal(comp, want["out"]), name
+        assert np.array_equal(d_offs.cpu().numpy().astype(np.uint64), want["offsets"]), name
+    d_back = torch.empty(raw.size + 16, dtype=torch.uint8, device="cuda")
+    assert codec.decode_enqueue(p, d_out, nbytes, d_offs, nrsi, d_back, raw.size) == 0
+    st, written = codec.decode_finish()
+    assert st == 0 and written == raw.size
+    back = d_back[:raw.size].cpu().numpy()
+    # decode == input for unsigned / full-width signed data (sign extension is a no-op here)
+    assert np.array_equal(back, raw), name
+    # the sequential boundary scan finds the same index
+    if nrsi <= 4096:
+        d_offs2 = torch.zeros(nrsi, dtype=torch.int64, device="cuda")
+        st, found = codec.scan_offsets(p, d_out, nbytes, d_offs2, nrsi)
+        assert st == 0 and found == nrsi
+        assert torch.equal(d_offs, d_offs2), name
+    return raw.size / nbytes
+
+
+@pytest.mark.parametrize("name", list(datagen.CONFIGS))
+def test_device_path_configs_vs_oracle(torch_cuda, name):
+    """BASELINE.json configs at a size the oracle finishes in seconds,
+    device-resident buffers, byte-exact stream + index, exact round trip."""
+    codec = L.DeviceCodec()
+    p, _ = datagen.CONFIGS[name]
+    ns = (8 << 20) // p.bytes_per_sample
+    ns -= ns % 7          # make the last RSI short
+    _device_roundtrip(torch_cuda, codec, name, ns, True)
+    codec.close()
+
+
+@pytest.mark.parametrize("name,mib", [("c1", 256), ("c2", 256), ("c4", 192), ("c5_noise", 128)])
+def test_device_path_full_size_round_trip(torch_cuda, name, mib):
+    """Full BASELINE sizes through size-independent properties: encode ->
+    decode round trip is exact, ratio is the one the CPU reference gets, and
+    stream = concatenation property (first 4 MiB prefix equals the oracle's
+    stream of that prefix up to its last whole byte)."""
+    codec = L.DeviceCodec()
+    p, _ = datagen.CONFIGS[name]
+    ns = (mib << 20) // p.bytes_per_sample
+    ratio = _device_roundtrip(torch_cuda, codec, name, ns, False)
+    expect = {"c1": 3.48, "c2": 11.25, "c4": 2.18, "c5_noise": 0.99}[name]
+    assert abs(ratio - expect) < 0.05 * expect, (name, ratio)
+    codec.close()
