@@ -102,7 +102,7 @@ def load_library() -> C.CDLL:
         path = os.path.join(LIBDIR, "libaec.so.0")
         if not os.path.exists(path):
             raise RuntimeError(f"{path} missing: run `python -m libaec_b200.build` (needs nvcc)")
-        lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        lib = C.CDLL(path)
         for name in LIBAEC_SYMBOLS + DEVICE_SYMBOLS:
             getattr(lib, name).restype = C.c_int
         lib.aecb200_last_error.restype = C.c_char_p
