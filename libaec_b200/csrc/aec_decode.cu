@@ -128,8 +128,8 @@ aec_decode_kernel(const AecDecArgs a)
     if (have) {
         if (a.rsi_count) a.rsi_count[r] = delivered;
         if (delivered < limit)
-            atomicMin(reinterpret_cast<unsigned long long *>(&a.result[0]),
-                      (unsigned long long)(r * (uint64_t)c.R + delivered));
+            atomicMax(reinterpret_cast<unsigned long long *>(&a.result[0]),
+                      ~(unsigned long long)(r * (uint64_t)c.R + delivered));
         if (st.status == DEC_ERROR)
             atomicOr(reinterpret_cast<unsigned long long *>(&a.result[1]), 1ull);
     }

@@ -62,6 +62,7 @@ struct aecb200_ctx {
     bool enc_pending = false;
     bool dec_pending = false;
     uint64_t dec_out_samples = 0;
+    uint64_t dec_expect = 0;
     uint32_t dec_B = 1;
 };
 
@@ -284,12 +285,12 @@ int aecb200_decode_device(aecb200_ctx *ctx, const aecb200_params *p,
     ctx->dec_B = c.B;
     CK(ctx->misc.ensure(256), "cudaMalloc(misc)");
     uint64_t *res = (uint64_t *)((uint8_t *)ctx->misc.p + 128);
-    /* delivered = min(out_samples, RSIs available * R) unless a lane reports less */
-    uint64_t init[2];
+    /* delivered = min(out_samples, RSIs available * R) unless a lane reports less:
+     * lanes that fall short atomicMax the complement of their position into
+     * res[0] (zero = nobody fell short), flags go to res[1] */
     uint64_t avail = need_rsi * (uint64_t)c.R;
-    init[0] = out_samples < avail ? out_samples : avail;
-    init[1] = 0;
-    CK(cudaMemcpyAsync(res, init, 16, cudaMemcpyHostToDevice, ctx->stream), "memcpy(init)");
+    ctx->dec_expect = out_samples < avail ? out_samples : avail;
+    CK(cudaMemsetAsync(res, 0, 16, ctx->stream), "memset(result)");
     if (need_rsi) {
         AecDecArgs a;
         memset(&a, 0, sizeof a);
@@ -315,7 +316,9 @@ int aecb200_decode_finish(aecb200_ctx *ctx, size_t *out_written)
     if (!ctx || !ctx->dec_pending) return AEC_CONF_ERROR;
     CK(cudaStreamSynchronize(ctx->stream), "decode sync");
     ctx->dec_pending = false;
-    if (out_written) *out_written = (size_t)(ctx->h_res[4] * ctx->dec_B);
+    uint64_t got = ctx->dec_expect;
+    if (ctx->h_res[4] != 0 && ~ctx->h_res[4] < got) got = ~ctx->h_res[4];
+    if (out_written) *out_written = (size_t)(got * ctx->dec_B);
     if (ctx->h_res[5] & 1ull) return AEC_DATA_ERROR;
     return AEC_OK;
 }
