@@ -225,6 +225,13 @@ def run_ours(args):
         dist.all_gather(allb, t)
         shard_bits = [int(x[0].item()) for x in allb]
 
+    sharded = None
+    if world > 1:
+        # N > 1: the full shard protocol (independent encode, 24-byte all_gather, k repair,
+        # placement at the global bit phase, boundary-word exchange) is inside every step
+        from libaec_b200.parallel import ShardedCodec
+        sharded = ShardedCodec(p, rank, world, local, stream=stream.cuda_stream)
+
     def step():
         codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs)
         codec.decode_enqueue(p, d_comp, comp_bytes, d_offs, nrsi, d_back, raw.size)
@@ -232,6 +239,8 @@ def run_ours(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     for _ in range(args.warmup):
         step()
+        if sharded is not None:
+            sharded.encode(d_raw, raw.size)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -241,6 +250,7 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.25)
     launches0 = codec.launches
+    sh_l0 = sharded.codec.launches if sharded is not None else 0
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     enc_ms, dec_ms = [], []
@@ -249,9 +259,14 @@ def run_ours(args):
     for i in range(args.steps):
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record()
-        codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs)
-        b.record()
-        codec.decode_enqueue(p, d_comp, comp_bytes, d_offs, nrsi, d_back, raw.size)
+        if sharded is not None:
+            sharded.encode(d_raw, raw.size)
+            b.record()
+            sharded.codec.decode_enqueue(p, sharded.local, comp_bytes, sharded.offsets, nrsi, d_back, raw.size)
+        else:
+            codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs)
+            b.record()
+            codec.decode_enqueue(p, d_comp, comp_bytes, d_offs, nrsi, d_back, raw.size)
         c.record()
         marks.append((a, b, c))
     t_end.record()
@@ -259,7 +274,7 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    launches = codec.launches - launches0
+    launches = codec.launches - launches0 + (sharded.codec.launches - sh_l0 if sharded is not None else 0)
     # keep the sampler alive long enough to see the load
     if rank == 0:
         t_busy = time.time()

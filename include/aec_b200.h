@@ -88,6 +88,23 @@ int aecb200_encode_device(aecb200_ctx *ctx, const aecb200_params *p,
  * `word` is not filled).  AEC_STREAM_ERROR when the stream did not fit out_cap. */
 int aecb200_encode_finish(aecb200_ctx *ctx, aecb200_carry *end);
 
+/* ---- multi-GPU shards: a shard is a contiguous range of whole RSIs
+ * coded on its own GPU from carry {0,0,0}.  In shard mode every encode also
+ * reports the shard's k clamp pair [klo,khi] (its outgoing k is
+ * clamp(k_in, klo, khi), independent of the seed) and a tile index after
+ * which k no longer depends on k_in.  After the ranks have exchanged
+ * (bits, klo, khi) a rank whose true k_in differs from 0 re-codes its first
+ * first_const_tile+1 tiles (aecb200_ctx_set_tile_limit + aecb200_encode_device
+ * with the true k in the carry), then moves its stream to its bit offset in the
+ * global stream with aecb200_place_bits_device. */
+void aecb200_ctx_set_shard_mode(aecb200_ctx *ctx, int on);
+int  aecb200_encode_shard_info(aecb200_ctx *ctx, uint32_t *klo, uint32_t *khi, uint64_t *first_const_tile);
+void aecb200_ctx_set_tile_limit(aecb200_ctx *ctx, uint64_t ntiles);
+/* d_dst[dst_bit ..) = d_src[0 .. nbits) (bit 0 = MSB of byte 0); whole destination
+ * words are written, bits outside the range are zero.  Asynchronous. */
+int  aecb200_place_bits_device(aecb200_ctx *ctx, const void *d_src, uint64_t nbits,
+                               void *d_dst, size_t dst_cap, uint64_t dst_bit);
+
 /* Enqueue the decode of out_bytes/bytes_per_sample samples from the stream at
  * d_in using the RSI start offsets d_rsi_offsets[0..nrsi).  Asynchronous. */
 int aecb200_decode_device(aecb200_ctx *ctx, const aecb200_params *p,

@@ -91,7 +91,8 @@ DEVICE_SYMBOLS = ["aecb200_device_count", "aecb200_ctx_create", "aecb200_ctx_des
                   "aecb200_ctx_launches", "aecb200_encode_bound", "aecb200_encode_device",
                   "aecb200_encode_finish", "aecb200_decode_device", "aecb200_decode_finish",
                   "aecb200_scan_offsets_device", "aecb200_encode_host", "aecb200_encode_host_piece",
-                  "aecb200_decode_host", "aecb200_decode_host_resume"]
+                  "aecb200_decode_host", "aecb200_decode_host_resume", "aecb200_ctx_set_shard_mode",
+                  "aecb200_encode_shard_info", "aecb200_ctx_set_tile_limit", "aecb200_place_bits_device"]
 SZ_SYMBOLS = ["SZ_BufftoBuffCompress", "SZ_BufftoBuffDecompress", "SZ_encoder_enabled", "SZ_Compress"]
 
 
@@ -110,6 +111,8 @@ def load_library() -> C.CDLL:
         lib.aecb200_encode_bound.restype = C.c_size_t
         lib.aecb200_ctx_destroy.restype = None
         lib.aecb200_ctx_set_encode_padding.restype = None
+        lib.aecb200_ctx_set_shard_mode.restype = None
+        lib.aecb200_ctx_set_tile_limit.restype = None
         _lib = lib
     return _lib
 
@@ -360,6 +363,24 @@ class DeviceCodec:
         end = Carry()
         st = self._check(self.lib.aecb200_encode_finish(self.ctx, C.byref(end)), "aecb200_encode_finish")
         return st, int(end.bits), int(end.k)
+
+    # ---- multi-GPU shard helpers (aec_b200.h "multi-GPU shards") ----
+    def set_shard_mode(self, on: bool = True):
+        self.lib.aecb200_ctx_set_shard_mode(self.ctx, C.c_int(int(on)))
+
+    def shard_info(self):
+        lo, hi, fc = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+        self.lib.aecb200_encode_shard_info(self.ctx, C.byref(lo), C.byref(hi), C.byref(fc))
+        return int(lo.value), int(hi.value), int(fc.value)
+
+    def set_tile_limit(self, ntiles: int):
+        self.lib.aecb200_ctx_set_tile_limit(self.ctx, C.c_uint64(ntiles))
+
+    def place_bits(self, d_src, nbits: int, d_dst, dst_bit: int):
+        st = self.lib.aecb200_place_bits_device(
+            self.ctx, C.c_void_p(d_src.data_ptr()), C.c_uint64(nbits), C.c_void_p(d_dst.data_ptr()),
+            C.c_size_t(d_dst.numel() * d_dst.element_size()), C.c_uint64(dst_bit))
+        return self._check(st, "aecb200_place_bits_device")
 
     def decode_enqueue(self, p: Params, d_in, in_bytes: int, d_offsets, nrsi: int, d_out, out_bytes: int):
         prm = _Params(p.bits_per_sample, p.block_size, p.rsi, p.flags)

@@ -18,7 +18,8 @@ struct AecEncArgs {
     uint64_t nrsi;              /* RSIs to code (last may be short) */
     uint32_t last_nblk;         /* coded blocks of the last RSI */
     uint32_t RP;                /* block slots per RSI (power of two <= TB, or multiple of TB) */
-    uint64_t ntiles;
+    uint64_t ntiles;            /* tiles the main kernel codes (a prefix of the shard when repairing) */
+    uint64_t ntiles_total;      /* tiles of the whole launch geometry (fix-up covers all of them) */
     uint32_t aligned;           /* `in` is 16-byte aligned */
     uint32_t staging_words;     /* dynamic shared memory in words */
     uint32_t *out_words;        /* output stream, 4-byte aligned, device */
@@ -32,8 +33,9 @@ struct AecEncArgs {
     uint32_t *ticket;           /* zeroed */
     uint32_t *head_c, *tail_c;  /* [ntiles] partial boundary words */
     uint64_t *tile_end;         /* [ntiles] absolute end bit of each tile */
+    uint32_t *tile_kagg;        /* [ntiles] clamp pair (lo | hi<<8) of each tile, independent of the seed */
     uint64_t *rsi_offsets;      /* optional [nrsi] absolute start bit of each RSI */
-    uint64_t *result;           /* [0] end bit, [1] k after the last block */
+    uint64_t *result;           /* [0] end bit, [1] k after the last block, [2..4] shard summary (lo, hi, first constant tile) */
 };
 
 /* Arguments of one decode launch. */
@@ -53,6 +55,10 @@ struct AecDecArgs {
 uint32_t aec_encode_tile_blocks(uint32_t J);
 uint32_t aec_encode_staging_words(const AecCfg &c);
 cudaError_t aec_encode_launch(const AecEncArgs &a, int num_sms, cudaStream_t st);
+/* result[2..4] = clamp pair of the whole launch and the first tile after which k no longer depends on the seed */
+cudaError_t aec_encode_summary_launch(const AecEncArgs &a, cudaStream_t st);
+/* copy nbits bits from src (bit 0 = MSB of word 0) to dst starting at bit dst_bit; dst words are private to the caller */
+cudaError_t aec_place_bits_launch(const uint32_t *src, uint64_t nbits, uint32_t *dst, uint64_t dst_bit, uint64_t dst_cap_words, cudaStream_t st);
 
 cudaError_t aec_decode_launch(const AecDecArgs &a, int num_sms, cudaStream_t st);
 /* Sequential RSI-boundary scan for streams without an offset index:

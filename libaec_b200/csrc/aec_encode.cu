@@ -358,7 +358,8 @@ aec_encode_kernel(const AecEncArgs a)
                 st_volatile_u64(&a.desc[tile], desc_pack_prefix(end, kout));
                 s_base = base; s_kin = kin;
                 a.tile_end[tile] = end;
-                if (tile + 1 == a.ntiles) { a.result[0] = end; a.result[1] = kout; }
+                a.tile_kagg[tile] = ktile;
+                if (tile + 1 == a.ntiles_total) { a.result[0] = end; a.result[1] = kout; }
             }
         }
         __syncthreads();
@@ -410,8 +411,8 @@ aec_encode_kernel(const AecEncArgs a)
 __global__ void aec_encode_fixup_kernel(const AecEncArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - 1;   /* -1 = the seed */
-    if (i >= (int64_t)a.ntiles) return;
-    const uint64_t total = a.tile_end[a.ntiles - 1];
+    if (i >= (int64_t)a.ntiles_total) return;
+    const uint64_t total = a.tile_end[a.ntiles_total - 1];
     uint64_t bi = (i <= 0) ? a.seed_bits : a.tile_end[i - 1];
     uint64_t ei = (i < 0) ? a.seed_bits : a.tile_end[i];
     uint32_t v;
@@ -425,7 +426,7 @@ __global__ void aec_encode_fixup_kernel(const AecEncArgs a)
         v = a.tail_c[i];
     }
     const uint64_t word = ei >> 5;
-    for (int64_t j = i + 1; j < (int64_t)a.ntiles; j++) {
+    for (int64_t j = i + 1; j < (int64_t)a.ntiles_total; j++) {
         uint64_t ej = a.tile_end[j];
         v |= a.head_c[j];
         if ((ej >> 5) > word) break;
@@ -437,6 +438,61 @@ __global__ void aec_encode_fixup_kernel(const AecEncArgs a)
     for (int bq = 0; bq < 4; bq++) {
         uint64_t bidx = word * 4 + bq;
         if (bidx < limit) o[bidx] = (uint8_t)(v >> (24 - 8 * bq));
+    }
+}
+
+/* Clamp pair of the whole launch (ordered composition of the per-tile pairs)
+ * and a tile index after which k no longer depends on the incoming k: what a
+ * multi-GPU shard publishes so its successors can chain k. */
+__global__ void aec_encode_summary_kernel(const AecEncArgs a)
+{
+    const uint32_t lane = threadIdx.x;
+    const uint64_t n = a.ntiles_total;
+    const uint64_t per = (n + 31) / 32;
+    uint64_t b0 = lane * per, b1 = b0 + per;
+    if (b0 > n) b0 = n;
+    if (b1 > n) b1 = n;
+    uint32_t acc = aec_kpair(0, a.cfg.kmax);
+    unsigned long long firstc = ~0ull;
+    for (uint64_t t = b0; t < b1; t++) {
+        acc = aec_kcompose(acc, a.tile_kagg[t]);
+        if (firstc == ~0ull && (acc & 0xFFu) == (acc >> 8)) firstc = t;
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t o = __shfl_up_sync(FULL, acc, off);       /* lower lane = earlier tiles */
+        if (lane >= (uint32_t)off) acc = aec_kcompose(o, acc);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        unsigned long long o = __shfl_xor_sync(FULL, firstc, off);
+        if (o < firstc) firstc = o;
+    }
+    if (lane == 31) {
+        a.result[2] = acc & 0xFFu;
+        a.result[3] = acc >> 8;
+        a.result[4] = (firstc == ~0ull) ? n : firstc;
+    }
+}
+
+/* dst[dst_bit ..) = src[0 .. nbits): one thread per destination word. */
+__global__ void aec_place_bits_kernel(const uint32_t *src, uint64_t nbits, uint32_t *dst, uint64_t dst_bit,
+                                      uint64_t dst_cap_words)
+{
+    const uint64_t w0 = dst_bit >> 5;
+    const uint32_t sh = (uint32_t)(dst_bit & 31u);
+    const uint64_t nw = ((dst_bit + nbits + 31) >> 5) - w0;
+    const uint64_t src_words = (nbits + 31) >> 5;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (uint64_t)gridDim.x * blockDim.x) {
+        /* destination word i holds source bits [32*i - sh, 32*i - sh + 32) */
+        uint32_t hi = (i >= 1 && i - 1 < src_words) ? __byte_perm(src[i - 1], 0, 0x0123) : 0u;
+        uint32_t lo = (i < src_words) ? __byte_perm(src[i], 0, 0x0123) : 0u;
+        uint32_t v = sh ? ((hi << (32u - sh)) | (lo >> sh)) : lo;
+        /* clear bits past the end of the stream in the last word */
+        uint64_t endbit = dst_bit + nbits;
+        if (w0 + i == (endbit >> 5) && (endbit & 31u)) v &= ~(0xFFFFFFFFu >> (endbit & 31u));
+        if (i == 0 && sh) v &= (0xFFFFFFFFu >> sh);
+        if (w0 + i < dst_cap_words) dst[w0 + i] = __byte_perm(v, 0, 0x0123);
     }
 }
 
@@ -488,6 +544,22 @@ uint32_t aec_encode_staging_words(const AecCfg &c)
     return (uint32_t)(bits / 32ull + 4ull);
 }
 
+cudaError_t aec_encode_summary_launch(const AecEncArgs &a, cudaStream_t st)
+{
+    aec_encode_summary_kernel<<<1, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t aec_place_bits_launch(const uint32_t *src, uint64_t nbits, uint32_t *dst, uint64_t dst_bit,
+                                  uint64_t dst_cap_words, cudaStream_t st)
+{
+    uint64_t nw = ((dst_bit + nbits + 31) >> 5) - (dst_bit >> 5);
+    if (nw == 0) return cudaSuccess;
+    unsigned grid = (unsigned)((nw + 255) / 256 > 148 * 16 ? 148 * 16 : (nw + 255) / 256);
+    aec_place_bits_kernel<<<grid, 256, 0, st>>>(src, nbits, dst, dst_bit, dst_cap_words);
+    return cudaGetLastError();
+}
+
 cudaError_t aec_encode_launch(const AecEncArgs &a, int num_sms, cudaStream_t st)
 {
     uint32_t smem = a.staging_words * 4u;
@@ -500,7 +572,7 @@ cudaError_t aec_encode_launch(const AecEncArgs &a, int num_sms, cudaStream_t st)
     default: e = launch_j<0>(a, smem, num_sms, st); break;
     }
     if (e != cudaSuccess) return e;
-    unsigned nthreads = (unsigned)(a.ntiles + 1);
+    unsigned nthreads = (unsigned)(a.ntiles_total + 1);
     aec_encode_fixup_kernel<<<(nthreads + 255) / 256, 256, 0, st>>>(a);
     return cudaGetLastError();
 }

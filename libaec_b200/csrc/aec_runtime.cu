@@ -54,7 +54,9 @@ struct aecb200_ctx {
     uint64_t launches = 0;
     char err[256] = {0};
 
-    DevBuf desc, headc, tailc, tile_end, misc, in_stage, out_stage, offs, rsi_count;
+    DevBuf desc, headc, tailc, tile_end, tile_kagg, misc, in_stage, out_stage, offs, rsi_count;
+    uint64_t tile_limit = 0;             /* next encode codes only this many leading tiles (k repair) */
+    bool want_summary = false;
     uint64_t *h_res = nullptr;           /* pinned: [0..3] encode result, [4..7] decode result */
 
     /* bookkeeping of the last enqueued operation */
@@ -152,6 +154,7 @@ void aecb200_ctx_destroy(aecb200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->tile_kagg.release();
     ctx->desc.release(); ctx->headc.release(); ctx->tailc.release(); ctx->tile_end.release();
     ctx->misc.release(); ctx->in_stage.release(); ctx->out_stage.release(); ctx->offs.release();
     ctx->rsi_count.release();
@@ -210,15 +213,14 @@ int aecb200_encode_device(aecb200_ctx *ctx, const aecb200_params *p,
     if (g.nsamples == 0) {
         /* nothing to code: the result is the carry itself */
         ctx->h_res[0] = carry->bits; ctx->h_res[1] = carry->k;
-        ctx->h_res[2] = 1;   /* marker: no launch */
         return AEC_OK;
     }
-    ctx->h_res[2] = 0;
 
     CK(ctx->desc.ensure(g.ntiles * 8), "cudaMalloc(desc)");
     CK(ctx->headc.ensure(g.ntiles * 4), "cudaMalloc(head)");
     CK(ctx->tailc.ensure(g.ntiles * 4), "cudaMalloc(tail)");
     CK(ctx->tile_end.ensure(g.ntiles * 8), "cudaMalloc(tile_end)");
+    CK(ctx->tile_kagg.ensure(g.ntiles * 4), "cudaMalloc(tile_kagg)");
     CK(ctx->misc.ensure(256), "cudaMalloc(misc)");
     CK(cudaMemsetAsync(ctx->desc.p, 0, g.ntiles * 8, ctx->stream), "memset(desc)");
     CK(cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream), "memset(misc)");
@@ -231,7 +233,8 @@ int aecb200_encode_device(aecb200_ctx *ctx, const aecb200_params *p,
     a.nrsi = g.nrsi;
     a.last_nblk = g.last_nblk;
     a.RP = g.RP;
-    a.ntiles = g.ntiles;
+    a.ntiles = (ctx->tile_limit && ctx->tile_limit < g.ntiles) ? ctx->tile_limit : g.ntiles;
+    a.ntiles_total = g.ntiles;
     a.aligned = (((uintptr_t)d_in & 15u) == 0) ? 1u : 0u;
     a.staging_words = aec_encode_staging_words(c);
     a.out_words = (uint32_t *)d_out;
@@ -246,10 +249,18 @@ int aecb200_encode_device(aecb200_ctx *ctx, const aecb200_params *p,
     a.head_c = (uint32_t *)ctx->headc.p;
     a.tail_c = (uint32_t *)ctx->tailc.p;
     a.tile_end = (uint64_t *)ctx->tile_end.p;
+    a.tile_kagg = (uint32_t *)ctx->tile_kagg.p;
     a.rsi_offsets = d_rsi_offsets;
+    const bool repair = a.ntiles < a.ntiles_total;
     CK(aec_encode_launch(a, ctx->num_sms, ctx->stream), "encode launch");
     ctx->launches += 2;
-    CK(cudaMemcpyAsync(ctx->h_res, a.result, 16, cudaMemcpyDeviceToHost, ctx->stream), "memcpy(result)");
+    if (ctx->want_summary && !repair) {
+        CK(aec_encode_summary_launch(a, ctx->stream), "summary launch");
+        ctx->launches += 1;
+    }
+    ctx->tile_limit = 0;
+    if (!repair)
+        CK(cudaMemcpyAsync(ctx->h_res, a.result, 40, cudaMemcpyDeviceToHost, ctx->stream), "memcpy(result)");
     return AEC_OK;
 }
 
@@ -260,6 +271,31 @@ int aecb200_encode_finish(aecb200_ctx *ctx, aecb200_carry *end)
     ctx->enc_pending = false;
     if (end) { end->bits = ctx->h_res[0]; end->k = (uint32_t)ctx->h_res[1]; end->word = 0; }
     if (ctx->h_res[0] > ctx->enc_out_cap_bits) return AEC_STREAM_ERROR;
+    return AEC_OK;
+}
+
+void aecb200_ctx_set_shard_mode(aecb200_ctx *ctx, int on) { if (ctx) ctx->want_summary = on != 0; }
+
+int aecb200_encode_shard_info(aecb200_ctx *ctx, uint32_t *klo, uint32_t *khi, uint64_t *first_const_tile)
+{
+    if (!ctx) return AEC_CONF_ERROR;
+    if (klo) *klo = (uint32_t)ctx->h_res[2];
+    if (khi) *khi = (uint32_t)ctx->h_res[3];
+    if (first_const_tile) *first_const_tile = ctx->h_res[4];
+    return AEC_OK;
+}
+
+void aecb200_ctx_set_tile_limit(aecb200_ctx *ctx, uint64_t ntiles) { if (ctx) ctx->tile_limit = ntiles; }
+
+int aecb200_place_bits_device(aecb200_ctx *ctx, const void *d_src, uint64_t nbits,
+                              void *d_dst, size_t dst_cap, uint64_t dst_bit)
+{
+    if (!ctx) return AEC_CONF_ERROR;
+    if ((((uintptr_t)d_src) & 3u) || (((uintptr_t)d_dst) & 3u)) return AEC_CONF_ERROR;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(aec_place_bits_launch((const uint32_t *)d_src, nbits, (uint32_t *)d_dst, dst_bit, dst_cap / 4, ctx->stream),
+       "place launch");
+    ctx->launches += 1;
     return AEC_OK;
 }
 

@@ -1,0 +1,182 @@
+"""Multi-GPU sharding of one AEC stream.
+
+One process per GPU.  The input is split into contiguous ranges of whole RSIs;
+the predictor and the zero-run logic reset at every RSI, so the only things
+that cross a shard boundary are the bit position and the split position k of
+the previous block.  Protocol per encode:
+
+  1. every rank codes its shard from carry (0 bits, k = 0)      [CUDA, no comm]
+  2. all_gather of (bits, klo, khi) per shard -- 24 bytes per rank  [NCCL]
+  3. a rank whose true incoming k is not 0 re-codes its leading tiles
+     (the lengths do not depend on k, only the ids / split bits do)  [CUDA]
+  4. every rank moves its stream to its bit offset in the global stream
+     (aecb200_place_bits_device, a funnel-shift copy)               [CUDA]
+  5. all_gather of each segment's first/last word; the word shared by two
+     shards is OR-merged into the later shard                       [NCCL]
+
+After step 5 rank r holds exactly the bytes [byte_lo(r), byte_hi(r)) of the
+single stream; the concatenation over ranks is byte-identical to the stream a
+single GPU (or the CPU reference) produces for the whole input.  Decode needs
+no exchange at all: each rank decodes its RSIs from its own segment.
+
+The pure functions at the top carry the host-side logic and are what the gloo
+CPU tests exercise; `ShardedCodec` wires them to the device layer.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+def shard_range(total_samples: int, rsi_samples: int, rank: int, world: int):
+    """Contiguous RSI-aligned shard [start, start + count) of `rank`."""
+    nrsi = (total_samples + rsi_samples - 1) // rsi_samples
+    per = (nrsi + world - 1) // world
+    s = min(rank * per, nrsi) * rsi_samples
+    e = min(min((rank + 1) * per, nrsi) * rsi_samples, total_samples)
+    return s, max(e - s, 0)
+
+
+def clamp(v: int, lo: int, hi: int) -> int:
+    return lo if v < lo else (hi if v > hi else v)
+
+
+@dataclass
+class ShardPlan:
+    bit_offset: int      # where this shard's first bit sits in the global stream
+    k_in: int            # k of the last coded block before this shard
+    end_bit: int         # bit_offset + bits
+    word_lo: int         # first 32-bit word of the global stream this rank owns
+    word_hi: int         # one past the last word it owns
+    total_bits: int
+
+
+def plan_shards(infos, seed_k: int = 0):
+    """infos: per rank (bits, klo, khi).  Exclusive scan of the bit lengths and
+    the clamp chain of k (k_out = clamp(k_in, klo, khi))."""
+    plans = []
+    off, k = 0, seed_k
+    total = sum(int(b) for b, _, _ in infos)
+    for r, (bits, lo, hi) in enumerate(infos):
+        bits, lo, hi = int(bits), int(lo), int(hi)
+        end = off + bits
+        last = r == len(infos) - 1
+        plans.append(ShardPlan(off, k, end, off >> 5, ((end + 31) >> 5) if last else (end >> 5), total))
+        k = clamp(k, lo, hi)
+        off = end
+    return plans
+
+
+def merge_boundary(first_word: int, prev_last_word: int, plan: ShardPlan) -> int:
+    """The word that holds a shard boundary belongs to the later shard: OR the
+    predecessor's tail bits into this shard's first word."""
+    if plan.bit_offset & 31:
+        return first_word | prev_last_word
+    return first_word
+
+
+def place_bits_host(stream: np.ndarray, nbits: int, dst_bit: int) -> np.ndarray:
+    """numpy model of aecb200_place_bits_device (CPU tests): returns the bytes of
+    the 32-bit words [dst_bit >> 5, (dst_bit + nbits + 31) >> 5) with the
+    stream's bits at their place and zeros elsewhere."""
+    bits = np.unpackbits(stream)[:nbits]
+    w0 = dst_bit >> 5
+    nw = ((dst_bit + nbits + 31) >> 5) - w0
+    out = np.zeros(nw * 32, dtype=np.uint8)
+    s = dst_bit - (w0 << 5)
+    out[s:s + nbits] = bits
+    return np.packbits(out)
+
+
+class ShardedCodec:
+    """Device-side sharded encoder/decoder for one rank."""
+
+    def __init__(self, params, rank: int, world: int, device: int, group=None, stream=None):
+        import torch
+        from .api import DeviceCodec, encode_bound
+        self.torch = torch
+        self.p = params
+        self.rank, self.world = rank, world
+        self.group = group
+        self.codec = DeviceCodec(device=device, stream=stream)
+        self.codec.set_shard_mode(True)
+        self._bound = encode_bound
+        self.local = None
+        self.placed = None
+        self.offsets = None
+        self.plan = None
+
+    def close(self):
+        self.codec.close()
+
+    def _ensure(self, nbytes: int, nrsi: int):
+        torch = self.torch
+        cap = (self._bound(self.p, nbytes) + 64 + 3) // 4 * 4
+        if self.local is None or self.local.numel() < cap:
+            self.local = torch.empty(cap, dtype=torch.uint8, device="cuda")
+            self.placed = torch.empty(cap + 8, dtype=torch.uint8, device="cuda")
+        if self.offsets is None or self.offsets.numel() < nrsi:
+            self.offsets = torch.empty(max(nrsi, 1), dtype=torch.int64, device="cuda")
+
+    def encode(self, d_raw, nbytes: int):
+        """Steps 1-5 for this rank's shard `d_raw` (uint8 CUDA tensor).  Returns
+        the ShardPlan; self.placed then holds this rank's words of the global
+        stream starting at word plan.word_lo."""
+        torch = self.torch
+        import torch.distributed as dist
+        from .api import Carry
+        p = self.p
+        R = p.rsi * p.block_size
+        nrsi = (nbytes // p.bytes_per_sample + R - 1) // R
+        self._ensure(nbytes, nrsi)
+        # 1. independent shard encode
+        self.codec.encode_enqueue(p, d_raw, nbytes, self.local, self.offsets)
+        st, bits, kend = self.codec.encode_finish()
+        assert st == 0
+        klo, khi, first_const = self.codec.shard_info()
+        # 2. tiny exchange
+        mine = torch.tensor([bits, klo, khi], dtype=torch.int64, device="cuda")
+        if self.world > 1:
+            allv = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(allv, mine, group=self.group)
+            infos = [tuple(int(x) for x in v.tolist()) for v in allv]
+        else:
+            infos = [(bits, klo, khi)]
+        plan = plan_shards(infos)[self.rank]
+        # 3. k repair of the leading tiles
+        if plan.k_in != 0 and nbytes:
+            self.codec.set_tile_limit(first_const + 1)
+            self.codec.encode_enqueue(p, d_raw, nbytes, self.local, None, Carry(0, plan.k_in, 0))
+        # 4. move to the global bit phase (placed[0] is global word floor(bit_offset / 32))
+        self.codec.place_bits(self.local, bits, self.placed, plan.bit_offset & 31)
+        # 5. boundary word exchange
+        if self.world > 1:
+            nwords = (((plan.bit_offset & 31) + bits + 31) >> 5)
+            w = self.placed.view(torch.int32)
+            edge = torch.stack([w[0], w[max(nwords - 1, 0)]]).to(torch.int64)
+            alle = [torch.zeros_like(edge) for _ in range(self.world)]
+            dist.all_gather(alle, edge, group=self.group)
+            if self.rank > 0 and (plan.bit_offset & 31):
+                prev_last = alle[self.rank - 1][1].to(torch.int32)
+                w[0] = w[0] | prev_last
+        torch.cuda.current_stream().synchronize()
+        self.plan = plan
+        self.bits = bits
+        return plan
+
+    def owned_bytes(self):
+        """This rank's bytes of the global stream (device tensor view)."""
+        plan = self.plan
+        nbytes = (plan.word_hi - plan.word_lo) * 4
+        if self.rank == self.world - 1:
+            nbytes = (plan.total_bits + 7) // 8 - plan.word_lo * 4
+        return self.placed[:max(nbytes, 0)]
+
+    def decode(self, d_out, nbytes: int):
+        """Decode this rank's shard from its own stream: no exchange needed."""
+        p = self.p
+        R = p.rsi * p.block_size
+        nrsi = (nbytes // p.bytes_per_sample + R - 1) // R
+        self.codec.decode_enqueue(p, self.local, (self.bits + 7) // 8, self.offsets, nrsi, d_out, nbytes)
+        return self.codec.decode_finish()
