@@ -242,13 +242,13 @@ def run_ours(args):
         if sharded is not None:
             sharded.encode(d_raw, raw.size)
     torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
     launches0 = codec.launches
     sh_l0 = sharded.codec.launches if sharded is not None else 0
     t_start = torch.cuda.Event(enable_timing=True)
