@@ -208,82 +208,71 @@ AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t 
      * k < kmax with T(k) < thisbs, both kmax when none. ---- */
     uint32_t split = 0xFFFFFFFFu;
     if (c.idl > 1) {
-        /* guess: smallest k with (S0 >> (k+1)) <= thisbs */
+        /* guess kg: smallest k with (S0 >> (k+1)) <= thisbs; the true klo is
+         * within one of it on every data set we measured */
+        const uint32_t kmax = c.kmax;
         uint64_t q = S0 >> 1;
         int kg = 0;
         if (q > thisbs) {
-            /* bits(q) - bits(thisbs) is within one of the answer */
             kg = (64 - aec_clz64(q)) - (32 - aec_clz32(thisbs));
             if (kg < 0) kg = 0;
             while (kg > 0 && (q >> (kg - 1)) <= thisbs) kg--;
             while ((q >> kg) > thisbs) kg++;
         }
-        uint32_t kmax = c.kmax;
-        uint32_t kb = (uint32_t)kg > kmax ? kmax : (uint32_t)kg;
-        kb = kb > 0 ? kb - 1 : 0;                       /* window base */
-        if (kb + 1 > kmax) kb = kmax > 0 ? kmax - 1 : 0;
-        /* S at kb..kb+4 (values beyond kmax are never consulted) */
-        uint32_t S[5];
+        uint32_t kgc = (uint32_t)kg > kmax ? kmax : (uint32_t)kg;
+        uint32_t kb = kgc >= 2 ? kgc - 2 : 0;               /* window base: T known for kb..kb+3 */
+        /* S at kb..kb+4; all sums fit 32 bits: S(kb) <= S0 >> kb <= 8*thisbs+7
+         * when kb = kg-2, and d >> (kmax-2) <= 31 when the guess was clamped */
+        uint32_t S1 = 0, S2 = 0, S3 = 0, S4 = 0, S5 = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = 0; j < 5; j++) S[j] = 0;
-        if (S0 >> kb <= 0xFFFFFFFFull / 2) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (uint32_t i = 0; i < J; i++) {
-                uint32_t v = d[i] >> kb;
-                S[0] += v; S[1] += v >> 1; S[2] += v >> 2; S[3] += v >> 3; S[4] += v >> 4;
-            }
-        } else {
-            kb = 0xFFFFFFFFu;                           /* force the exact path */
+        for (uint32_t i = 0; i < J; i++) {
+            uint32_t v = d[i] >> kb;
+            S1 += v; S2 += v >> 1; S3 += v >> 2; S4 += v >> 3; S5 += v >> 4;
         }
-        bool done = false;
-        uint32_t lo = 0, hi = 0, slo = 0;
-        if (kb != 0xFFFFFFFFu) {
-            /* T_j for k = kb+j, j = 0..3, only meaningful while kb+j < kmax */
-            int jlo = -1, jhi = -1;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int j = 0; j < 4; j++) {
-                uint32_t k = kb + (uint32_t)j;
-                bool valid = k < kmax;
-                uint32_t T = S[j] - S[j + 1];
-                if (valid && jlo < 0 && T <= thisbs) jlo = j;
-                if (valid && jhi < 0 && T < thisbs) jhi = j;
-            }
-            /* low side resolved when the first T<=thisbs is not at the window's
-             * left edge (or the window starts at k = 0) */
-            bool lo_ok, hi_ok;
-            if (jlo >= 0) { lo = kb + (uint32_t)jlo; lo_ok = (jlo > 0) || (kb == 0); }
-            else { lo = kmax; lo_ok = (kb + 4 >= kmax); }
-            if (jhi >= 0) { hi = kb + (uint32_t)jhi; hi_ok = true; }
-            else { hi = kmax; hi_ok = (kb + 4 >= kmax); }
-            if (lo_ok && hi_ok) {
-                done = true;
-                slo = (lo - kb <= 4) ? S[lo - kb] : 0;
-                if (lo - kb > 4) done = false;
+        const uint32_t T0 = S1 - S2, T1 = S2 - S3, T2 = S3 - S4, T3 = S4 - S5;
+        uint32_t lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu, slo = 0;
+        /* first k in the window with T <= thisbs (lo) and with T < thisbs (hi) */
+        if (kb + 3 < kmax && T3 <= thisbs) { lo = kb + 3; slo = S4; }
+        if (kb + 2 < kmax && T2 <= thisbs) { lo = kb + 2; slo = S3; }
+        if (kb + 1 < kmax && T1 <= thisbs) { lo = kb + 1; slo = S2; }
+        if (kb + 0 < kmax && T0 <= thisbs) { lo = kb + 0; slo = S1; }
+        if (kb + 3 < kmax && T3 < thisbs) hi = kb + 3;
+        if (kb + 2 < kmax && T2 < thisbs) hi = kb + 2;
+        if (kb + 1 < kmax && T1 < thisbs) hi = kb + 1;
+        if (kb + 0 < kmax && T0 < thisbs) hi = kb + 0;
+        if (lo == kb && kb > 0) {
+            /* left edge: smaller k may qualify as well -> walk down (rare) */
+            uint32_t snext = S1, k = kb;
+            while (k > 0) {
+                uint32_t sk = 0;
+                for (uint32_t i = 0; i < J; i++) sk += d[i] >> (k - 1);
+                uint32_t T = sk - snext;
+                if (T > thisbs) break;
+                k--; lo = k; slo = sk;
+                if (T < thisbs) hi = k;
+                snext = sk;
             }
         }
-        if (!done) {
-            /* exact scan over every k (rare) */
-            lo = kmax; hi = kmax;
-            bool flo = false, fhi = false;
-            uint64_t prev = S0;
-            for (uint32_t k = 0; k < kmax; k++) {
-                uint64_t nxt = 0;
-                for (uint32_t i = 0; i < J; i++) nxt += d[i] >> (k + 1);
-                uint64_t T = prev - nxt;
-                if (!flo && T <= thisbs) { lo = k; flo = true; }
-                if (!fhi && T < thisbs) { hi = k; fhi = true; }
-                prev = nxt;
-                if (fhi) break;
+        if (hi == 0xFFFFFFFFu) {
+            /* nothing strictly below thisbs inside the window -> walk up (rare) */
+            uint32_t k = kb + 4, sk = S5;
+            while (k < kmax) {
+                uint32_t sn = 0;
+                for (uint32_t i = 0; i < J; i++) sn += d[i] >> (k + 1);
+                uint32_t T = sk - sn;
+                if (lo == 0xFFFFFFFFu && T <= thisbs) { lo = k; slo = sk; }
+                if (T < thisbs) { hi = k; break; }
+                sk = sn; k++;
             }
-            uint64_t s = 0;
-            for (uint32_t i = 0; i < J; i++) s += d[i] >> lo;
-            slo = (uint32_t)s;
+            if (hi == 0xFFFFFFFFu) hi = kmax;
+        }
+        if (lo == 0xFFFFFFFFu) {
+            lo = kmax;
+            uint32_t sk = 0;
+            for (uint32_t i = 0; i < J; i++) sk += d[i] >> kmax;
+            slo = sk;
         }
         bi.klo = lo; bi.khi = hi;
         split = slo + thisbs * (lo + 1);
@@ -399,28 +388,42 @@ AEC_HD uint64_t aec_papply(const PosFn &f, uint64_t p)
  * exclusively and stored plainly. */
 struct BitPack {
     uint32_t *buf;
+    uint32_t sbase;   /* device: shared-window byte address of buf[0] */
     uint32_t cur;     /* bits accumulated for word widx, MSB first */
     uint32_t fill;    /* bits of cur in use (may reach 32 transiently) */
     uint32_t widx;
-    uint32_t first;   /* next flush is the shared first word */
+    uint32_t wfirst;  /* index of the CDS's first word (shared with the previous CDS) */
 
     AEC_HDM void merge(uint32_t idx, uint32_t v)
     {
 #if defined(__CUDA_ARCH__)
-        if (v) atomicOr(&buf[idx], v);
+        asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(sbase + idx * 4u), "r"(v) : "memory");
 #else
         buf[idx] |= v;
+#endif
+    }
+    AEC_HDM void store(uint32_t idx, uint32_t v)
+    {
+#if defined(__CUDA_ARCH__)
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(sbase + idx * 4u), "r"(v) : "memory");
+#else
+        buf[idx] = v;
 #endif
     }
     AEC_HDM void init(uint32_t *b, uint64_t bitpos)
     {
         buf = b; cur = 0; fill = (uint32_t)(bitpos & 31u); widx = (uint32_t)(bitpos >> 5);
-        first = 1;
+        wfirst = widx;
+#if defined(__CUDA_ARCH__)
+        sbase = (uint32_t)__cvta_generic_to_shared(b);
+#else
+        sbase = 0;
+#endif
     }
     AEC_HDM void flush_word()
     {
-        if (first) { merge(widx, cur); first = 0; }
-        else buf[widx] = cur;
+        if (widx == wfirst) merge(widx, cur);
+        else store(widx, cur);
         cur = 0;
     }
     /* append len (1..32) bits of v (v < 2^len) */
@@ -458,6 +461,9 @@ struct BitPack {
  * Emit the CDS of one non-zero block (results of encode.c:520-563).
  *   d      mapped samples; refs: raw reference sample when ref
  *   k      split position (already clamp(k_prev, klo, khi))
+ * Fields are combined four samples at a time before they go through the
+ * word packer: a group's unary codes (or its k-bit remainders) usually fit
+ * one 32-bit field, which cuts the data-dependent word-flush branches 4x.
  */
 template <int JT>
 AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint32_t opt,
@@ -467,18 +473,76 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
     if (opt == OPT_SPLIT) {
         bp.put(k + 1, c.idl);
         if (ref) bp.put(refs, c.n);
+        /* unary part */
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (uint32_t i = 0; i < J; i++)
-            if (i >= ref) bp.put_fs(d[i] >> k);
+        for (uint32_t g = 0; g < J; g += 4) {
+            uint32_t acc = 0, len = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (uint32_t j = 0; j < 4; j++) {
+                uint32_t i = g + j;
+                if (i < ref || i >= J) continue;
+                uint32_t s1 = (d[i] >> k) + 1u;
+                acc = (acc << (s1 > 31u ? 31u : s1)) | 1u;
+                len += s1 > 64u ? 64u : s1;
+            }
+            if (len <= 32u) {
+                if (len) bp.put(acc, len);
+            } else {
+                for (uint32_t j = 0; j < 4; j++) {
+                    uint32_t i = g + j;
+                    if (i < ref || i >= J) continue;
+                    bp.put_fs(d[i] >> k);
+                }
+            }
+        }
+        /* binary part: k low bits of every sample */
         if (k) {
-            uint32_t m = (1u << k) - 1u;
+            const uint32_t m = (1u << k) - 1u;
+            if (k <= 8) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (uint32_t i = 0; i < J; i++)
-                if (i >= ref) bp.put(d[i] & m, k);
+                for (uint32_t g = 0; g < J; g += 4) {
+                    uint32_t acc = 0, len = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (uint32_t j = 0; j < 4; j++) {
+                        uint32_t i = g + j;
+                        if (i < ref || i >= J) continue;
+                        acc = (acc << k) | (d[i] & m);
+                        len += k;
+                    }
+                    if (len) bp.put(acc, len);
+                }
+            } else if (k <= 16) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (uint32_t g = 0; g < J; g += 2) {
+                    uint32_t acc = 0, len = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (uint32_t j = 0; j < 2; j++) {
+                        uint32_t i = g + j;
+                        if (i < ref || i >= J) continue;
+                        acc = (acc << k) | (d[i] & m);
+                        len += k;
+                    }
+                    if (len) bp.put(acc, len);
+                }
+            } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (uint32_t i = 0; i < J; i++)
+                    if (i >= ref) bp.put(d[i] & m, k);
+            }
         }
     } else if (opt == OPT_SE) {
         bp.put(1, c.idl + 1);

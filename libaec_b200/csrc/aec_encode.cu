@@ -289,24 +289,28 @@ aec_encode_kernel(const AecEncArgs a)
         PosFn pexc; pexc.has_end = 0; pexc.a = 0; pexc.rest = 0;
         uint32_t kbefore = aec_kpair(0, c.kmax);
         PosFn ptile = pexc; uint32_t ktile = kbefore;
+        if (c.pad) {
 #pragma unroll
-        for (int w = 0; w < NWARP; w++) {
-            PosFn f;
-            if (c.pad) { f.has_end = s_wend[w]; f.a = s_wa[w]; f.rest = s_wrest[w]; }
-            else { f.has_end = 0; f.a = s_wlen[w]; f.rest = 0; }
-            if ((uint32_t)w < warp) { pexc = aec_pcompose(pexc, f); kbefore = aec_kcompose(kbefore, s_wk[w]); }
-            ptile = aec_pcompose(ptile, f); ktile = aec_kcompose(ktile, s_wk[w]);
-        }
-        {   /* add the lanes before me in my own warp */
-            PosFn f;
-            if (c.pad) {
-                f = shfl_posfn(pinc, (int)lane - 1);
-            } else {
-                f.has_end = 0; f.a = __shfl_up_sync(FULL, linc, 1); f.rest = 0;
+            for (int w = 0; w < NWARP; w++) {
+                PosFn f; f.has_end = s_wend[w]; f.a = s_wa[w]; f.rest = s_wrest[w];
+                if ((uint32_t)w < warp) { pexc = aec_pcompose(pexc, f); kbefore = aec_kcompose(kbefore, s_wk[w]); }
+                ptile = aec_pcompose(ptile, f); ktile = aec_kcompose(ktile, s_wk[w]);
             }
+            PosFn f = shfl_posfn(pinc, (int)lane - 1);      /* the lanes before me in my own warp */
             if (lane > 0) pexc = aec_pcompose(pexc, f);
-            kbefore = aec_kcompose(kbefore, kexc);
+        } else {
+            /* plain sums: no RSI padding */
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < NWARP; w++) {
+                uint32_t v = s_wlen[w];
+                if ((uint32_t)w < warp) { before += v; kbefore = aec_kcompose(kbefore, s_wk[w]); }
+                total += v; ktile = aec_kcompose(ktile, s_wk[w]);
+            }
+            pexc.a = before + (linc - len);
+            ptile.a = total;
         }
+        kbefore = aec_kcompose(kbefore, kexc);
 
         /* ---- zero the staging area (upper bound on the tile's bits) ---- */
         {
