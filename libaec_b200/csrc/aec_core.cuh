@@ -247,6 +247,9 @@ AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t 
             uint32_t snext = S1, k = kb;
             while (k > 0) {
                 uint32_t sk = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
                 for (uint32_t i = 0; i < J; i++) sk += d[i] >> (k - 1);
                 uint32_t T = sk - snext;
                 if (T > thisbs) break;
@@ -260,6 +263,9 @@ AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t 
             uint32_t k = kb + 4, sk = S5;
             while (k < kmax) {
                 uint32_t sn = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
                 for (uint32_t i = 0; i < J; i++) sn += d[i] >> (k + 1);
                 uint32_t T = sk - sn;
                 if (lo == 0xFFFFFFFFu && T <= thisbs) { lo = k; slo = sk; }
@@ -271,6 +277,9 @@ AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t 
         if (lo == 0xFFFFFFFFu) {
             lo = kmax;
             uint32_t sk = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
             for (uint32_t i = 0; i < J; i++) sk += d[i] >> kmax;
             slo = sk;
         }
@@ -283,6 +292,9 @@ AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t 
     if (S0 <= unc) {       /* se >= 1 + J/2 + S0, so larger S0 can never win */
         uint64_t len = 1;
         bool inf = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
         for (uint32_t i = 0; i < J; i += 2) {
             uint64_t s = (uint64_t)d[i] + (uint64_t)d[i + 1];
             len += s * (s + 1) / 2 + d[i + 1] + 1;
@@ -294,6 +306,9 @@ AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t 
          * reachable when a pair sum reaches 2^32; replicate exactly */
         uint64_t len = 1;
         bool inf = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
         for (uint32_t i = 0; i < J; i += 2) {
             uint64_t s = (uint64_t)d[i] + (uint64_t)d[i + 1];
             len += s * (s + 1) / 2 + d[i + 1] + 1;
@@ -492,6 +507,9 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
             if (len <= 32u) {
                 if (len) bp.put(acc, len);
             } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
                 for (uint32_t j = 0; j < 4; j++) {
                     uint32_t i = g + j;
                     if (i < ref || i >= J) continue;
@@ -547,6 +565,9 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
     } else if (opt == OPT_SE) {
         bp.put(1, c.idl + 1);
         if (ref) bp.put(refs, c.n);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
         for (uint32_t i = 0; i < J; i += 2) {
             uint32_t s = d[i] + d[i + 1];
             bp.put_fs(s * (s + 1) / 2 + d[i + 1]);      /* u32 like encode.c:558-559 */

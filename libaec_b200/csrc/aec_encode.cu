@@ -143,7 +143,8 @@ __device__ __forceinline__ void load_block(const AecCfg &c, const uint8_t *in, u
         for (int i = 0; i < JT; i++) x[i] = extract_sample<B>(w, i, c.msb);
     } else {
         /* generic: bytewise, index clamped to the last sample (encode.c:681-684) */
-        for (uint32_t i = 0; i < J; i++) {
+#pragma unroll
+        for (uint32_t i = 0; i < (JT ? (uint32_t)JT : J); i++) {
             uint64_t idx = first + i;
             if (idx >= nsamples) idx = nsamples - 1;
             x[i] = aec_load_sample(in + idx * c.B, c.B, c.msb);
@@ -158,10 +159,18 @@ struct TileCfg {
     static constexpr int TB = (JT == 0 || JT == 64) ? 128 : 256;
     static constexpr int NWARP = TB / 32;
     static constexpr int JMAX = JT ? JT : AEC_MAX_J;
+    /* resident CTAs per SM the register allocation aims for */
+    static constexpr int MINB = (JT == 8 || JT == 16) ? 4 : ((JT == 32) ? 3 : ((JT == 64) ? 4 : 2));
 };
 
+__device__ __forceinline__ void pair_barrier(uint32_t warp)
+{
+    /* the two warps of one 64-block zero-run segment */
+    asm volatile("bar.sync %0, 64;" :: "r"(1u + (warp >> 1)) : "memory");
+}
+
 template <int JT, int B>
-__global__ void __launch_bounds__(TileCfg<JT>::TB)
+__global__ void __launch_bounds__(TileCfg<JT>::TB, TileCfg<JT>::MINB)
 aec_encode_kernel(const AecEncArgs a)
 {
     constexpr int TB = TileCfg<JT>::TB;
@@ -170,21 +179,30 @@ aec_encode_kernel(const AecEncArgs a)
     const AecCfg &c = a.cfg;
     const uint32_t J = JT ? (uint32_t)JT : c.J;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t kident = aec_kpair(0, c.kmax);
+    /* RSIs longer than a tile with RSI padding: a tile may start at an unknown
+     * bit phase mod 8, so its bits can only be laid out after the look-back */
+    const bool late = c.pad && a.RP > (uint32_t)TB;
 
     extern __shared__ uint32_t staging[];
-    __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_ticket[2];
     __shared__ uint32_t s_zb[NWARP + 1];
     __shared__ uint32_t s_wlen[NWARP];       /* per-warp sums (no-pad mode) */
     __shared__ uint32_t s_wend[NWARP], s_wa[NWARP], s_wrest[NWARP];   /* per-warp PosFn (pad mode) */
     __shared__ uint32_t s_wk[NWARP];
     __shared__ unsigned long long s_base;
     __shared__ uint32_t s_kin;
+    __shared__ uint32_t s_kready;            /* iteration (+1) for which s_base/s_kin are valid */
 
-    for (;;) {
-        if (tid == 0) s_ticket = atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        const uint64_t tile = s_ticket;
+    for (uint32_t i = tid; i < a.staging_words; i += TB) staging[i] = 0;
+    if (tid == 0) { s_ticket[0] = atomicAdd(a.ticket, 1u); s_kready = 0; }
+    __syncthreads();
+
+    for (uint32_t it = 0;; it++) {
+        const uint64_t tile = s_ticket[it & 1u];
         if (tile >= a.ntiles) break;
+        /* next ticket: becomes visible with the next CTA barrier */
+        if (tid == 0) s_ticket[(it + 1u) & 1u] = atomicAdd(a.ticket, 1u);
 
         /* ---- which block is mine ---- */
         uint64_t rsi_idx; uint32_t b;
@@ -202,22 +220,24 @@ aec_encode_kernel(const AecEncArgs a)
         const bool valid = b < nblk;
         const uint32_t ref = (valid && c.pp && b == 0) ? 1u : 0u;
 
-        /* ---- load, map ---- */
+        /* ---- load, map, cost ---- */
         uint32_t d[JMAX];
         uint32_t refs = 0;
         BlockInfo bi; bi.opt = OPT_NONE; bi.klo = 0; bi.khi = c.kmax; bi.len = 0;
-        if (valid) {
+        {
             const uint64_t first = rsi_idx * (uint64_t)c.R + (uint64_t)b * J;
-            const bool fast = a.aligned && (first + J <= a.nsamples);
-            load_block<JT, B>(c, a.in, first, a.nsamples, fast, d);
-            if (c.pp) {
-                uint32_t prev;
-                if (b == 0) { refs = d[0]; prev = d[0] ^ c.sflip; }
-                else {
+            const bool fast = valid && a.aligned && (first + J <= a.nsamples);
+            if (valid) load_block<JT, B>(c, a.in, first, a.nsamples, fast, d);
+            /* last raw sample of the previous block = last sample of the lane below */
+            uint32_t prev = __shfl_up_sync(FULL, valid ? d[J - 1] : 0u, 1);
+            if (valid && c.pp) {
+                if (b == 0) { refs = d[0]; prev = d[0]; }
+                else if (lane == 0) {
                     uint64_t pi = first - 1;
                     if (pi >= a.nsamples) pi = a.nsamples - 1;
-                    prev = aec_load_sample(a.in + pi * c.B, c.B, c.msb) ^ c.sflip;
+                    prev = aec_load_sample(a.in + pi * c.B, c.B, c.msb);
                 }
+                prev ^= c.sflip;
 #pragma unroll
                 for (uint32_t i = 0; i < (JT ? (uint32_t)JT : J); i++) {
                     uint32_t u = d[i] ^ c.sflip;
@@ -226,17 +246,17 @@ aec_encode_kernel(const AecEncArgs a)
                 }
                 if (b == 0) d[0] = 0;
             }
-            bi = aec_analyze_block<JT>(c, d, ref);
+            if (valid) bi = aec_analyze_block<JT>(c, d, ref);
         }
         const bool is_zero = valid && bi.opt == OPT_ZERO;
 
         /* ---- zero-run structure of my 64-block segment ---- */
         uint32_t ball = __ballot_sync(FULL, is_zero);
         if (lane == 0) s_zb[warp] = ball;
-        __syncthreads();
+        pair_barrier(warp);
         uint32_t len = bi.len, zcode = 0, zref = 0;
         if (is_zero) {
-            uint64_t m64 = (uint64_t)s_zb[warp & ~1u] | ((uint64_t)((warp | 1u) < NWARP ? s_zb[warp | 1u] : 0u) << 32);
+            uint64_t m64 = (uint64_t)s_zb[warp & ~1u] | ((uint64_t)s_zb[warp | 1u] << 32);
             uint32_t q = tid & 63u;                       /* position in the aligned 64-slot group */
             uint32_t g0 = q - (b & 63u);                  /* where my segment starts in the group */
             uint32_t seg = b >> 6;
@@ -251,8 +271,8 @@ aec_encode_kernel(const AecEncArgs a)
         }
         const bool rsi_end = valid && (b + 1 == nblk);
 
-        /* ---- intra-tile exclusive scans: bit offsets and k clamp chain ---- */
-        uint32_t kp = aec_kpair(bi.klo, bi.khi);          /* identity for zero/invalid/idl<=1 */
+        /* ---- intra-warp inclusive scans: CDS lengths and the k clamp chain ---- */
+        const uint32_t kp = aec_kpair(bi.klo, bi.khi);    /* identity for zero/invalid/idl<=1 */
         uint32_t kinc = kp;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -260,7 +280,7 @@ aec_encode_kernel(const AecEncArgs a)
             if (lane >= (uint32_t)off) kinc = aec_kcompose(o, kinc);
         }
         uint32_t kexc = __shfl_up_sync(FULL, kinc, 1);
-        if (lane == 0) kexc = aec_kpair(0, c.kmax);
+        if (lane == 0) kexc = kident;
 
         PosFn pinc; pinc.has_end = 0; pinc.a = 0; pinc.rest = 0;   /* pad mode */
         uint32_t linc = len;                                      /* no-pad mode */
@@ -281,50 +301,57 @@ aec_encode_kernel(const AecEncArgs a)
         if (lane == 31) {
             s_wk[warp] = kinc;
             s_wlen[warp] = linc;
-            s_wend[warp] = pinc.has_end; s_wa[warp] = (uint32_t)pinc.a; s_wrest[warp] = (uint32_t)pinc.rest;
+            if (c.pad) { s_wend[warp] = pinc.has_end; s_wa[warp] = (uint32_t)pinc.a; s_wrest[warp] = (uint32_t)pinc.rest; }
         }
-        __syncthreads();
+        __syncthreads();                                           /* S2 */
 
-        /* function of everything before me in the tile */
-        PosFn pexc; pexc.has_end = 0; pexc.a = 0; pexc.rest = 0;
-        uint32_t kbefore = aec_kpair(0, c.kmax);
-        PosFn ptile = pexc; uint32_t ktile = kbefore;
-        if (c.pad) {
-#pragma unroll
-            for (int w = 0; w < NWARP; w++) {
-                PosFn f; f.has_end = s_wend[w]; f.a = s_wa[w]; f.rest = s_wrest[w];
-                if ((uint32_t)w < warp) { pexc = aec_pcompose(pexc, f); kbefore = aec_kcompose(kbefore, s_wk[w]); }
-                ptile = aec_pcompose(ptile, f); ktile = aec_kcompose(ktile, s_wk[w]);
-            }
-            PosFn f = shfl_posfn(pinc, (int)lane - 1);      /* the lanes before me in my own warp */
-            if (lane > 0) pexc = aec_pcompose(pexc, f);
-        } else {
-            /* plain sums: no RSI padding */
-            uint32_t before = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < NWARP; w++) {
-                uint32_t v = s_wlen[w];
-                if ((uint32_t)w < warp) { before += v; kbefore = aec_kcompose(kbefore, s_wk[w]); }
-                total += v; ktile = aec_kcompose(ktile, s_wk[w]);
-            }
-            pexc.a = before + (linc - len);
-            ptile.a = total;
-        }
-        kbefore = aec_kcompose(kbefore, kexc);
-
-        /* ---- zero the staging area (upper bound on the tile's bits) ---- */
+        /* ---- cross-warp: every warp scans the NWARP warp totals with its first lanes ---- */
+        PosFn pexc; pexc.has_end = 0; pexc.a = 0; pexc.rest = 0;  /* everything before me in the tile */
+        PosFn ptile = pexc;
+        uint32_t kbefore, ktile;
         {
-            uint32_t ub = (uint32_t)(ptile.a + ptile.rest) + (c.pad ? 8u * TB : 0u);
-            uint32_t nz = (31u + ub + 31u) / 32u + 1u;
-            if (nz > a.staging_words) nz = a.staging_words;
-            for (uint32_t i = tid; i < nz; i += TB) staging[i] = 0;
+            uint32_t wk = lane < (uint32_t)NWARP ? s_wk[lane] : kident;
+#pragma unroll
+            for (int off = 1; off < NWARP; off <<= 1) {
+                uint32_t o = __shfl_up_sync(FULL, wk, off);
+                if (lane >= (uint32_t)off) wk = aec_kcompose(o, wk);
+            }
+            kbefore = __shfl_sync(FULL, wk, warp ? warp - 1 : 0);
+            if (warp == 0) kbefore = kident;
+            ktile = __shfl_sync(FULL, wk, NWARP - 1);
+            kbefore = aec_kcompose(kbefore, kexc);
+            if (c.pad) {
+                PosFn w; w.has_end = 0; w.a = 0; w.rest = 0;
+                if (lane < (uint32_t)NWARP) { w.has_end = s_wend[lane]; w.a = s_wa[lane]; w.rest = s_wrest[lane]; }
+#pragma unroll
+                for (int off = 1; off < NWARP; off <<= 1) {
+                    PosFn o = shfl_posfn(w, (int)lane - off);
+                    if (lane >= (uint32_t)off) w = aec_pcompose(o, w);
+                }
+                PosFn bw = shfl_posfn(w, warp ? (int)warp - 1 : 0);
+                ptile = shfl_posfn(w, NWARP - 1);
+                if (warp) pexc = bw;
+                PosFn f = shfl_posfn(pinc, (int)lane - 1);          /* the lanes before me in my own warp */
+                if (lane > 0) pexc = aec_pcompose(pexc, f);
+            } else {
+                uint32_t wl = lane < (uint32_t)NWARP ? s_wlen[lane] : 0u;
+#pragma unroll
+                for (int off = 1; off < NWARP; off <<= 1) {
+                    uint32_t o = __shfl_up_sync(FULL, wl, off);
+                    if (lane >= (uint32_t)off) wl += o;
+                }
+                uint32_t before = __shfl_sync(FULL, wl, warp ? warp - 1 : 0);
+                if (warp == 0) before = 0;
+                ptile.a = __shfl_sync(FULL, wl, NWARP - 1);
+                pexc.a = before + (linc - len);
+            }
         }
 
         /* ---- publish aggregate, decoupled look-back (warp 0) ---- */
         if (warp == 0) {
             if (lane == 0) st_volatile_u64(&a.desc[tile], desc_pack_agg(ptile, ktile));
             PosFn accp; accp.has_end = 0; accp.a = 0; accp.rest = 0;
-            uint32_t acck = aec_kpair(0, c.kmax);
+            uint32_t acck = kident;
             int64_t pred = (int64_t)tile - 1;
             for (;;) {
                 int64_t idx = pred - (int64_t)lane;
@@ -341,7 +368,7 @@ aec_encode_kernel(const AecEncArgs a)
                 int firstp = pm ? (__ffs((int)pm) - 1) : 32;
                 PosFn f; uint32_t k;
                 desc_unpack(dv, f, k);
-                if ((int)lane > firstp) { f.has_end = 0; f.a = 0; f.rest = 0; k = aec_kpair(0, c.kmax); }
+                if ((int)lane > firstp) { f.has_end = 0; f.a = 0; f.rest = 0; k = kident; }
                 /* ordered reduction: higher lane = earlier tile */
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
@@ -364,49 +391,74 @@ aec_encode_kernel(const AecEncArgs a)
                 a.tile_end[tile] = end;
                 a.tile_kagg[tile] = ktile;
                 if (tile + 1 == a.ntiles_total) { a.result[0] = end; a.result[1] = kout; }
+                __threadfence_block();
+                *reinterpret_cast<volatile uint32_t *>(&s_kready) = it + 1u;
             }
+            __syncwarp();
         }
-        __syncthreads();
+        if (late) __syncthreads();          /* bit layout needs the absolute phase */
 
         /* ---- pack my CDS into the staging area ---- */
-        const uint64_t base = s_base;
-        const uint64_t w0 = base >> 5;
-        const uint64_t myoff = aec_papply(pexc, base);
-        if (valid && b == 0 && a.rsi_offsets) a.rsi_offsets[rsi_idx] = myoff;
+        uint64_t base_l = 0;                /* staging bit 0 <-> this absolute bit */
+        if (late) { uint64_t bs = s_base; base_l = (bs >> 5) << 5; }
+        const uint64_t tile0 = late ? (uint64_t)s_base : 0ull;
+        const uint64_t myoff = aec_papply(pexc, tile0) - base_l;   /* bit offset inside staging */
         if (valid && len) {
             BitPack bp;
-            bp.init(staging, myoff - (w0 << 5));
+            bp.init(staging, myoff);
             if (is_zero) {
                 aec_pack_zero(c, bp, zcode, zref, refs);
             } else {
-                uint32_t kprev = aec_clampu(s_kin, kbefore & 0xFFu, kbefore >> 8);
-                uint32_t k = aec_clampu(kprev, bi.klo, bi.khi);
+                uint32_t k = bi.klo;
+                if (bi.opt == OPT_SPLIT && bi.klo != bi.khi) {
+                    uint32_t kprev;
+                    if ((kbefore & 0xFFu) == (kbefore >> 8)) kprev = kbefore & 0xFFu;
+                    else {
+                        /* depends on the k carried into this tile: wait for the look-back */
+                        while (*reinterpret_cast<volatile uint32_t *>(&s_kready) != it + 1u) { }
+                        kprev = aec_clampu(*reinterpret_cast<volatile uint32_t *>(&s_kin), kbefore & 0xFFu, kbefore >> 8);
+                    }
+                    k = aec_clampu(kprev, bi.klo, bi.khi);
+                }
                 aec_pack_block<JT>(c, bp, d, bi.opt, k, ref, refs);
             }
             bp.finish();
         }
-        __syncthreads();
+        __syncthreads();                                           /* S3 */
 
-        /* ---- stream the tile's words out ---- */
+        /* ---- stream the tile's words out, shifted to the absolute bit phase ---- */
+        const uint64_t base = s_base;
+        if (valid && b == 0 && a.rsi_offsets) a.rsi_offsets[rsi_idx] = late ? myoff + base_l : base + myoff;
+        uint32_t nsl;
         {
-            const uint64_t end = aec_papply(ptile, base);
-            const uint64_t we = end >> 5;
+            const uint64_t end = aec_papply(ptile, late ? base : 0ull) + (late ? 0ull : base);
+            const uint64_t w0 = base >> 5, we = end >> 5;
+            const uint32_t ph = late ? (uint32_t)(base & 31u) : 0u;
+            const uint32_t sh = (uint32_t)(base & 31u) - ph;
+            const uint32_t tbits = (uint32_t)(end - base);
             const uint32_t nw = (uint32_t)(we - w0) + ((end & 31u) ? 1u : 0u);
+            nsl = (ph + tbits + 31u) >> 5;
             const bool head_partial = (base & 31u) != 0;
             const bool tail_partial = (end & 31u) != 0 && (we > w0 || !head_partial);
             for (uint32_t i = tid; i < nw; i += TB) {
-                uint32_t v = staging[i];
+                uint32_t lo = i < nsl ? staging[i] : 0u;
+                uint32_t v = lo;
+                if (sh) {
+                    uint32_t hi = (i >= 1u && i - 1u < nsl) ? staging[i - 1u] : 0u;
+                    v = (hi << (32u - sh)) | (lo >> sh);
+                }
                 uint64_t wi = w0 + i;
-                if (i == 0 && head_partial) continue;
-                if (wi == we) continue;                   /* partial tail word */
+                if (i == 0 && head_partial) { a.head_c[tile] = (end > base) ? v : 0u; continue; }
+                if (wi == we) { if (tail_partial) a.tail_c[tile] = v; continue; }
                 if (wi < a.out_cap_words) a.out_words[wi] = __byte_perm(v, 0, 0x0123);
             }
             if (tid == 0) {
-                a.head_c[tile] = (head_partial && end > base) ? staging[0] : 0u;
-                a.tail_c[tile] = tail_partial ? staging[(uint32_t)(we - w0)] : 0u;
+                if (!head_partial || nw == 0) a.head_c[tile] = 0u;
+                if (!tail_partial) a.tail_c[tile] = 0u;
             }
         }
-        __syncthreads();
+        __syncthreads();                                           /* S4 */
+        for (uint32_t i = tid; i < nsl + 1u && i < a.staging_words; i += TB) staging[i] = 0;
     }
 }
 
