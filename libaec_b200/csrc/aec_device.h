@@ -29,7 +29,8 @@ struct AecEncArgs {
     uint32_t seed_k;            /* k carried in from the stream so far */
     uint32_t seed_word;         /* content of the partial word at seed_bits (bits already there) */
     /* workspace, device */
-    uint64_t *desc;             /* [ntiles], zeroed */
+    uint64_t *desc;             /* [ntiles], zeroed: per-tile aggregates, written by the worker CTAs */
+    uint64_t *pref;             /* [ntiles], zeroed: per-tile exclusive prefixes, written by the scanner */
     uint32_t *ticket;           /* zeroed */
     uint32_t *head_c, *tail_c;  /* [ntiles] partial boundary words */
     uint64_t *tile_end;         /* [ntiles] absolute end bit of each tile */

@@ -62,13 +62,16 @@ __device__ __forceinline__ void desc_unpack(uint64_t d, PosFn &f, uint32_t &kp)
     }
 }
 
+/* descriptor accesses: relaxed, gpu scope (L2 is the coherence point) */
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p)
 {
-    return *reinterpret_cast<const volatile uint64_t *>(p);
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void st_volatile_u64(uint64_t *p, uint64_t v)
 {
-    *reinterpret_cast<volatile uint64_t *>(p) = v;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
 __device__ __forceinline__ PosFn shfl_posfn(const PosFn &v, int src)
@@ -152,6 +155,84 @@ __device__ __forceinline__ void load_block(const AecCfg &c, const uint8_t *in, u
     }
 }
 
+/* ---- dedicated scanner ------------------------------------------------------
+ * CTA 0 turns the per-tile aggregates into exclusive prefixes (absolute bit
+ * offset + incoming k of every tile).  Worker CTAs never look back: they
+ * publish their aggregate, pack their tile, and read their prefix when they
+ * are ready to write.  Warp w of the scanner owns the batches w, w+NW, ... of
+ * 32 consecutive tiles: it loads the 32 aggregates and scans them on its own,
+ * then takes the running (position, k) carry from the previous batch through
+ * shared memory, writes the 32 prefixes and passes the carry on.  The serial
+ * part of the chain is that hand-over only (no memory round trip per tile). */
+template <int NW>
+__device__ __noinline__ void aec_encode_scanner(const AecEncArgs &a, uint64_t *s_carry_pos, uint32_t *s_carry_k,
+                                                volatile uint32_t *s_done)
+{
+    const AecCfg &c = a.cfg;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t kident = aec_kpair(0, c.kmax);
+    const uint64_t nbatch = (a.ntiles + 31) / 32;
+    if (threadIdx.x == 0) { s_carry_pos[0] = a.seed_bits; s_carry_k[0] = a.seed_k; *s_done = 0; }
+    __syncthreads();
+    for (uint64_t b = warp; b < nbatch; b += NW) {
+        const uint64_t t = b * 32 + lane;
+        uint64_t dv = ST_AGG | ((uint64_t)c.kmax << 7);           /* identity beyond the last tile */
+        if (t < a.ntiles) {
+            dv = ld_volatile_u64(&a.desc[t]);
+            while ((dv & 3) == 0) { __nanosleep(100); dv = ld_volatile_u64(&a.desc[t]); }
+        }
+        __syncwarp();
+        PosFn f; uint32_t kj;
+        desc_unpack(dv, f, kj);
+        /* inclusive scan over the batch (lower lane = earlier tile) */
+        PosFn fi = f; uint32_t ki = kj;
+        if (c.pad) {
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                PosFn o = shfl_posfn(fi, (int)lane - off);
+                if (lane >= (uint32_t)off) fi = aec_pcompose(o, fi);
+            }
+        } else {
+            uint32_t li = (uint32_t)f.a;                          /* 32 tiles x < 2^21 bits fit 32 bits */
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t o = __shfl_up_sync(FULL, li, off);
+                if (lane >= (uint32_t)off) li += o;
+            }
+            fi.a = li;
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t ok = __shfl_up_sync(FULL, ki, off);
+            if (lane >= (uint32_t)off) ki = aec_kcompose(ok, ki);
+        }
+        PosFn fe = shfl_posfn(fi, (int)lane - 1);
+        uint32_t ke = __shfl_up_sync(FULL, ki, 1);
+        if (lane == 0) { fe.has_end = 0; fe.a = 0; fe.rest = 0; ke = kident; }
+        /* carry of everything before this batch */
+        while (*s_done != (uint32_t)b) __nanosleep(20);
+        const uint64_t P = *reinterpret_cast<volatile uint64_t *>(&s_carry_pos[b & 1]);
+        const uint32_t kc = *reinterpret_cast<volatile uint32_t *>(&s_carry_k[b & 1]);
+        const uint64_t pos = aec_papply(fe, P);
+        const uint32_t k = aec_clampu(kc, ke & 0xFFu, ke >> 8);
+        const uint64_t end = aec_papply(f, pos);
+        if (lane == 31) {
+            *reinterpret_cast<volatile uint64_t *>(&s_carry_pos[(b + 1) & 1]) = end;
+            *reinterpret_cast<volatile uint32_t *>(&s_carry_k[(b + 1) & 1]) = aec_clampu(k, kj & 0xFFu, kj >> 8);
+            __threadfence_block();
+            *s_done = (uint32_t)(b + 1);
+            if (b + 1 == nbatch && a.ntiles == a.ntiles_total) {
+                /* lane 31 of the last batch: identity tiles beyond the end keep the totals */
+                a.result[0] = end; a.result[1] = aec_clampu(k, kj & 0xFFu, kj >> 8);
+            }
+        }
+        if (t < a.ntiles) {
+            st_volatile_u64(&a.pref[t], desc_pack_prefix(pos, k));
+            a.tile_end[t] = end;
+        }
+    }
+}
+
 /* ---- the kernel ----------------------------------------------------------- */
 
 template <int JT>
@@ -194,6 +275,13 @@ aec_encode_kernel(const AecEncArgs a)
     __shared__ uint32_t s_kin;
     __shared__ uint32_t s_kready;            /* iteration (+1) for which s_base/s_kin are valid */
 
+    if (blockIdx.x == 0) {                  /* CTA 0 is the scanner */
+        __shared__ unsigned long long s_cpos[2];
+        __shared__ uint32_t s_ck[2];
+        __shared__ uint32_t s_sdone;
+        aec_encode_scanner<NWARP>(a, reinterpret_cast<uint64_t *>(s_cpos), s_ck, &s_sdone);
+        return;
+    }
     for (uint32_t i = tid; i < a.staging_words; i += TB) staging[i] = 0;
     if (tid == 0) { s_ticket[0] = atomicAdd(a.ticket, 1u); s_kready = 0; }
     __syncthreads();
@@ -201,8 +289,6 @@ aec_encode_kernel(const AecEncArgs a)
     for (uint32_t it = 0;; it++) {
         const uint64_t tile = s_ticket[it & 1u];
         if (tile >= a.ntiles) break;
-        /* next ticket: becomes visible with the next CTA barrier */
-        if (tid == 0) s_ticket[(it + 1u) & 1u] = atomicAdd(a.ticket, 1u);
 
         /* ---- which block is mine ---- */
         uint64_t rsi_idx; uint32_t b;
@@ -347,82 +433,68 @@ aec_encode_kernel(const AecEncArgs a)
             }
         }
 
-        /* ---- publish aggregate, decoupled look-back (warp 0) ---- */
-        if (warp == 0) {
-            if (lane == 0) st_volatile_u64(&a.desc[tile], desc_pack_agg(ptile, ktile));
-            PosFn accp; accp.has_end = 0; accp.a = 0; accp.rest = 0;
-            uint32_t acck = kident;
-            int64_t pred = (int64_t)tile - 1;
-            for (;;) {
-                int64_t idx = pred - (int64_t)lane;
-                uint64_t dv = 0;
-                if (idx >= 0) {
-                    do { dv = ld_volatile_u64(&a.desc[idx]); } while ((dv & 3) == 0);
-                } else if (idx == -1) {
-                    dv = desc_pack_prefix(a.seed_bits, a.seed_k);
-                } else {
-                    dv = ST_AGG | ((uint64_t)c.kmax << 7);      /* identity, never reached */
-                }
-                __syncwarp();
-                uint32_t pm = __ballot_sync(FULL, (dv & 3) == ST_PREFIX);
-                int firstp = pm ? (__ffs((int)pm) - 1) : 32;
-                PosFn f; uint32_t k;
-                desc_unpack(dv, f, k);
-                if ((int)lane > firstp) { f.has_end = 0; f.a = 0; f.rest = 0; k = kident; }
-                /* ordered reduction: higher lane = earlier tile */
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    PosFn o = shfl_posfn(f, (int)lane + off);
-                    uint32_t ok = __shfl_down_sync(FULL, k, off);
-                    if (lane + off < 32u) { f = aec_pcompose(o, f); k = aec_kcompose(ok, k); }
-                }
-                f = shfl_posfn(f, 0); k = __shfl_sync(FULL, k, 0);
-                accp = aec_pcompose(f, accp); acck = aec_kcompose(k, acck);
-                if (pm) break;
-                pred -= 32;
-            }
-            if (lane == 0) {
-                uint64_t base = aec_papply(accp, 0);
-                uint32_t kin = acck & 0xFFu;              /* constant map: lo == hi */
-                uint64_t end = aec_papply(ptile, base);
-                uint32_t kout = aec_clampu(kin, ktile & 0xFFu, ktile >> 8);
-                st_volatile_u64(&a.desc[tile], desc_pack_prefix(end, kout));
-                s_base = base; s_kin = kin;
-                a.tile_end[tile] = end;
-                a.tile_kagg[tile] = ktile;
-                if (tile + 1 == a.ntiles_total) { a.result[0] = end; a.result[1] = kout; }
-                __threadfence_block();
-                *reinterpret_cast<volatile uint32_t *>(&s_kready) = it + 1u;
-            }
-            __syncwarp();
+        /* publish this tile's aggregate for the scanner */
+        if (tid == 0) {
+            st_volatile_u64(&a.desc[tile], desc_pack_agg(ptile, ktile));
+            a.tile_kagg[tile] = ktile;
         }
-        if (late) __syncthreads();          /* bit layout needs the absolute phase */
 
-        /* ---- pack my CDS into the staging area ---- */
-        uint64_t base_l = 0;                /* staging bit 0 <-> this absolute bit */
-        if (late) { uint64_t bs = s_base; base_l = (bs >> 5) << 5; }
-        const uint64_t tile0 = late ? (uint64_t)s_base : 0ull;
-        const uint64_t myoff = aec_papply(pexc, tile0) - base_l;   /* bit offset inside staging */
-        if (valid && len) {
-            BitPack bp;
-            bp.init(staging, myoff);
-            if (is_zero) {
-                aec_pack_zero(c, bp, zcode, zref, refs);
-            } else {
-                uint32_t k = bi.klo;
-                if (bi.opt == OPT_SPLIT && bi.klo != bi.khi) {
-                    uint32_t kprev;
-                    if ((kbefore & 0xFFu) == (kbefore >> 8)) kprev = kbefore & 0xFFu;
-                    else {
-                        /* depends on the k carried into this tile: wait for the look-back */
-                        while (*reinterpret_cast<volatile uint32_t *>(&s_kready) != it + 1u) { }
-                        kprev = aec_clampu(*reinterpret_cast<volatile uint32_t *>(&s_kin), kbefore & 0xFFu, kbefore >> 8);
-                    }
-                    k = aec_clampu(kprev, bi.klo, bi.khi);
+        /* Packing happens in two passes around the look-back: pass 0 packs every
+         * CDS that needs nothing from preceding tiles (all of them in the common
+         * case) while the predecessors are still publishing; pass 1, after warp 0
+         * has resolved the tile's bit offset and incoming k, packs the few CDSs
+         * whose split position depends on that k (or everything in `late` mode). */
+        const bool need_kin = valid && len && !is_zero && bi.opt == OPT_SPLIT && bi.klo != bi.khi &&
+                              (kbefore & 0xFFu) != (kbefore >> 8);
+        uint64_t myoff = pexc.a;            /* bit offset inside staging (early mode: local phase 0) */
+        uint64_t base_l = 0;                /* staging bit 0 <-> this absolute bit (late mode) */
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1) {
+                /* the scanner's exclusive prefix of this tile: absolute bit offset and incoming k */
+                if (tid == 0) {
+                    uint64_t pv = ld_volatile_u64(&a.pref[tile]);
+                    while ((pv & 3) == 0) { __nanosleep(40); pv = ld_volatile_u64(&a.pref[tile]); }
+                    s_base = pv >> 12;
+                    s_kin = (uint32_t)(pv >> 2) & 0x1Fu;
+                    __threadfence_block();
+                    *reinterpret_cast<volatile uint32_t *>(&s_kready) = it + 1u;
+                    /* Claim the next tile only now: a claimed tile must never wait for
+                     * anything but earlier tiles, or the scanner's fixed batches of 32
+                     * could wait for a tile whose CTA is itself waiting for that batch.
+                     * Visible to the CTA after barrier S3. */
+                    s_ticket[(it + 1u) & 1u] = atomicAdd(a.ticket, 1u);
                 }
-                aec_pack_block<JT>(c, bp, d, bi.opt, k, ref, refs);
+                if (late) {
+                    __syncthreads();        /* bit layout needs the absolute phase */
+                    uint64_t bs = s_base;
+                    base_l = (bs >> 5) << 5;
+                    myoff = aec_papply(pexc, bs) - base_l;
+                }
+            } else if (c.pad && !late) {
+                myoff = aec_papply(pexc, 0);
             }
-            bp.finish();
+            const bool doit = valid && len && (pass == 0 ? (!late && !need_kin) : (late || need_kin));
+            if (doit) {
+                BitPack bp;
+                bp.init(staging, myoff);
+                if (is_zero) {
+                    aec_pack_zero(c, bp, zcode, zref, refs);
+                } else {
+                    uint32_t k = bi.klo;
+                    if (bi.opt == OPT_SPLIT && bi.klo != bi.khi) {
+                        uint32_t kprev = kbefore & 0xFFu;
+                        if (kprev != (kbefore >> 8)) {
+                            /* depends on the k carried into this tile: wait for the look-back */
+                            while (*reinterpret_cast<volatile uint32_t *>(&s_kready) != it + 1u) __nanosleep(32);
+                            kprev = aec_clampu(*reinterpret_cast<volatile uint32_t *>(&s_kin), kbefore & 0xFFu, kbefore >> 8);
+                        }
+                        k = aec_clampu(kprev, bi.klo, bi.khi);
+                    }
+                    aec_pack_block<JT>(c, bp, d, bi.opt, k, ref, refs);
+                }
+                bp.finish();
+            }
         }
         __syncthreads();                                           /* S3 */
 
@@ -567,9 +639,11 @@ cudaError_t launch_variant(const AecEncArgs &a, uint32_t smem_bytes, int num_sms
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TileCfg<JT>::TB, smem_bytes);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
+    /* CTA 0 is the scanner, the others are workers; all of them must be resident */
     uint64_t grid = (uint64_t)occ * (uint64_t)num_sms;
-    if (grid > a.ntiles) grid = a.ntiles;
-    if (grid == 0) return cudaSuccess;
+    if (grid > a.ntiles + 1) grid = a.ntiles + 1;
+    if (grid < 2) grid = 2;
+    if (a.ntiles == 0) return cudaSuccess;
     kern<<<(unsigned)grid, TileCfg<JT>::TB, smem_bytes, st>>>(a);
     return cudaGetLastError();
 }

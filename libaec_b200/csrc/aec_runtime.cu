@@ -54,7 +54,7 @@ struct aecb200_ctx {
     uint64_t launches = 0;
     char err[256] = {0};
 
-    DevBuf desc, headc, tailc, tile_end, tile_kagg, misc, in_stage, out_stage, offs, rsi_count;
+    DevBuf desc, pref, headc, tailc, tile_end, tile_kagg, misc, in_stage, out_stage, offs, rsi_count;
     uint64_t tile_limit = 0;             /* next encode codes only this many leading tiles (k repair) */
     bool want_summary = false;
     uint64_t *h_res = nullptr;           /* pinned: [0..3] encode result, [4..7] decode result */
@@ -154,7 +154,7 @@ void aecb200_ctx_destroy(aecb200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    ctx->tile_kagg.release();
+    ctx->tile_kagg.release(); ctx->pref.release();
     ctx->desc.release(); ctx->headc.release(); ctx->tailc.release(); ctx->tile_end.release();
     ctx->misc.release(); ctx->in_stage.release(); ctx->out_stage.release(); ctx->offs.release();
     ctx->rsi_count.release();
@@ -217,12 +217,14 @@ int aecb200_encode_device(aecb200_ctx *ctx, const aecb200_params *p,
     }
 
     CK(ctx->desc.ensure(g.ntiles * 8), "cudaMalloc(desc)");
+    CK(ctx->pref.ensure(g.ntiles * 8), "cudaMalloc(pref)");
     CK(ctx->headc.ensure(g.ntiles * 4), "cudaMalloc(head)");
     CK(ctx->tailc.ensure(g.ntiles * 4), "cudaMalloc(tail)");
     CK(ctx->tile_end.ensure(g.ntiles * 8), "cudaMalloc(tile_end)");
     CK(ctx->tile_kagg.ensure(g.ntiles * 4), "cudaMalloc(tile_kagg)");
     CK(ctx->misc.ensure(256), "cudaMalloc(misc)");
     CK(cudaMemsetAsync(ctx->desc.p, 0, g.ntiles * 8, ctx->stream), "memset(desc)");
+    CK(cudaMemsetAsync(ctx->pref.p, 0, g.ntiles * 8, ctx->stream), "memset(pref)");
     CK(cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream), "memset(misc)");
 
     AecEncArgs a;
@@ -244,6 +246,7 @@ int aecb200_encode_device(aecb200_ctx *ctx, const aecb200_params *p,
     a.seed_k = carry->k;
     a.seed_word = carry->word;
     a.desc = (uint64_t *)ctx->desc.p;
+    a.pref = (uint64_t *)ctx->pref.p;
     a.ticket = (uint32_t *)ctx->misc.p;
     a.result = (uint64_t *)((uint8_t *)ctx->misc.p + 64);
     a.head_c = (uint32_t *)ctx->headc.p;
