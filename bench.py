@@ -204,13 +204,14 @@ def run_ours(args):
     d_comp = torch.empty(cap, dtype=torch.uint8, device="cuda")
     d_offs = torch.empty(nrsi, dtype=torch.int64, device="cuda")
     d_back = torch.empty(raw.size + 16, dtype=torch.uint8, device="cuda")
+    d_grp = torch.zeros(max(codec.group_index_entries(p, raw.size), 1), dtype=torch.int64, device="cuda")
 
     # one checked pass: byte-exact round trip on this rank's shard
-    codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs)
+    codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs, d_grp=d_grp)
     st, bits, kend = codec.encode_finish()
     assert st == 0
     comp_bytes = (bits + 7) // 8
-    codec.decode_enqueue(p, d_comp, comp_bytes, d_offs, nrsi, d_back, raw.size)
+    codec.decode_enqueue(p, d_comp, comp_bytes, d_offs, nrsi, d_back, raw.size, d_grp=d_grp)
     st, written = codec.decode_finish()
     assert st == 0 and written == raw.size
     assert torch.equal(d_back[:raw.size], d_raw), "round trip differs"
@@ -233,8 +234,8 @@ def run_ours(args):
         sharded = ShardedCodec(p, rank, world, local, stream=stream.cuda_stream)
 
     def step():
-        codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs)
-        codec.decode_enqueue(p, d_comp, comp_bytes, d_offs, nrsi, d_back, raw.size)
+        codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs, d_grp=d_grp)
+        codec.decode_enqueue(p, d_comp, comp_bytes, d_offs, nrsi, d_back, raw.size, d_grp=d_grp)
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     for _ in range(args.warmup):
@@ -264,9 +265,9 @@ def run_ours(args):
             b.record()
             sharded.codec.decode_enqueue(p, sharded.local, comp_bytes, sharded.offsets, nrsi, d_back, raw.size)
         else:
-            codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs)
+            codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs, d_grp=d_grp)
             b.record()
-            codec.decode_enqueue(p, d_comp, comp_bytes, d_offs, nrsi, d_back, raw.size)
+            codec.decode_enqueue(p, d_comp, comp_bytes, d_offs, nrsi, d_back, raw.size, d_grp=d_grp)
         c.record()
         marks.append((a, b, c))
     t_end.record()

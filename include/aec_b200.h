@@ -84,6 +84,18 @@ int aecb200_encode_device(aecb200_ctx *ctx, const aecb200_params *p,
                           void *d_out, size_t out_cap,
                           const aecb200_carry *carry,
                           uint64_t *d_rsi_offsets);
+/* Same, and also records the group index the warp-per-RSI decoder reads
+ * (d_grp_index: aecb200_group_index_entries() uint64 entries, 32 per RSI: for
+ * each group of ceil(rsi/32) blocks the bit offset of its first CDS and the
+ * number of leading blocks that belong to a zero run started earlier).  No
+ * reference counterpart. */
+int aecb200_encode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
+                                  const void *d_in, size_t in_bytes,
+                                  void *d_out, size_t out_cap,
+                                  const aecb200_carry *carry,
+                                  uint64_t *d_rsi_offsets, uint64_t *d_grp_index);
+size_t aecb200_group_index_entries(const aecb200_params *p, size_t in_bytes);
+
 /* Wait for the last enqueued encode; returns the carry after it (end bit, k;
  * `word` is not filled).  AEC_STREAM_ERROR when the stream did not fit out_cap. */
 int aecb200_encode_finish(aecb200_ctx *ctx, aecb200_carry *end);
@@ -111,6 +123,15 @@ int aecb200_decode_device(aecb200_ctx *ctx, const aecb200_params *p,
                           const void *d_in, size_t in_bytes,
                           const uint64_t *d_rsi_offsets, size_t nrsi,
                           void *d_out, size_t out_bytes);
+/* Same with the encoder's group index (NULL: it is rebuilt on the device by
+ * skimming every RSI from its start offset). */
+int aecb200_decode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
+                                  const void *d_in, size_t in_bytes,
+                                  const uint64_t *d_rsi_offsets, size_t nrsi,
+                                  const uint64_t *d_grp_index,
+                                  void *d_out, size_t out_bytes);
+/* Force the lane-per-RSI ("careful") decode kernel for everything (testing). */
+void aecb200_ctx_set_careful_decode(aecb200_ctx *ctx, int on);
 /* Wait for the last enqueued decode; *out_written = bytes of samples delivered. */
 int aecb200_decode_finish(aecb200_ctx *ctx, size_t *out_written);
 

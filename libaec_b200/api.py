@@ -92,7 +92,9 @@ DEVICE_SYMBOLS = ["aecb200_device_count", "aecb200_ctx_create", "aecb200_ctx_des
                   "aecb200_encode_finish", "aecb200_decode_device", "aecb200_decode_finish",
                   "aecb200_scan_offsets_device", "aecb200_encode_host", "aecb200_encode_host_piece",
                   "aecb200_decode_host", "aecb200_decode_host_resume", "aecb200_ctx_set_shard_mode",
-                  "aecb200_encode_shard_info", "aecb200_ctx_set_tile_limit", "aecb200_place_bits_device"]
+                  "aecb200_encode_shard_info", "aecb200_ctx_set_tile_limit", "aecb200_place_bits_device",
+                  "aecb200_encode_device_indexed", "aecb200_decode_device_indexed", "aecb200_group_index_entries",
+                  "aecb200_ctx_set_careful_decode"]
 SZ_SYMBOLS = ["SZ_BufftoBuffCompress", "SZ_BufftoBuffDecompress", "SZ_encoder_enabled", "SZ_Compress"]
 
 
@@ -112,6 +114,8 @@ def load_library() -> C.CDLL:
         lib.aecb200_ctx_destroy.restype = None
         lib.aecb200_ctx_set_encode_padding.restype = None
         lib.aecb200_ctx_set_shard_mode.restype = None
+        lib.aecb200_ctx_set_careful_decode.restype = None
+        lib.aecb200_group_index_entries.restype = C.c_size_t
         lib.aecb200_ctx_set_tile_limit.restype = None
         _lib = lib
     return _lib
@@ -350,14 +354,23 @@ class DeviceCodec:
         return st
 
     # tensors are torch uint8/any-dtype CUDA tensors; only data_ptr()/nbytes are used
-    def encode_enqueue(self, p: Params, d_in, in_bytes: int, d_out, d_offsets=None, carry: Carry | None = None):
+    def encode_enqueue(self, p: Params, d_in, in_bytes: int, d_out, d_offsets=None, carry: Carry | None = None,
+                       d_grp=None):
         prm = _Params(p.bits_per_sample, p.block_size, p.rsi, p.flags)
-        st = self.lib.aecb200_encode_device(
+        st = self.lib.aecb200_encode_device_indexed(
             self.ctx, C.byref(prm), C.c_void_p(d_in.data_ptr()), C.c_size_t(in_bytes),
             C.c_void_p(d_out.data_ptr()), C.c_size_t(d_out.numel() * d_out.element_size()),
             C.byref(carry) if carry is not None else None,
-            C.c_void_p(d_offsets.data_ptr()) if d_offsets is not None else None)
-        return self._check(st, "aecb200_encode_device")
+            C.c_void_p(d_offsets.data_ptr()) if d_offsets is not None else None,
+            C.c_void_p(d_grp.data_ptr()) if d_grp is not None else None)
+        return self._check(st, "aecb200_encode_device_indexed")
+
+    def group_index_entries(self, p: Params, in_bytes: int) -> int:
+        prm = _Params(p.bits_per_sample, p.block_size, p.rsi, p.flags)
+        return int(self.lib.aecb200_group_index_entries(C.byref(prm), C.c_size_t(in_bytes)))
+
+    def set_careful_decode(self, on: bool = True):
+        self.lib.aecb200_ctx_set_careful_decode(self.ctx, C.c_int(int(on)))
 
     def encode_finish(self):
         end = Carry()
@@ -382,13 +395,15 @@ class DeviceCodec:
             C.c_size_t(d_dst.numel() * d_dst.element_size()), C.c_uint64(dst_bit))
         return self._check(st, "aecb200_place_bits_device")
 
-    def decode_enqueue(self, p: Params, d_in, in_bytes: int, d_offsets, nrsi: int, d_out, out_bytes: int):
+    def decode_enqueue(self, p: Params, d_in, in_bytes: int, d_offsets, nrsi: int, d_out, out_bytes: int,
+                       d_grp=None):
         prm = _Params(p.bits_per_sample, p.block_size, p.rsi, p.flags)
-        st = self.lib.aecb200_decode_device(
+        st = self.lib.aecb200_decode_device_indexed(
             self.ctx, C.byref(prm), C.c_void_p(d_in.data_ptr()), C.c_size_t(in_bytes),
             C.c_void_p(d_offsets.data_ptr()), C.c_size_t(nrsi),
+            C.c_void_p(d_grp.data_ptr()) if d_grp is not None else None,
             C.c_void_p(d_out.data_ptr()), C.c_size_t(out_bytes))
-        return self._check(st, "aecb200_decode_device")
+        return self._check(st, "aecb200_decode_device_indexed")
 
     def decode_finish(self):
         n = C.c_size_t(0)

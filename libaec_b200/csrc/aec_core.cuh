@@ -341,16 +341,18 @@ AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t 
  * of its run) and fills *fs_code / *zref.  Results of encode.c:614-659 and
  * :565-583. */
 AEC_HD uint32_t aec_zero_run(const AecCfg &c, uint64_t segmask, uint32_t V, uint32_t b,
-                             uint32_t *fs_code, uint32_t *zref)
+                             uint32_t *fs_code, uint32_t *zref, uint32_t *runlen)
 {
     uint32_t p = b & 63u;
     bool last = (p + 1 == V);
     bool next_zero = !last && ((segmask >> (p + 1)) & 1ull);
+    *runlen = 0;
     if (next_zero) return 0;                           /* run continues */
     /* run length: consecutive ones ending at bit p */
     uint64_t sh = segmask << (63u - p);
     uint32_t L = (uint32_t)aec_clz64(~sh);
     if (L > p + 1) L = p + 1;
+    *runlen = L;
     uint32_t code;
     if (last && L > 4) code = 4;                       /* ROS */
     else if (L >= 5)   code = L;

@@ -69,10 +69,14 @@ aec_decode_kernel(const AecDecArgs a)
     uint32_t *wrows = rows + (size_t)warp * 32u * stride;
     uint32_t *row = wrows + (size_t)lane * stride;
 
-    const uint64_t rsi0 = ((uint64_t)blockIdx.x * DEC_WARPS + warp) * 32ull;   /* first RSI of this warp */
-    if (rsi0 >= a.nrsi) return;
-    const uint64_t r = rsi0 + lane;
-    const bool have = r < a.nrsi;
+    /* with a list: slot i decodes RSI rsi_list[i] (the RSIs the fast kernel handed over) */
+    const uint64_t nslots = a.rsi_list ? (uint64_t)*a.rsi_list_count : a.nrsi;
+    const uint64_t slot0 = ((uint64_t)blockIdx.x * DEC_WARPS + warp) * 32ull;
+    if (slot0 >= nslots) return;
+    const bool have = slot0 + lane < nslots;
+    const uint64_t r = have ? (a.rsi_list ? (uint64_t)a.rsi_list[slot0 + lane] : slot0 + lane) : 0;
+    const bool contiguous = a.rsi_list == nullptr;
+    const uint64_t rsi0 = slot0;
 
     /* how many samples this RSI has to deliver */
     uint64_t limit = 0;
@@ -101,7 +105,7 @@ aec_decode_kernel(const AecDecArgs a)
         /* ---- cooperative store of the 32 rows of this block index ---- */
         const uint32_t fullmask = __ballot_sync(FULL, cnt == J);
         const uint32_t partmask = __ballot_sync(FULL, cnt != J && cnt != 0);
-        if (JT != 0 && a.out_aligned && partmask == 0) {
+        if (JT != 0 && a.out_aligned && partmask == 0 && contiguous) {
             /* rows are full or empty: flat index over 32*J samples, one 32-bit store per lane-step */
             constexpr int SPG = (B == 4) ? 1 : ((B == 2) ? 2 : 4);       /* samples per 32-bit group */
             constexpr int GPR = (JT ? JT : 4) / SPG;                     /* groups per row */
@@ -132,6 +136,291 @@ aec_decode_kernel(const AecDecArgs a)
                       ~(unsigned long long)(r * (uint64_t)c.R + delivered));
         if (st.status == DEC_ERROR)
             atomicOr(reinterpret_cast<unsigned long long *>(&a.result[1]), 1ull);
+    }
+}
+
+/* ======================================================================== */
+/* Fast path: one warp per RSI                                               */
+/* ======================================================================== */
+
+constexpr int DW_MAX_WARPS = 4;      /* warps (= RSIs) per CTA; fewer when rows are long */
+
+/* Bit reader with a 64-bit left-aligned window refilled one word at a time. */
+struct Rd64 {
+    const uint32_t *w;
+    uint32_t nwords, widx;
+    uint64_t acc;
+    int nb;
+    __device__ __forceinline__ uint32_t ld(uint32_t i) const { return i < nwords ? __byte_perm(__ldg(w + i), 0, 0x0123) : 0u; }
+    __device__ __forceinline__ void init(const uint32_t *base, uint32_t nw, uint64_t bitpos)
+    {
+        w = base; nwords = nw;
+        widx = (uint32_t)(bitpos >> 5);
+        uint32_t sh = (uint32_t)(bitpos & 31u);
+        acc = (((uint64_t)ld(widx) << 32) | ld(widx + 1)) << sh;
+        nb = 64 - (int)sh;
+        widx += 2;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (nb <= 32) { acc |= (uint64_t)ld(widx) << (32 - nb); widx++; nb += 32; }
+    }
+    __device__ __forceinline__ uint64_t pos() const { return (uint64_t)widx * 32ull - (uint64_t)nb; }
+    /* n in 1..32 */
+    __device__ __forceinline__ uint32_t get(uint32_t n)
+    {
+        refill();
+        uint32_t v = (uint32_t)(acc >> 32) >> (32u - n);
+        acc <<= n; nb -= (int)n;
+        return v;
+    }
+    /* unary code; sets *bad when the window runs off the stream */
+    __device__ __forceinline__ uint32_t fs(uint32_t *bad)
+    {
+        uint32_t cnt = 0;
+        for (;;) {
+            refill();
+            uint32_t hi = (uint32_t)(acc >> 32);
+            if (hi) {
+                uint32_t z = (uint32_t)__clz((int)hi);
+                acc <<= (z + 1); nb -= (int)(z + 1);
+                return cnt + z;
+            }
+            cnt += 32; acc <<= 32; nb -= 32;
+            if (widx > nwords + 2u) { *bad = 1u; return cnt; }
+        }
+    }
+};
+
+/* One block of J mapped values into row[0..J): fast restatement of
+ * aec_decode_block for clean streams (anything unusual sets *bad and the RSI
+ * is handed to the careful kernel). */
+template <int JT>
+__device__ __forceinline__ void warp_decode_block(const AecCfg &c, Rd64 &rd, uint32_t b, uint32_t *row,
+                                                  uint32_t &zero_left, uint32_t *bad)
+{
+    const uint32_t J = JT ? (uint32_t)JT : c.J;
+    if (zero_left) {
+        zero_left--;
+#pragma unroll 4
+        for (uint32_t i = 0; i < J; i++) row[i] = 0;
+        return;
+    }
+    const uint32_t ref = (c.pp && b == 0) ? 1u : 0u;
+    const uint32_t id = rd.get(c.idl);
+    if (id == 0) {
+        const uint32_t sel = rd.get(1);
+        if (ref) row[0] = rd.get(c.n);
+        if (sel == 0) {
+            uint32_t zb = rd.fs(bad) + 1u;
+            if (zb == 5u) { uint32_t a1 = c.rsi - b, a2 = 64u - (b & 63u); zb = a1 < a2 ? a1 : a2; }
+            else if (zb > 5u) zb--;
+            if (zb > c.rsi - b) { *bad = 1u; zb = 1; }
+            zero_left = zb - 1u;
+#pragma unroll 4
+            for (uint32_t i = ref; i < J; i++) row[i] = 0;
+            return;
+        }
+        uint32_t i = ref;
+        while (i < J) {
+            uint32_t m = rd.fs(bad);
+            if (m > 90u) { *bad = 1u; m = 0; }
+            uint32_t s = (uint32_t)((sqrtf(8.0f * (float)m + 1.0f) - 1.0f) * 0.5f);
+            while (s * (s + 1u) / 2u > m) s--;
+            while ((s + 1u) * (s + 2u) / 2u <= m) s++;
+            uint32_t d1 = m - s * (s + 1u) / 2u;
+            if ((i & 1u) == 0) { row[i] = s - d1; i++; }
+            row[i] = d1; i++;
+        }
+        return;
+    }
+    if (id == (1u << c.idl) - 1u) {
+#pragma unroll 4
+        for (uint32_t i = 0; i < J; i++) row[i] = rd.get(c.n);
+        return;
+    }
+    const uint32_t k = id - 1u;
+    if (ref) row[0] = rd.get(c.n);
+#pragma unroll 4
+    for (uint32_t i = ref; i < J; i++) row[i] = rd.fs(bad) << k;
+    if (k) {
+#pragma unroll 4
+        for (uint32_t i = ref; i < J; i++) row[i] += rd.get(k);
+    }
+}
+
+/* exact inverse mapper step on normalised values; sets clip when the clipped branch was taken */
+__device__ __forceinline__ uint32_t unmap_step(uint32_t u, uint32_t d, uint32_t M, uint32_t &clip)
+{
+    uint32_t h = (d >> 1) + (d & 1u);
+    uint32_t mu = M - u;
+    uint32_t step = (d & 1u) ? (u - h) : (u + h);
+    uint32_t cv = (u <= mu) ? d : (M - d);
+    bool cl = (u < h) || (mu < h);
+    clip |= cl ? 1u : 0u;
+    return cl ? cv : step;
+}
+
+template <int JT, int B>
+__global__ void __launch_bounds__(DW_MAX_WARPS * 32)
+aec_decode_warp_kernel(const AecDecArgs a)
+{
+    const AecCfg &c = a.cfg;
+    const uint32_t J = JT ? (uint32_t)JT : c.J;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t G = a.grp_G;
+    const uint32_t GJ = G * J;                        /* samples per lane */
+    const uint32_t stride = GJ | 1u;                  /* odd row stride: conflict free */
+    extern __shared__ uint32_t rows[];
+    uint32_t *row = rows + ((size_t)warp * 32u + lane) * stride;
+
+    const uint64_t r = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (r >= a.nrsi) return;
+    /* only whole RSIs inside the requested output are handled here */
+    const uint64_t startS = r * (uint64_t)c.R;
+    bool whole = a.out_samples >= startS + c.R;
+    uint32_t bad = whole ? 0u : 1u;
+
+    const uint32_t b0 = lane * G;
+    const uint32_t nblk = b0 < c.rsi ? (c.rsi - b0 < G ? c.rsi - b0 : G) : 0u;
+    uint32_t sum = 0;                                  /* wrapping sum of my deltas */
+    uint32_t uref = 0;
+    uint64_t endpos = 0, startpos = 0;
+    uint32_t lead0 = 0, zl_end = 0;
+    if (whole && nblk) {
+        const uint64_t e = a.grp_index[r * 32ull + lane];
+        uint32_t lead = (uint32_t)(e >> 56);
+        lead0 = lead;
+        startpos = e & 0x00FFFFFFFFFFFFFFull;
+        const uint32_t nwords = (uint32_t)((a.in_bytes + 3) >> 2);
+        if (startpos > a.in_bytes * 8ull) { bad = 1u; startpos = 0; }
+        Rd64 rd;
+        rd.init(a.in_words, nwords, startpos);
+        uint32_t zero_left = 0;
+        for (uint32_t q = 0; q < nblk; q++) {
+            uint32_t *rw = row + q * J;
+            if (lead) {
+                lead--;
+                for (uint32_t i = 0; i < J; i++) rw[i] = 0;
+            } else {
+                warp_decode_block<JT>(c, rd, b0 + q, rw, zero_left, &bad);
+            }
+            if (c.pp) {
+                uint32_t i0 = (b0 + q == 0) ? 1u : 0u;      /* sample 0 of the RSI is the reference */
+#pragma unroll 4
+                for (uint32_t i = i0; i < J; i++) {
+                    uint32_t dv = rw[i];
+                    sum += (dv >> 1) ^ (0u - (dv & 1u));     /* +h for even d, -h for odd d */
+                }
+            }
+        }
+        endpos = rd.pos();
+        zl_end = zero_left;
+        if (endpos > a.in_bytes * 8ull) bad = 1u;
+        if (lane == 0 && c.pp) uref = (row[0] ^ (c.sext ? (1u << (c.n - 1)) : 0u)) & c.mask;
+    }
+    /* index sanity: the next lane's group must start where mine ended, unless it inherits a zero run */
+    {
+        unsigned long long nstart = __shfl_down_sync(FULL, (unsigned long long)startpos, 1);
+        uint32_t nlead = __shfl_down_sync(FULL, lead0, 1);
+        uint32_t nn = __shfl_down_sync(FULL, nblk, 1);
+        if (whole && nblk && lane < 31 && nn && nlead == 0 && zl_end == 0 && nstart != endpos) bad = 1u;
+    }
+    bad = __any_sync(FULL, bad) ? 1u : 0u;
+
+    const uint32_t sflip = c.sext ? (1u << (c.n - 1)) : 0u;
+    if (!bad && c.pp) {
+        /* ---- unit-delay predictor undone in parallel: every lane walks its samples with the
+         * exact map from a speculated start value; start values are re-derived from the lanes'
+         * results until every lane starts where its predecessor ended ---- */
+        uref = __shfl_sync(FULL, uref, 0);
+        uint32_t inc = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t o = __shfl_up_sync(FULL, inc, off);
+            if (lane >= (uint32_t)off) inc += o;
+        }
+        uint32_t us = uref + (inc - sum);              /* speculated value before my first sample */
+        const uint32_t n_s = nblk * J;
+        for (int iter = 0; iter < 34; iter++) {
+            uint32_t u = us, clip = 0;
+            uint32_t i = 0;
+            if (lane == 0) { u = uref; i = 1; }
+            for (; i < n_s; i++) u = unmap_step(u, row[i], c.mask, clip);
+            /* consistent when every lane started at its predecessor's end */
+            uint32_t uprev = __shfl_up_sync(FULL, u, 1);
+            bool ok = (lane == 0) || (n_s == 0) || (uprev == us);
+            if (__all_sync(FULL, ok)) break;
+            /* new start values: absolute after a lane that clipped, relative otherwise
+             * (segmented inclusive scan of (reset, value)) */
+            uint32_t val = clip ? u : (u - us);        /* absolute end, or my net offset */
+            uint32_t rst = clip;
+            if (lane == 0) { val = u; rst = 1u; }
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t ov = __shfl_up_sync(FULL, val, off);
+                uint32_t orst = __shfl_up_sync(FULL, rst, off);
+                if (lane >= (uint32_t)off && !rst) { val += ov; rst = orst; }
+            }
+            uint32_t nus = __shfl_up_sync(FULL, val, 1);   /* predecessor's (speculated) end */
+            if (lane > 0) us = nus;
+            if (iter == 33) bad = 1u;                  /* cannot happen: at least one lane settles per round */
+        }
+        bad = __any_sync(FULL, bad) ? 1u : 0u;
+        if (!bad) {
+            /* final walk: samples in place */
+            uint32_t u = us, clip = 0, i = 0;
+            if (lane == 0) { u = uref; i = 1; uint32_t x = uref ^ sflip; if (c.sext && c.n < 32 && ((x >> (c.n - 1)) & 1u)) x |= ~c.mask; row[0] = x; }
+            for (; i < n_s; i++) {
+                u = unmap_step(u, row[i], c.mask, clip);
+                uint32_t x = u ^ sflip;
+                if (c.sext && c.n < 32 && ((x >> (c.n - 1)) & 1u)) x |= ~c.mask;
+                row[i] = x;
+            }
+        }
+    }
+    if (bad) {
+        if (lane == 0) { uint32_t slot = atomicAdd(a.rsi_list_count, 1u); a.rsi_list[slot] = (uint32_t)r; }
+        return;
+    }
+    __syncwarp();
+    /* ---- cooperative store of the RSI's R samples (contiguous in the output) ---- */
+    uint32_t *wrows = rows + (size_t)warp * 32u * stride;
+    if (JT != 0 && a.out_aligned && (GJ % 4u) == 0) {
+        constexpr int SPG = (B == 4) ? 1 : ((B == 2) ? 2 : 4);
+        const uint32_t ngroups = c.R / SPG;
+        for (uint32_t g = lane; g < ngroups; g += 32) {
+            uint32_t s0 = g * SPG;
+            uint32_t rowi = s0 / GJ, col = s0 % GJ;
+            const uint32_t *src = wrows + (size_t)rowi * stride + col;
+            uint32_t sv[4] = {src[0], SPG > 1 ? src[1] : 0u, SPG > 2 ? src[2] : 0u, SPG > 2 ? src[3] : 0u};
+            store_group<B>(a.out, startS + s0, sv, c.msb);
+        }
+    } else {
+        for (uint32_t s0 = lane; s0 < c.R; s0 += 32) {
+            uint32_t rowi = s0 / GJ, col = s0 % GJ;
+            aec_store_sample(a.out + (startS + s0) * c.B, wrows[(size_t)rowi * stride + col], c.B, c.msb);
+        }
+    }
+}
+
+/* Group index of RSIs with known start offsets: lane-per-RSI skim. */
+__global__ void aec_build_group_index_kernel(const AecDecArgs a, uint64_t *grp_index)
+{
+    const AecCfg &c = a.cfg;
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.nrsi) return;
+    const uint32_t G = a.grp_G;
+    BitRd br;
+    br.init(a.in_words, (a.in_bytes + 3) >> 2, a.in_bytes * 8ull);
+    RsiDec st; st.pos = a.rsi_offsets[r]; st.zero_left = 0; st.status = DEC_OK;
+    for (uint32_t b = 0; b < c.rsi; b++) {
+        if (b % G == 0) grp_index[r * 32ull + b / G] = ((uint64_t)st.zero_left << 56) | (st.pos & 0x00FFFFFFFFFFFFFFull);
+        if (!aec_skim_block(c, br, st, b)) {
+            /* truncated or corrupt: poison the remaining groups so the fast kernel hands the RSI over */
+            for (uint32_t g = b / G + 1; g * G < c.rsi; g++) grp_index[r * 32ull + g] = 0x00FFFFFFFFFFFFFFull;
+            break;
+        }
     }
 }
 
@@ -201,6 +490,72 @@ cudaError_t aec_decode_launch(const AecDecArgs &a, int num_sms, cudaStream_t st)
     case 64: return launch_dec_j<64>(a, st);
     default: return launch_dec_j<0>(a, st);
     }
+}
+
+namespace {
+
+template <int JT, int B>
+cudaError_t launch_decw(const AecDecArgs &a, cudaStream_t st)
+{
+    auto kern = aec_decode_warp_kernel<JT, B>;
+    uint32_t warps = aec_decode_warp_warps(a.cfg);
+    if (warps == 0) return cudaErrorInvalidConfiguration;
+    uint32_t J = JT ? (uint32_t)JT : a.cfg.J;
+    uint32_t stride = (a.grp_G * J) | 1u;
+    uint32_t smem = warps * 32u * stride * 4u;
+    static uint32_t attr = 48 * 1024;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    uint64_t grid = (a.nrsi + warps - 1) / warps;
+    if (grid == 0) return cudaSuccess;
+    kern<<<(unsigned)grid, warps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int JT>
+cudaError_t launch_decw_j(const AecDecArgs &a, cudaStream_t st)
+{
+    switch (a.cfg.B) {
+    case 1: return launch_decw<JT, 1>(a, st);
+    case 2: return launch_decw<JT, 2>(a, st);
+    case 3: return launch_decw<JT, 3>(a, st);
+    default: return launch_decw<JT, 4>(a, st);
+    }
+}
+
+} // namespace
+
+uint32_t aec_decode_group_blocks(const AecCfg &c) { return (c.rsi + 31u) / 32u; }
+
+/* warps per CTA of the warp-per-RSI kernel (0: an RSI's rows do not fit shared memory -> careful kernel only) */
+uint32_t aec_decode_warp_warps(const AecCfg &c)
+{
+    uint32_t stride = (aec_decode_group_blocks(c) * c.J) | 1u;
+    for (uint32_t w = 4; w >= 1; w >>= 1)
+        if ((uint64_t)w * 32u * stride * 4u <= 96u * 1024u) return w;
+    return 0;
+}
+
+cudaError_t aec_decode_warp_launch(const AecDecArgs &a, int num_sms, cudaStream_t st)
+{
+    (void)num_sms;
+    switch (a.cfg.J) {
+    case 8:  return launch_decw_j<8>(a, st);
+    case 16: return launch_decw_j<16>(a, st);
+    case 32: return launch_decw_j<32>(a, st);
+    case 64: return launch_decw_j<64>(a, st);
+    default: return launch_decw_j<0>(a, st);
+    }
+}
+
+cudaError_t aec_build_group_index_launch(const AecDecArgs &a, uint64_t *grp_index, cudaStream_t st)
+{
+    if (a.nrsi == 0) return cudaSuccess;
+    aec_build_group_index_kernel<<<(unsigned)((a.nrsi + 127) / 128), 128, 0, st>>>(a, grp_index);
+    return cudaGetLastError();
 }
 
 cudaError_t aec_scan_offsets_launch(const AecCfg &c, const uint32_t *in_words, uint64_t in_bytes,

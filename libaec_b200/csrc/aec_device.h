@@ -36,6 +36,8 @@ struct AecEncArgs {
     uint64_t *tile_end;         /* [ntiles] absolute end bit of each tile */
     uint32_t *tile_kagg;        /* [ntiles] clamp pair (lo | hi<<8) of each tile, independent of the seed */
     uint64_t *rsi_offsets;      /* optional [nrsi] absolute start bit of each RSI */
+    uint64_t *grp_index;        /* optional [nrsi*32] group index for the warp-per-RSI decoder (see AecDecArgs) */
+    uint32_t grp_G;             /* blocks per group = ceil(rsi / 32) */
     uint64_t *result;           /* [0] end bit, [1] k after the last block, [2..4] shard summary (lo, hi, first constant tile) */
 };
 
@@ -49,8 +51,17 @@ struct AecDecArgs {
     uint8_t *out;               /* decoded samples, device */
     uint64_t out_samples;       /* samples wanted in total */
     uint32_t out_aligned;       /* out is 16-byte aligned */
-    uint64_t *result;           /* [0] samples delivered (contiguous prefix), [1] status flags */
+    uint64_t *result;           /* [0] ~(first sample position that fell short) or 0, [1] status flags */
     uint32_t *rsi_count;        /* [nrsi] samples each RSI delivered */
+    /* Group index: entry [r*32 + l] describes the G = ceil(rsi/32) blocks lane l of the
+     * warp that decodes RSI r owns: bits 55..0 = absolute bit offset of the first CDS
+     * to parse, bits 63..56 = leading blocks that still belong to a zero run started
+     * in an earlier group (they are zero and have no CDS of their own). */
+    const uint64_t *grp_index;
+    uint32_t grp_G;
+    /* careful (lane-per-RSI) kernel only: decode the RSIs listed here instead of 0..nrsi */
+    uint32_t *rsi_list;         /* [nrsi] */
+    uint32_t *rsi_list_count;
 };
 
 uint32_t aec_encode_tile_blocks(uint32_t J);
@@ -62,6 +73,12 @@ cudaError_t aec_encode_summary_launch(const AecEncArgs &a, cudaStream_t st);
 cudaError_t aec_place_bits_launch(const uint32_t *src, uint64_t nbits, uint32_t *dst, uint64_t dst_bit, uint64_t dst_cap_words, cudaStream_t st);
 
 cudaError_t aec_decode_launch(const AecDecArgs &a, int num_sms, cudaStream_t st);
+uint32_t aec_decode_group_blocks(const AecCfg &c);     /* G = ceil(rsi / 32) */
+uint32_t aec_decode_warp_warps(const AecCfg &c);       /* 0 when the fast kernel cannot be used */
+/* fast path: one warp per RSI from the group index; RSIs it cannot finish are appended to rsi_list */
+cudaError_t aec_decode_warp_launch(const AecDecArgs &a, int num_sms, cudaStream_t st);
+/* build the group index of RSIs whose start offsets are known (one lane skims one RSI) */
+cudaError_t aec_build_group_index_launch(const AecDecArgs &a, uint64_t *grp_index, cudaStream_t st);
 /* Sequential RSI-boundary scan for streams without an offset index:
  * fills offsets[0..max_rsi) and result[0] = RSIs found, result[1] = status. */
 cudaError_t aec_scan_offsets_launch(const AecCfg &c, const uint32_t *in_words, uint64_t in_bytes,

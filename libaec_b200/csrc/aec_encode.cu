@@ -340,7 +340,8 @@ aec_encode_kernel(const AecEncArgs a)
         uint32_t ball = __ballot_sync(FULL, is_zero);
         if (lane == 0) s_zb[warp] = ball;
         pair_barrier(warp);
-        uint32_t len = bi.len, zcode = 0, zref = 0;
+        uint32_t len = bi.len, zcode = 0, zref = 0, zrun = 0;
+        bool zinherit = false;              /* zero block that is not the first of its run */
         if (is_zero) {
             uint64_t m64 = (uint64_t)s_zb[warp & ~1u] | ((uint64_t)s_zb[warp | 1u] << 32);
             uint32_t q = tid & 63u;                       /* position in the aligned 64-slot group */
@@ -349,7 +350,8 @@ aec_encode_kernel(const AecEncArgs a)
             uint32_t V = nblk - seg * 64u; if (V > 64u) V = 64u;
             uint64_t segmask = (m64 >> g0);
             if (V < 64u) segmask &= ((1ull << V) - 1ull);
-            len = aec_zero_run(c, segmask, V, b, &zcode, &zref);
+            len = aec_zero_run(c, segmask, V, b, &zcode, &zref, &zrun);
+            zinherit = (b & 63u) != 0 && ((segmask >> ((b & 63u) - 1u)) & 1ull);
         }
         if (zref) {   /* run owner needs the reference sample of block 0 of the RSI */
             uint64_t f0 = rsi_idx * (uint64_t)c.R;
@@ -500,7 +502,19 @@ aec_encode_kernel(const AecEncArgs a)
 
         /* ---- stream the tile's words out, shifted to the absolute bit phase ---- */
         const uint64_t base = s_base;
-        if (valid && b == 0 && a.rsi_offsets) a.rsi_offsets[rsi_idx] = late ? myoff + base_l : base + myoff;
+        const uint64_t myabs = late ? myoff + base_l : base + myoff;
+        if (valid && b == 0 && a.rsi_offsets) a.rsi_offsets[rsi_idx] = myabs;
+        if (a.grp_index && valid) {
+            /* group index for the warp-per-RSI decoder (aec_device.h) */
+            const uint32_t G = a.grp_G;
+            if (b % G == 0 && !zinherit) a.grp_index[rsi_idx * 32ull + b / G] = myabs;
+            if (is_zero && len && zrun > 1) {
+                /* I own a zero run: group starts inside it inherit their leading blocks from me */
+                uint32_t b0 = b + 1u - zrun;
+                for (uint32_t g = (b0 / G + 1u) * G; g <= b; g += G)
+                    a.grp_index[rsi_idx * 32ull + g / G] = ((uint64_t)(b - g + 1u) << 56) | (myabs + len);
+            }
+        }
         uint32_t nsl;
         {
             const uint64_t end = aec_papply(ptile, late ? base : 0ull) + (late ? 0ull : base);

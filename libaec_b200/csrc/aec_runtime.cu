@@ -54,9 +54,10 @@ struct aecb200_ctx {
     uint64_t launches = 0;
     char err[256] = {0};
 
-    DevBuf desc, pref, headc, tailc, tile_end, tile_kagg, misc, in_stage, out_stage, offs, rsi_count;
+    DevBuf grp, rsi_list, desc, pref, headc, tailc, tile_end, tile_kagg, misc, in_stage, out_stage, offs, rsi_count;
     uint64_t tile_limit = 0;             /* next encode codes only this many leading tiles (k repair) */
     bool want_summary = false;
+    bool careful_only = false;           /* decode with the lane-per-RSI kernel only (tests) */
     uint64_t *h_res = nullptr;           /* pinned: [0..3] encode result, [4..7] decode result */
 
     /* bookkeeping of the last enqueued operation */
@@ -154,7 +155,7 @@ void aecb200_ctx_destroy(aecb200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    ctx->tile_kagg.release(); ctx->pref.release();
+    ctx->tile_kagg.release(); ctx->pref.release(); ctx->grp.release(); ctx->rsi_list.release();
     ctx->desc.release(); ctx->headc.release(); ctx->tailc.release(); ctx->tile_end.release();
     ctx->misc.release(); ctx->in_stage.release(); ctx->out_stage.release(); ctx->offs.release();
     ctx->rsi_count.release();
@@ -194,6 +195,23 @@ int aecb200_encode_device(aecb200_ctx *ctx, const aecb200_params *p,
                           const void *d_in, size_t in_bytes,
                           void *d_out, size_t out_cap,
                           const aecb200_carry *carry, uint64_t *d_rsi_offsets)
+{
+    return aecb200_encode_device_indexed(ctx, p, d_in, in_bytes, d_out, out_cap, carry, d_rsi_offsets, nullptr);
+}
+
+size_t aecb200_group_index_entries(const aecb200_params *p, size_t in_bytes)
+{
+    AecCfg c;
+    if (aec_cfg_init(&c, p->bits_per_sample, p->block_size, p->rsi, p->flags, 0, 0) != 0 || c.R == 0) return 0;
+    size_t ns = in_bytes / c.B;
+    return ((ns + c.R - 1) / c.R) * 32;
+}
+
+int aecb200_encode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
+                                  const void *d_in, size_t in_bytes,
+                                  void *d_out, size_t out_cap,
+                                  const aecb200_carry *carry, uint64_t *d_rsi_offsets,
+                                  uint64_t *d_grp_index)
 {
     if (!ctx || !p) return AEC_CONF_ERROR;
     AecCfg c;
@@ -254,6 +272,8 @@ int aecb200_encode_device(aecb200_ctx *ctx, const aecb200_params *p,
     a.tile_end = (uint64_t *)ctx->tile_end.p;
     a.tile_kagg = (uint32_t *)ctx->tile_kagg.p;
     a.rsi_offsets = d_rsi_offsets;
+    a.grp_index = d_grp_index;
+    a.grp_G = aec_decode_group_blocks(c);
     const bool repair = a.ntiles < a.ntiles_total;
     CK(aec_encode_launch(a, ctx->num_sms, ctx->stream), "encode launch");
     ctx->launches += 2;
@@ -307,6 +327,15 @@ int aecb200_decode_device(aecb200_ctx *ctx, const aecb200_params *p,
                           const uint64_t *d_rsi_offsets, size_t nrsi,
                           void *d_out, size_t out_bytes)
 {
+    return aecb200_decode_device_indexed(ctx, p, d_in, in_bytes, d_rsi_offsets, nrsi, nullptr, d_out, out_bytes);
+}
+
+int aecb200_decode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
+                                  const void *d_in, size_t in_bytes,
+                                  const uint64_t *d_rsi_offsets, size_t nrsi,
+                                  const uint64_t *d_grp_index,
+                                  void *d_out, size_t out_bytes)
+{
     if (!ctx || !p) return AEC_CONF_ERROR;
     AecCfg c;
     int rc = make_cfg(ctx, p, 0, &c);
@@ -326,10 +355,10 @@ int aecb200_decode_device(aecb200_ctx *ctx, const aecb200_params *p,
     uint64_t *res = (uint64_t *)((uint8_t *)ctx->misc.p + 128);
     /* delivered = min(out_samples, RSIs available * R) unless a lane reports less:
      * lanes that fall short atomicMax the complement of their position into
-     * res[0] (zero = nobody fell short), flags go to res[1] */
+     * res[0] (zero = nobody fell short), flags go to res[1], res[2] = hand-over count */
     uint64_t avail = need_rsi * (uint64_t)c.R;
     ctx->dec_expect = out_samples < avail ? out_samples : avail;
-    CK(cudaMemsetAsync(res, 0, 16, ctx->stream), "memset(result)");
+    CK(cudaMemsetAsync(res, 0, 32, ctx->stream), "memset(result)");
     if (need_rsi) {
         AecDecArgs a;
         memset(&a, 0, sizeof a);
@@ -343,12 +372,31 @@ int aecb200_decode_device(aecb200_ctx *ctx, const aecb200_params *p,
         a.out_aligned = (((uintptr_t)d_out & 3u) == 0) ? 1u : 0u;
         a.result = res;
         a.rsi_count = nullptr;
+        a.grp_G = aec_decode_group_blocks(c);
+        const bool fast = aec_decode_warp_warps(c) != 0 && need_rsi < 0xFFFFFFFFull && !ctx->careful_only;
+        if (fast) {
+            /* warp-per-RSI kernel from the group index; what it cannot finish goes to the careful kernel */
+            CK(ctx->rsi_list.ensure(need_rsi * 4), "cudaMalloc(rsi_list)");
+            a.rsi_list = (uint32_t *)ctx->rsi_list.p;
+            a.rsi_list_count = (uint32_t *)(res + 2);
+            if (!d_grp_index) {
+                CK(ctx->grp.ensure(need_rsi * 32 * 8), "cudaMalloc(group index)");
+                CK(aec_build_group_index_launch(a, (uint64_t *)ctx->grp.p, ctx->stream), "group index launch");
+                ctx->launches += 1;
+                d_grp_index = (const uint64_t *)ctx->grp.p;
+            }
+            a.grp_index = d_grp_index;
+            CK(aec_decode_warp_launch(a, ctx->num_sms, ctx->stream), "decode (warp) launch");
+            ctx->launches += 1;
+        }
         CK(aec_decode_launch(a, ctx->num_sms, ctx->stream), "decode launch");
         ctx->launches += 1;
     }
-    CK(cudaMemcpyAsync(&ctx->h_res[4], res, 16, cudaMemcpyDeviceToHost, ctx->stream), "memcpy(result)");
+    CK(cudaMemcpyAsync(&ctx->h_res[4], res, 24, cudaMemcpyDeviceToHost, ctx->stream), "memcpy(result)");
     return AEC_OK;
 }
+
+void aecb200_ctx_set_careful_decode(aecb200_ctx *ctx, int on) { if (ctx) ctx->careful_only = on != 0; }
 
 int aecb200_decode_finish(aecb200_ctx *ctx, size_t *out_written)
 {

@@ -100,7 +100,7 @@ extern "C" int model_encode(uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags
                 uint32_t V = nblk - seg * 64u; if (V > 64u) V = 64u;
                 uint64_t segmask = m64 >> g0;
                 if (V < 64u) segmask &= ((1ull << V) - 1ull);
-                s.len = aec_zero_run(c, segmask, V, s.b, &s.zcode, &s.zref);
+                uint32_t rl = 0; s.len = aec_zero_run(c, segmask, V, s.b, &s.zcode, &s.zref, &rl);
                 if (s.zref) s.refs = aec_load_sample(in + s.rsi_idx * (uint64_t)c.R * c.B, c.B, c.msb);
             }
         }

@@ -241,7 +241,8 @@ def _device_roundtrip(torch, codec, name, nsamples, check_oracle):
     R = p.rsi * p.block_size
     nrsi = (nsamples + R - 1) // R
     d_offs = torch.empty(nrsi, dtype=torch.int64, device="cuda")
-    assert codec.encode_enqueue(p, d_in, raw.size, d_out, d_offs) == 0
+    d_grp = torch.zeros(codec.group_index_entries(p, raw.size), dtype=torch.int64, device="cuda")
+    assert codec.encode_enqueue(p, d_in, raw.size, d_out, d_offs, d_grp=d_grp) == 0
     st, bits, _ = codec.encode_finish()
     assert st == 0
     nbytes = (bits + 7) // 8
@@ -250,13 +251,18 @@ def _device_roundtrip(torch, codec, name, nsamples, check_oracle):
         want = po.orc_encode(po.Params(p.bits_per_sample, p.block_size, p.rsi, p.flags), raw, want_offsets=True)
         assert np.array_equal(comp, want["out"]), name
         assert np.array_equal(d_offs.cpu().numpy().astype(np.uint64), want["offsets"]), name
-    d_back = torch.empty(raw.size + 16, dtype=torch.uint8, device="cuda")
-    assert codec.decode_enqueue(p, d_out, nbytes, d_offs, nrsi, d_back, raw.size) == 0
-    st, written = codec.decode_finish()
-    assert st == 0 and written == raw.size
-    back = d_back[:raw.size].cpu().numpy()
-    # decode == input for unsigned / full-width signed data (sign extension is a no-op here)
-    assert np.array_equal(back, raw), name
+    # three decode routes must agree bit for bit: warp-per-RSI kernel from the encoder's group
+    # index, the same kernel from an index rebuilt on the device, and the careful kernel alone
+    for route in ("encoder-index", "rebuilt-index", "careful"):
+        d_back = torch.zeros(raw.size + 16, dtype=torch.uint8, device="cuda")
+        codec.set_careful_decode(route == "careful")
+        grp = d_grp if route == "encoder-index" else None
+        assert codec.decode_enqueue(p, d_out, nbytes, d_offs, nrsi, d_back, raw.size, d_grp=grp) == 0
+        st, written = codec.decode_finish()
+        assert st == 0 and written == raw.size, (name, route)
+        # decode == input for unsigned / full-width signed data (sign extension is a no-op here)
+        assert np.array_equal(d_back[:raw.size].cpu().numpy(), raw), (name, route)
+    codec.set_careful_decode(False)
     # the sequential boundary scan finds the same index
     if nrsi <= 4096:
         d_offs2 = torch.zeros(nrsi, dtype=torch.int64, device="cuda")
@@ -275,6 +281,34 @@ def test_device_path_configs_vs_oracle(torch_cuda, name):
     ns = (8 << 20) // p.bytes_per_sample
     ns -= ns % 7          # make the last RSI short
     _device_roundtrip(torch_cuda, codec, name, ns, True)
+    codec.close()
+
+
+def test_device_decode_routes_random_cases(torch_cuda):
+    """Warp-per-RSI decode (exact iterative inverse predictor) vs oracle on the random sweep:
+    clipping-heavy distributions, signed data with sign extension, every storage layout."""
+    torch = torch_cuda
+    codec = L.DeviceCodec()
+    for seed in range(300):
+        p, raw = random_case(7000 + seed)
+        B = p.bytes_per_sample
+        ns = len(raw) // B
+        if ns == 0:
+            continue
+        want = po.orc_encode(p, raw, want_offsets=True)
+        comp = want["out"]
+        pad = np.zeros((comp.size + 3) // 4 * 4 + 8, np.uint8)
+        pad[:comp.size] = comp
+        d_comp = torch.from_numpy(pad).cuda()
+        d_offs = torch.from_numpy(want["offsets"].astype(np.int64)).cuda()
+        ref = po.orc_decode(p, comp, ns * B)
+        for careful in (False, True):
+            codec.set_careful_decode(careful)
+            d_back = torch.zeros(ns * B + 16, dtype=torch.uint8, device="cuda")
+            assert codec.decode_enqueue(P(p), d_comp, comp.size, d_offs, d_offs.numel(), d_back, ns * B) == 0
+            st, written = codec.decode_finish()
+            assert st == ref["status"] and written == ref["out"].size, (seed, p, careful)
+            assert np.array_equal(d_back[:written].cpu().numpy(), ref["out"]), (seed, p, careful)
     codec.close()
 
 
