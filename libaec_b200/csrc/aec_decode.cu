@@ -148,10 +148,12 @@ constexpr int DW_MAX_WARPS = 4;      /* warps (= RSIs) per CTA; fewer when rows 
 /* Bit reader with a 64-bit left-aligned window refilled one word at a time. */
 struct Rd64 {
     const uint32_t *w;
-    uint32_t nwords, widx;
+    uint32_t nwords, widx;       /* widx: index of the word held in `nextw` */
+    uint32_t nextw;              /* prefetched: loaded one refill ahead so its latency hides behind ~32 bits of decoding */
     uint64_t acc;
     int nb;
-    __device__ __forceinline__ uint32_t ld(uint32_t i) const { return i < nwords ? __byte_perm(__ldg(w + i), 0, 0x0123) : 0u; }
+    __device__ __forceinline__ uint32_t ldraw(uint32_t i) const { return i < nwords ? __ldg(w + i) : 0u; }
+    __device__ __forceinline__ uint32_t ld(uint32_t i) const { return __byte_perm(ldraw(i), 0, 0x0123); }
     __device__ __forceinline__ void init(const uint32_t *base, uint32_t nw, uint64_t bitpos)
     {
         w = base; nwords = nw;
@@ -160,11 +162,18 @@ struct Rd64 {
         acc = (((uint64_t)ld(widx) << 32) | ld(widx + 1)) << sh;
         nb = 64 - (int)sh;
         widx += 2;
+        nextw = ldraw(widx);
     }
     __device__ __forceinline__ void refill()
     {
-        if (nb <= 32) { acc |= (uint64_t)ld(widx) << (32 - nb); widx++; nb += 32; }
+        if (nb <= 32) {
+            acc |= (uint64_t)__byte_perm(nextw, 0, 0x0123) << (32 - nb);
+            nb += 32;
+            widx++;
+            nextw = ldraw(widx);      /* consumed at the next refill: the load latency stays off the chain */
+        }
     }
+    /* bit position of the next unread bit (nextw is not part of the window yet) */
     __device__ __forceinline__ uint64_t pos() const { return (uint64_t)widx * 32ull - (uint64_t)nb; }
     /* n in 1..32 */
     __device__ __forceinline__ uint32_t get(uint32_t n)
@@ -195,16 +204,20 @@ struct Rd64 {
 /* One block of J mapped values into row[0..J): fast restatement of
  * aec_decode_block for clean streams (anything unusual sets *bad and the RSI
  * is handed to the careful kernel). */
+__device__ __forceinline__ uint32_t delta_of(uint32_t dv) { return (dv >> 1) ^ (0u - (dv & 1u)); }   /* +h even, -h odd */
+
+/* returns the wrapping sum of the block's deltas (reference sample excluded) */
 template <int JT>
-__device__ __forceinline__ void warp_decode_block(const AecCfg &c, Rd64 &rd, uint32_t b, uint32_t *row,
-                                                  uint32_t &zero_left, uint32_t *bad)
+__device__ __forceinline__ uint32_t warp_decode_block(const AecCfg &c, Rd64 &rd, uint32_t b, uint32_t *row,
+                                                      uint32_t &zero_left, uint32_t *bad)
 {
     const uint32_t J = JT ? (uint32_t)JT : c.J;
+    uint32_t dsum = 0;
     if (zero_left) {
         zero_left--;
 #pragma unroll 4
         for (uint32_t i = 0; i < J; i++) row[i] = 0;
-        return;
+        return 0;
     }
     const uint32_t ref = (c.pp && b == 0) ? 1u : 0u;
     const uint32_t id = rd.get(c.idl);
@@ -219,7 +232,7 @@ __device__ __forceinline__ void warp_decode_block(const AecCfg &c, Rd64 &rd, uin
             zero_left = zb - 1u;
 #pragma unroll 4
             for (uint32_t i = ref; i < J; i++) row[i] = 0;
-            return;
+            return 0;
         }
         uint32_t i = ref;
         while (i < J) {
@@ -229,24 +242,64 @@ __device__ __forceinline__ void warp_decode_block(const AecCfg &c, Rd64 &rd, uin
             while (s * (s + 1u) / 2u > m) s--;
             while ((s + 1u) * (s + 2u) / 2u <= m) s++;
             uint32_t d1 = m - s * (s + 1u) / 2u;
-            if ((i & 1u) == 0) { row[i] = s - d1; i++; }
-            row[i] = d1; i++;
+            if ((i & 1u) == 0) { row[i] = s - d1; dsum += delta_of(s - d1); i++; }
+            row[i] = d1; dsum += delta_of(d1); i++;
         }
-        return;
+        return dsum;
     }
     if (id == (1u << c.idl) - 1u) {
 #pragma unroll 4
-        for (uint32_t i = 0; i < J; i++) row[i] = rd.get(c.n);
-        return;
+        for (uint32_t i = 0; i < J; i++) { uint32_t v = rd.get(c.n); row[i] = v; if (i >= ref) dsum += delta_of(v); }
+        return dsum;
     }
     const uint32_t k = id - 1u;
     if (ref) row[0] = rd.get(c.n);
-#pragma unroll 4
-    for (uint32_t i = ref; i < J; i++) row[i] = rd.fs(bad) << k;
-    if (k) {
-#pragma unroll 4
-        for (uint32_t i = ref; i < J; i++) row[i] += rd.get(k);
+    /* unary part: after a refill the window holds >= 32 valid bits; decode every code that
+     * completes inside it before touching the 64-bit accumulator again */
+    {
+        uint32_t i = ref, pend = 0;
+        while (i < J) {
+            rd.refill();
+            uint32_t wnd = (uint32_t)(rd.acc >> 32);
+            uint32_t left = 32;
+            while (wnd != 0 && i < J) {
+                uint32_t z = (uint32_t)__clz((int)wnd);
+                row[i++] = (pend + z) << k;
+                pend = 0;
+                wnd = (wnd << z) << 1;
+                left -= z + 1u;
+            }
+            uint32_t used = 32u - left;
+            if (i < J) { pend += left; used = 32u; if (rd.widx > rd.nwords + 2u) { *bad = 1u; break; } }
+            rd.acc <<= used; rd.nb -= (int)used;
+        }
     }
+    if (k == 0) {
+#pragma unroll 4
+        for (uint32_t i = ref; i < J; i++) dsum += delta_of(row[i]);
+        return dsum;
+    }
+    /* binary part: k low bits per sample, fetched four (k <= 8) or two (k <= 16) samples at a time */
+    uint32_t i = ref;
+    const uint32_t m = (1u << k) - 1u;
+    if (k <= 8) {
+        for (; i + 4 <= J; i += 4) {
+            uint32_t q = rd.get(4u * k);
+            uint32_t v0 = row[i] + (q >> (3u * k)), v1 = row[i + 1] + ((q >> (2u * k)) & m);
+            uint32_t v2 = row[i + 2] + ((q >> k) & m), v3 = row[i + 3] + (q & m);
+            row[i] = v0; row[i + 1] = v1; row[i + 2] = v2; row[i + 3] = v3;
+            dsum += delta_of(v0) + delta_of(v1) + delta_of(v2) + delta_of(v3);
+        }
+    } else if (k <= 16) {
+        for (; i + 2 <= J; i += 2) {
+            uint32_t q = rd.get(2u * k);
+            uint32_t v0 = row[i] + (q >> k), v1 = row[i + 1] + (q & m);
+            row[i] = v0; row[i + 1] = v1;
+            dsum += delta_of(v0) + delta_of(v1);
+        }
+    }
+    for (; i < J; i++) { uint32_t v = row[i] + rd.get(k); row[i] = v; dsum += delta_of(v); }
+    return dsum;
 }
 
 /* exact inverse mapper step on normalised values; sets clip when the clipped branch was taken */
@@ -303,15 +356,7 @@ aec_decode_warp_kernel(const AecDecArgs a)
                 lead--;
                 for (uint32_t i = 0; i < J; i++) rw[i] = 0;
             } else {
-                warp_decode_block<JT>(c, rd, b0 + q, rw, zero_left, &bad);
-            }
-            if (c.pp) {
-                uint32_t i0 = (b0 + q == 0) ? 1u : 0u;      /* sample 0 of the RSI is the reference */
-#pragma unroll 4
-                for (uint32_t i = i0; i < J; i++) {
-                    uint32_t dv = rw[i];
-                    sum += (dv >> 1) ^ (0u - (dv & 1u));     /* +h for even d, -h for odd d */
-                }
+                sum += warp_decode_block<JT>(c, rd, b0 + q, rw, zero_left, &bad);
             }
         }
         endpos = rd.pos();
@@ -331,8 +376,11 @@ aec_decode_warp_kernel(const AecDecArgs a)
     const uint32_t sflip = c.sext ? (1u << (c.n - 1)) : 0u;
     if (!bad && c.pp) {
         /* ---- unit-delay predictor undone in parallel: every lane walks its samples with the
-         * exact map from a speculated start value; start values are re-derived from the lanes'
-         * results until every lane starts where its predecessor ended ---- */
+         * exact inverse map from a speculated start value.  The first walk is optimistic (start
+         * values from the prefix sum of the deltas, exact whenever no sample clips) and writes
+         * the normalised samples in place; if a lane did not start where its predecessor ended,
+         * the mapped values are recovered (the map is a bijection) and the start values are
+         * re-derived from the lanes' results until they agree. ---- */
         uref = __shfl_sync(FULL, uref, 0);
         uint32_t inc = sum;
 #pragma unroll
@@ -340,42 +388,47 @@ aec_decode_warp_kernel(const AecDecArgs a)
             uint32_t o = __shfl_up_sync(FULL, inc, off);
             if (lane >= (uint32_t)off) inc += o;
         }
-        uint32_t us = uref + (inc - sum);              /* speculated value before my first sample */
+        /* speculated value before my first sample; kept inside [0, M] so that every walk stays in the
+         * mapper's domain and the mapped values can be recovered exactly after a wrong guess */
+        uint32_t us = (uref + (inc - sum)) & c.mask;
         const uint32_t n_s = nblk * J;
-        for (int iter = 0; iter < 34; iter++) {
-            uint32_t u = us, clip = 0;
-            uint32_t i = 0;
-            if (lane == 0) { u = uref; i = 1; }
-            for (; i < n_s; i++) u = unmap_step(u, row[i], c.mask, clip);
-            /* consistent when every lane started at its predecessor's end */
-            uint32_t uprev = __shfl_up_sync(FULL, u, 1);
-            bool ok = (lane == 0) || (n_s == 0) || (uprev == us);
-            if (__all_sync(FULL, ok)) break;
-            /* new start values: absolute after a lane that clipped, relative otherwise
-             * (segmented inclusive scan of (reset, value)) */
-            uint32_t val = clip ? u : (u - us);        /* absolute end, or my net offset */
-            uint32_t rst = clip;
-            if (lane == 0) { val = u; rst = 1u; }
+        const uint32_t i_first = (lane == 0) ? 1u : 0u;
+        if (lane == 0) us = uref;
+        uint32_t u = us, clip = 0;
+        if (lane == 0 && n_s) row[0] = uref;
+#pragma unroll 4
+        for (uint32_t i = i_first; i < n_s; i++) { u = unmap_step(u, row[i], c.mask, clip); row[i] = u; }
+        uint32_t uprev = __shfl_up_sync(FULL, u, 1);
+        bool ok = (lane == 0) || (n_s == 0) || (uprev == us);
+        if (!__all_sync(FULL, ok)) {
+            /* recover the mapped values from the (wrongly started) samples */
+            uint32_t pv = us;
+            for (uint32_t i = i_first; i < n_s; i++) { uint32_t cur = row[i]; row[i] = aec_map_delta(pv, cur, c.mask); pv = cur; }
+            for (int iter = 0; iter < 34; iter++) {
+                /* new start values: absolute after a lane that clipped, relative otherwise
+                 * (segmented inclusive scan of (reset, value)) */
+                uint32_t val = clip ? u : (u - us);    /* absolute end, or my net offset */
+                uint32_t rst = clip;
+                if (lane == 0) { val = u; rst = 1u; }
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                uint32_t ov = __shfl_up_sync(FULL, val, off);
-                uint32_t orst = __shfl_up_sync(FULL, rst, off);
-                if (lane >= (uint32_t)off && !rst) { val += ov; rst = orst; }
+                for (int off = 1; off < 32; off <<= 1) {
+                    uint32_t ov = __shfl_up_sync(FULL, val, off);
+                    uint32_t orst = __shfl_up_sync(FULL, rst, off);
+                    if (lane >= (uint32_t)off && !rst) { val += ov; rst = orst; }
+                }
+                uint32_t nus = __shfl_up_sync(FULL, val, 1);   /* predecessor's (speculated) end */
+                if (lane > 0) us = nus & c.mask;
+                u = us; clip = 0;
+                for (uint32_t i = i_first; i < n_s; i++) u = unmap_step(u, row[i], c.mask, clip);
+                uprev = __shfl_up_sync(FULL, u, 1);
+                ok = (lane == 0) || (n_s == 0) || (uprev == us);
+                if (__all_sync(FULL, ok)) break;
+                if (iter == 33) bad = 1u;              /* cannot happen: at least one more lane settles per round */
             }
-            uint32_t nus = __shfl_up_sync(FULL, val, 1);   /* predecessor's (speculated) end */
-            if (lane > 0) us = nus;
-            if (iter == 33) bad = 1u;                  /* cannot happen: at least one lane settles per round */
-        }
-        bad = __any_sync(FULL, bad) ? 1u : 0u;
-        if (!bad) {
-            /* final walk: samples in place */
-            uint32_t u = us, clip = 0, i = 0;
-            if (lane == 0) { u = uref; i = 1; uint32_t x = uref ^ sflip; if (c.sext && c.n < 32 && ((x >> (c.n - 1)) & 1u)) x |= ~c.mask; row[0] = x; }
-            for (; i < n_s; i++) {
-                u = unmap_step(u, row[i], c.mask, clip);
-                uint32_t x = u ^ sflip;
-                if (c.sext && c.n < 32 && ((x >> (c.n - 1)) & 1u)) x |= ~c.mask;
-                row[i] = x;
+            bad = __any_sync(FULL, bad) ? 1u : 0u;
+            if (!bad) {
+                u = us; clip = 0;
+                for (uint32_t i = i_first; i < n_s; i++) { u = unmap_step(u, row[i], c.mask, clip); row[i] = u; }
             }
         }
     }
@@ -386,20 +439,34 @@ aec_decode_warp_kernel(const AecDecArgs a)
     __syncwarp();
     /* ---- cooperative store of the RSI's R samples (contiguous in the output) ---- */
     uint32_t *wrows = rows + (size_t)warp * 32u * stride;
+    const bool sxt = c.sext && c.n < 32;
     if (JT != 0 && a.out_aligned && (GJ % 4u) == 0) {
         constexpr int SPG = (B == 4) ? 1 : ((B == 2) ? 2 : 4);
         const uint32_t ngroups = c.R / SPG;
+        const bool pow2 = (GJ & (GJ - 1u)) == 0;
+        const uint32_t gsh = 31u - (uint32_t)__clz((int)GJ);
         for (uint32_t g = lane; g < ngroups; g += 32) {
             uint32_t s0 = g * SPG;
-            uint32_t rowi = s0 / GJ, col = s0 % GJ;
+            uint32_t rowi = pow2 ? (s0 >> gsh) : (s0 / GJ);
+            uint32_t col = pow2 ? (s0 & (GJ - 1u)) : (s0 % GJ);
             const uint32_t *src = wrows + (size_t)rowi * stride + col;
             uint32_t sv[4] = {src[0], SPG > 1 ? src[1] : 0u, SPG > 2 ? src[2] : 0u, SPG > 2 ? src[3] : 0u};
+            if (c.pp) {
+#pragma unroll
+                for (int j = 0; j < SPG; j++) {
+                    uint32_t x = sv[j] ^ sflip;                     /* back to the n-bit pattern */
+                    if (sxt && ((x >> (c.n - 1)) & 1u)) x |= ~c.mask; /* decode.c:78-84, :131 */
+                    sv[j] = x;
+                }
+            }
             store_group<B>(a.out, startS + s0, sv, c.msb);
         }
     } else {
         for (uint32_t s0 = lane; s0 < c.R; s0 += 32) {
             uint32_t rowi = s0 / GJ, col = s0 % GJ;
-            aec_store_sample(a.out + (startS + s0) * c.B, wrows[(size_t)rowi * stride + col], c.B, c.msb);
+            uint32_t x = wrows[(size_t)rowi * stride + col];
+            if (c.pp) { x ^= sflip; if (sxt && ((x >> (c.n - 1)) & 1u)) x |= ~c.mask; }
+            aec_store_sample(a.out + (startS + s0) * c.B, x, c.B, c.msb);
         }
     }
 }
