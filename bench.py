@@ -263,7 +263,7 @@ def run_ours(args):
         if sharded is not None:
             sharded.encode(d_raw, raw.size)
             b.record()
-            sharded.codec.decode_enqueue(p, sharded.local, comp_bytes, sharded.offsets, nrsi, d_back, raw.size)
+            sharded.decode_enqueue(d_back, raw.size)
         else:
             codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs, d_grp=d_grp)
             b.record()

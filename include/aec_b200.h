@@ -110,12 +110,15 @@ int aecb200_encode_finish(aecb200_ctx *ctx, aecb200_carry *end);
  * with the true k in the carry), then moves its stream to its bit offset in the
  * global stream with aecb200_place_bits_device. */
 void aecb200_ctx_set_shard_mode(aecb200_ctx *ctx, int on);
-int  aecb200_encode_shard_info(aecb200_ctx *ctx, uint32_t *klo, uint32_t *khi, uint64_t *first_const_tile);
+/* tail64: the shard's last 64 bits, right-aligned (the next shard completes the word both share) */
+int  aecb200_encode_shard_info(aecb200_ctx *ctx, uint32_t *klo, uint32_t *khi, uint64_t *first_const_tile,
+                               uint64_t *tail64);
 void aecb200_ctx_set_tile_limit(aecb200_ctx *ctx, uint64_t ntiles);
 /* d_dst[dst_bit ..) = d_src[0 .. nbits) (bit 0 = MSB of byte 0); whole destination
- * words are written, bits outside the range are zero.  Asynchronous. */
+ * words are written, bits after the range are zero and the dst_bit % 32 bits in
+ * front of it are taken from head_or (the predecessor shard's tail).  Asynchronous. */
 int  aecb200_place_bits_device(aecb200_ctx *ctx, const void *d_src, uint64_t nbits,
-                               void *d_dst, size_t dst_cap, uint64_t dst_bit);
+                               void *d_dst, size_t dst_cap, uint64_t dst_bit, uint32_t head_or);
 
 /* Enqueue the decode of out_bytes/bytes_per_sample samples from the stream at
  * d_in using the RSI start offsets d_rsi_offsets[0..nrsi).  Asynchronous. */

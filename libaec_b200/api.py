@@ -382,17 +382,17 @@ class DeviceCodec:
         self.lib.aecb200_ctx_set_shard_mode(self.ctx, C.c_int(int(on)))
 
     def shard_info(self):
-        lo, hi, fc = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
-        self.lib.aecb200_encode_shard_info(self.ctx, C.byref(lo), C.byref(hi), C.byref(fc))
-        return int(lo.value), int(hi.value), int(fc.value)
+        lo, hi, fc, tail = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+        self.lib.aecb200_encode_shard_info(self.ctx, C.byref(lo), C.byref(hi), C.byref(fc), C.byref(tail))
+        return int(lo.value), int(hi.value), int(fc.value), int(tail.value)
 
     def set_tile_limit(self, ntiles: int):
         self.lib.aecb200_ctx_set_tile_limit(self.ctx, C.c_uint64(ntiles))
 
-    def place_bits(self, d_src, nbits: int, d_dst, dst_bit: int):
+    def place_bits(self, d_src, nbits: int, d_dst, dst_bit: int, head_or: int = 0):
         st = self.lib.aecb200_place_bits_device(
             self.ctx, C.c_void_p(d_src.data_ptr()), C.c_uint64(nbits), C.c_void_p(d_dst.data_ptr()),
-            C.c_size_t(d_dst.numel() * d_dst.element_size()), C.c_uint64(dst_bit))
+            C.c_size_t(d_dst.numel() * d_dst.element_size()), C.c_uint64(dst_bit), C.c_uint32(head_or))
         return self._check(st, "aecb200_place_bits_device")
 
     def decode_enqueue(self, p: Params, d_in, in_bytes: int, d_offsets, nrsi: int, d_out, out_bytes: int,

@@ -38,7 +38,7 @@ struct AecEncArgs {
     uint64_t *rsi_offsets;      /* optional [nrsi] absolute start bit of each RSI */
     uint64_t *grp_index;        /* optional [nrsi*32] group index for the warp-per-RSI decoder (see AecDecArgs) */
     uint32_t grp_G;             /* blocks per group = ceil(rsi / 32) */
-    uint64_t *result;           /* [0] end bit, [1] k after the last block, [2..4] shard summary (lo, hi, first constant tile) */
+    uint64_t *result;           /* [0] end bit, [1] k after the last block, [2..5] shard summary (lo, hi, first constant tile, last 64 bits) */
 };
 
 /* Arguments of one decode launch. */
@@ -70,7 +70,7 @@ cudaError_t aec_encode_launch(const AecEncArgs &a, int num_sms, cudaStream_t st)
 /* result[2..4] = clamp pair of the whole launch and the first tile after which k no longer depends on the seed */
 cudaError_t aec_encode_summary_launch(const AecEncArgs &a, cudaStream_t st);
 /* copy nbits bits from src (bit 0 = MSB of word 0) to dst starting at bit dst_bit; dst words are private to the caller */
-cudaError_t aec_place_bits_launch(const uint32_t *src, uint64_t nbits, uint32_t *dst, uint64_t dst_bit, uint64_t dst_cap_words, cudaStream_t st);
+cudaError_t aec_place_bits_launch(const uint32_t *src, uint64_t nbits, uint32_t *dst, uint64_t dst_bit, uint64_t dst_cap_words, uint32_t head_or, cudaStream_t st);
 
 cudaError_t aec_decode_launch(const AecDecArgs &a, int num_sms, cudaStream_t st);
 uint32_t aec_decode_group_blocks(const AecCfg &c);     /* G = ceil(rsi / 32) */

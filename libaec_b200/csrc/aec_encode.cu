@@ -614,12 +614,27 @@ __global__ void aec_encode_summary_kernel(const AecEncArgs a)
         a.result[2] = acc & 0xFFu;
         a.result[3] = acc >> 8;
         a.result[4] = (firstc == ~0ull) ? n : firstc;
+        /* last 64 bits of the stream, right-aligned: what the next shard needs to complete the
+         * word its own first bits share with this shard's last bits */
+        const uint64_t total = a.tile_end[n - 1];
+        const uint64_t endbyte = (total + 7) >> 3;
+        const uint8_t *pb = reinterpret_cast<const uint8_t *>(a.out_words);
+        uint64_t lo8 = 0, hi1 = 0;                      /* the last 9 bytes of the stream, big endian */
+        for (int j = 0; j < 9; j++) {
+            int64_t bi = (int64_t)endbyte - 9 + j;
+            uint64_t byte = (bi >= 0 && (uint64_t)bi < a.out_cap_bytes) ? pb[bi] : 0u;
+            if (j == 0) hi1 = byte; else lo8 = (lo8 << 8) | byte;
+        }
+        const uint32_t padb = (8u - (uint32_t)(total & 7u)) & 7u;   /* zero fill bits after the last stream bit */
+        uint64_t t64 = padb ? ((lo8 >> padb) | (hi1 << (64u - padb))) : lo8;
+        if (total < 64) t64 &= (total ? ((1ull << total) - 1ull) : 0ull);
+        a.result[5] = t64;
     }
 }
 
 /* dst[dst_bit ..) = src[0 .. nbits): one thread per destination word. */
 __global__ void aec_place_bits_kernel(const uint32_t *src, uint64_t nbits, uint32_t *dst, uint64_t dst_bit,
-                                      uint64_t dst_cap_words)
+                                      uint64_t dst_cap_words, uint32_t head_or)
 {
     const uint64_t w0 = dst_bit >> 5;
     const uint32_t sh = (uint32_t)(dst_bit & 31u);
@@ -633,7 +648,7 @@ __global__ void aec_place_bits_kernel(const uint32_t *src, uint64_t nbits, uint3
         /* clear bits past the end of the stream in the last word */
         uint64_t endbit = dst_bit + nbits;
         if (w0 + i == (endbit >> 5) && (endbit & 31u)) v &= ~(0xFFFFFFFFu >> (endbit & 31u));
-        if (i == 0 && sh) v &= (0xFFFFFFFFu >> sh);
+        if (i == 0 && sh) v = (v & (0xFFFFFFFFu >> sh)) | (head_or & ~(0xFFFFFFFFu >> sh));
         if (w0 + i < dst_cap_words) dst[w0 + i] = __byte_perm(v, 0, 0x0123);
     }
 }
@@ -695,12 +710,12 @@ cudaError_t aec_encode_summary_launch(const AecEncArgs &a, cudaStream_t st)
 }
 
 cudaError_t aec_place_bits_launch(const uint32_t *src, uint64_t nbits, uint32_t *dst, uint64_t dst_bit,
-                                  uint64_t dst_cap_words, cudaStream_t st)
+                                  uint64_t dst_cap_words, uint32_t head_or, cudaStream_t st)
 {
     uint64_t nw = ((dst_bit + nbits + 31) >> 5) - (dst_bit >> 5);
     if (nw == 0) return cudaSuccess;
     unsigned grid = (unsigned)((nw + 255) / 256 > 148 * 16 ? 148 * 16 : (nw + 255) / 256);
-    aec_place_bits_kernel<<<grid, 256, 0, st>>>(src, nbits, dst, dst_bit, dst_cap_words);
+    aec_place_bits_kernel<<<grid, 256, 0, st>>>(src, nbits, dst, dst_bit, dst_cap_words, head_or);
     return cudaGetLastError();
 }
 

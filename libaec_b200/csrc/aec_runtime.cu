@@ -283,7 +283,7 @@ int aecb200_encode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
     }
     ctx->tile_limit = 0;
     if (!repair)
-        CK(cudaMemcpyAsync(ctx->h_res, a.result, 40, cudaMemcpyDeviceToHost, ctx->stream), "memcpy(result)");
+        CK(cudaMemcpyAsync(ctx->h_res, a.result, 48, cudaMemcpyDeviceToHost, ctx->stream), "memcpy(result)");
     return AEC_OK;
 }
 
@@ -299,9 +299,11 @@ int aecb200_encode_finish(aecb200_ctx *ctx, aecb200_carry *end)
 
 void aecb200_ctx_set_shard_mode(aecb200_ctx *ctx, int on) { if (ctx) ctx->want_summary = on != 0; }
 
-int aecb200_encode_shard_info(aecb200_ctx *ctx, uint32_t *klo, uint32_t *khi, uint64_t *first_const_tile)
+int aecb200_encode_shard_info(aecb200_ctx *ctx, uint32_t *klo, uint32_t *khi, uint64_t *first_const_tile,
+                              uint64_t *tail64)
 {
     if (!ctx) return AEC_CONF_ERROR;
+    if (tail64) *tail64 = ctx->h_res[5];
     if (klo) *klo = (uint32_t)ctx->h_res[2];
     if (khi) *khi = (uint32_t)ctx->h_res[3];
     if (first_const_tile) *first_const_tile = ctx->h_res[4];
@@ -311,12 +313,12 @@ int aecb200_encode_shard_info(aecb200_ctx *ctx, uint32_t *klo, uint32_t *khi, ui
 void aecb200_ctx_set_tile_limit(aecb200_ctx *ctx, uint64_t ntiles) { if (ctx) ctx->tile_limit = ntiles; }
 
 int aecb200_place_bits_device(aecb200_ctx *ctx, const void *d_src, uint64_t nbits,
-                              void *d_dst, size_t dst_cap, uint64_t dst_bit)
+                              void *d_dst, size_t dst_cap, uint64_t dst_bit, uint32_t head_or)
 {
     if (!ctx) return AEC_CONF_ERROR;
     if ((((uintptr_t)d_src) & 3u) || (((uintptr_t)d_dst) & 3u)) return AEC_CONF_ERROR;
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    CK(aec_place_bits_launch((const uint32_t *)d_src, nbits, (uint32_t *)d_dst, dst_bit, dst_cap / 4, ctx->stream),
+    CK(aec_place_bits_launch((const uint32_t *)d_src, nbits, (uint32_t *)d_dst, dst_bit, dst_cap / 4, head_or, ctx->stream),
        "place launch");
     ctx->launches += 1;
     return AEC_OK;

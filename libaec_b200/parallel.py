@@ -5,17 +5,17 @@ the predictor and the zero-run logic reset at every RSI, so the only things
 that cross a shard boundary are the bit position and the split position k of
 the previous block.  Protocol per encode:
 
-  1. every rank codes its shard from carry (0 bits, k = 0)      [CUDA, no comm]
-  2. all_gather of (bits, klo, khi) per shard -- 24 bytes per rank  [NCCL]
+  1. every rank codes its shard from carry (0 bits, k = 0)          [CUDA, no comm]
+  2. ONE all_gather of (bits, klo, khi, last 64 bits) per shard -- 32 bytes
+     per rank                                                        [NCCL]
   3. a rank whose true incoming k is not 0 re-codes its leading tiles
      (the lengths do not depend on k, only the ids / split bits do)  [CUDA]
   4. every rank moves its stream to its bit offset in the global stream
-     (aecb200_place_bits_device, a funnel-shift copy)               [CUDA]
-  5. all_gather of each segment's first/last word; the word shared by two
-     shards is OR-merged into the later shard                       [NCCL]
+     (aecb200_place_bits_device, a funnel-shift copy) and completes its
+     first word with the predecessor's tail bits                     [CUDA]
 
-After step 5 rank r holds exactly the bytes [byte_lo(r), byte_hi(r)) of the
-single stream; the concatenation over ranks is byte-identical to the stream a
+After step 4 rank r holds exactly the bytes [4*word_lo, ...) of the single
+stream it owns; the concatenation over ranks is byte-identical to the stream a
 single GPU (or the CPU reference) produces for the whole input.  Decode needs
 no exchange at all: each rank decodes its RSIs from its own segment.
 
@@ -50,43 +50,61 @@ class ShardPlan:
     word_lo: int         # first 32-bit word of the global stream this rank owns
     word_hi: int         # one past the last word it owns
     total_bits: int
+    head_or: int         # predecessor bits that share this shard's first word (already in place)
+
+
+def boundary_bits(prev_tail64: int, bit_offset: int) -> int:
+    """The bit_offset % 32 bits in front of a shard inside its first word: the
+    last bits of the stream so far, taken from the predecessor's last 64 bits."""
+    n = bit_offset & 31
+    if n == 0:
+        return 0
+    return ((prev_tail64 & ((1 << n) - 1)) << (32 - n)) & 0xFFFFFFFF
 
 
 def plan_shards(infos, seed_k: int = 0):
-    """infos: per rank (bits, klo, khi).  Exclusive scan of the bit lengths and
-    the clamp chain of k (k_out = clamp(k_in, klo, khi))."""
+    """infos: per rank (bits, klo, khi[, tail64]).  Exclusive scan of the bit
+    lengths and the clamp chain of k (k_out = clamp(k_in, klo, khi)).
+    Shards must be at least 64 bits long unless they are empty."""
     plans = []
     off, k = 0, seed_k
-    total = sum(int(b) for b, _, _ in infos)
-    for r, (bits, lo, hi) in enumerate(infos):
-        bits, lo, hi = int(bits), int(lo), int(hi)
+    total = sum(int(i[0]) for i in infos)
+    prev_tail = 0
+    for r, info in enumerate(infos):
+        bits, lo, hi = int(info[0]), int(info[1]), int(info[2])
         end = off + bits
         last = r == len(infos) - 1
-        plans.append(ShardPlan(off, k, end, off >> 5, ((end + 31) >> 5) if last else (end >> 5), total))
+        plans.append(ShardPlan(off, k, end, off >> 5, ((end + 31) >> 5) if last else (end >> 5), total,
+                               boundary_bits(prev_tail, off)))
         k = clamp(k, lo, hi)
         off = end
+        if len(info) > 3 and bits:
+            prev_tail = int(info[3]) & 0xFFFFFFFFFFFFFFFF
     return plans
 
 
-def merge_boundary(first_word: int, prev_last_word: int, plan: ShardPlan) -> int:
-    """The word that holds a shard boundary belongs to the later shard: OR the
-    predecessor's tail bits into this shard's first word."""
-    if plan.bit_offset & 31:
-        return first_word | prev_last_word
-    return first_word
-
-
-def place_bits_host(stream: np.ndarray, nbits: int, dst_bit: int) -> np.ndarray:
+def place_bits_host(stream: np.ndarray, nbits: int, dst_bit: int, head_or: int = 0) -> np.ndarray:
     """numpy model of aecb200_place_bits_device (CPU tests): returns the bytes of
     the 32-bit words [dst_bit >> 5, (dst_bit + nbits + 31) >> 5) with the
-    stream's bits at their place and zeros elsewhere."""
+    stream's bits at their place, head_or in front and zeros behind."""
     bits = np.unpackbits(stream)[:nbits]
     w0 = dst_bit >> 5
     nw = ((dst_bit + nbits + 31) >> 5) - w0
     out = np.zeros(nw * 32, dtype=np.uint8)
     s = dst_bit - (w0 << 5)
+    if s:
+        out[:s] = np.unpackbits(np.array([head_or], dtype=">u4").view(np.uint8))[:s]
     out[s:s + nbits] = bits
     return np.packbits(out)
+
+
+def tail64_host(stream: np.ndarray, nbits: int) -> int:
+    """Last 64 bits of a stream, right-aligned (numpy model of the shard summary)."""
+    bits = np.unpackbits(stream)[:nbits][-64:]
+    v = 0
+    for b in bits.tolist():
+        v = (v << 1) | int(b)
+    return v
 
 
 class ShardedCodec:
@@ -105,7 +123,11 @@ class ShardedCodec:
         self.local = None
         self.placed = None
         self.offsets = None
+        self.grp = None
         self.plan = None
+        self._mine = torch.zeros(4, dtype=torch.int64, device="cuda")
+        self._all = torch.zeros(4 * world, dtype=torch.int64, device="cuda")
+        self._mine_h = torch.zeros(4, dtype=torch.int64).pin_memory()
 
     def close(self):
         self.codec.close()
@@ -118,9 +140,10 @@ class ShardedCodec:
             self.placed = torch.empty(cap + 8, dtype=torch.uint8, device="cuda")
         if self.offsets is None or self.offsets.numel() < nrsi:
             self.offsets = torch.empty(max(nrsi, 1), dtype=torch.int64, device="cuda")
+            self.grp = torch.zeros(max(nrsi, 1) * 32, dtype=torch.int64, device="cuda")
 
     def encode(self, d_raw, nbytes: int):
-        """Steps 1-5 for this rank's shard `d_raw` (uint8 CUDA tensor).  Returns
+        """Steps 1-4 for this rank's shard `d_raw` (uint8 CUDA tensor).  Returns
         the ShardPlan; self.placed then holds this rank's words of the global
         stream starting at word plan.word_lo."""
         torch = self.torch
@@ -130,37 +153,30 @@ class ShardedCodec:
         R = p.rsi * p.block_size
         nrsi = (nbytes // p.bytes_per_sample + R - 1) // R
         self._ensure(nbytes, nrsi)
-        # 1. independent shard encode
-        self.codec.encode_enqueue(p, d_raw, nbytes, self.local, self.offsets)
+        # 1. independent shard encode (also records the RSI and group indexes for the decoder)
+        self.codec.encode_enqueue(p, d_raw, nbytes, self.local, self.offsets, d_grp=self.grp)
         st, bits, kend = self.codec.encode_finish()
         assert st == 0
-        klo, khi, first_const = self.codec.shard_info()
-        # 2. tiny exchange
-        mine = torch.tensor([bits, klo, khi], dtype=torch.int64, device="cuda")
+        klo, khi, first_const, tail64 = self.codec.shard_info()
+        # 2. the only exchange: 32 bytes per rank
         if self.world > 1:
-            allv = [torch.zeros_like(mine) for _ in range(self.world)]
-            dist.all_gather(allv, mine, group=self.group)
-            infos = [tuple(int(x) for x in v.tolist()) for v in allv]
+            h = self._mine_h
+            h[0], h[1], h[2] = bits, klo, khi
+            h[3] = tail64 - (1 << 64) if tail64 >= (1 << 63) else tail64
+            self._mine.copy_(h, non_blocking=True)
+            dist.all_gather_into_tensor(self._all, self._mine, group=self.group)
+            allv = self._all.cpu().view(self.world, 4).tolist()
+            infos = [(v[0], v[1], v[2], v[3] & 0xFFFFFFFFFFFFFFFF) for v in allv]
         else:
-            infos = [(bits, klo, khi)]
+            infos = [(bits, klo, khi, tail64)]
         plan = plan_shards(infos)[self.rank]
         # 3. k repair of the leading tiles
         if plan.k_in != 0 and nbytes:
             self.codec.set_tile_limit(first_const + 1)
             self.codec.encode_enqueue(p, d_raw, nbytes, self.local, None, Carry(0, plan.k_in, 0))
-        # 4. move to the global bit phase (placed[0] is global word floor(bit_offset / 32))
-        self.codec.place_bits(self.local, bits, self.placed, plan.bit_offset & 31)
-        # 5. boundary word exchange
-        if self.world > 1:
-            nwords = (((plan.bit_offset & 31) + bits + 31) >> 5)
-            w = self.placed.view(torch.int32)
-            edge = torch.stack([w[0], w[max(nwords - 1, 0)]]).to(torch.int64)
-            alle = [torch.zeros_like(edge) for _ in range(self.world)]
-            dist.all_gather(alle, edge, group=self.group)
-            if self.rank > 0 and (plan.bit_offset & 31):
-                prev_last = alle[self.rank - 1][1].to(torch.int32)
-                w[0] = w[0] | prev_last
-        torch.cuda.current_stream().synchronize()
+        # 4. move to the global bit phase (placed[0] is global word floor(bit_offset / 32)) and
+        #    complete the first word with the predecessor's tail
+        self.codec.place_bits(self.local, bits, self.placed, plan.bit_offset & 31, plan.head_or)
         self.plan = plan
         self.bits = bits
         return plan
@@ -173,10 +189,14 @@ class ShardedCodec:
             nbytes = (plan.total_bits + 7) // 8 - plan.word_lo * 4
         return self.placed[:max(nbytes, 0)]
 
-    def decode(self, d_out, nbytes: int):
+    def decode_enqueue(self, d_out, nbytes: int):
         """Decode this rank's shard from its own stream: no exchange needed."""
         p = self.p
         R = p.rsi * p.block_size
         nrsi = (nbytes // p.bytes_per_sample + R - 1) // R
-        self.codec.decode_enqueue(p, self.local, (self.bits + 7) // 8, self.offsets, nrsi, d_out, nbytes)
+        return self.codec.decode_enqueue(p, self.local, (self.bits + 7) // 8, self.offsets, nrsi, d_out, nbytes,
+                                         d_grp=self.grp)
+
+    def decode(self, d_out, nbytes: int):
+        self.decode_enqueue(d_out, nbytes)
         return self.codec.decode_finish()

@@ -15,7 +15,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from cases import pack_samples, synth_values
-from libaec_b200.parallel import merge_boundary, place_bits_host, plan_shards, shard_range
+from libaec_b200.parallel import place_bits_host, plan_shards, shard_range, tail64_host
 from oracle import pyoracle as po
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -67,26 +67,23 @@ def _worker(rank, world, port, results):
         s, c = shard_range(total, R, rank, world)
         shard = raw[s * B:(s + c) * B]
         kmax = {5: 29, 4: 13, 3: 5, 2: 1, 1: 0}[p.id_len]
-        # 1. independent shard encode (k seed 0) + the shard's clamp pair
-        _, bits, klo = _model_encode(m, p, shard, 0)
+        # 1. independent shard encode (k seed 0) + the shard's clamp pair + its last 64 bits
+        s0, bits, klo = _model_encode(m, p, shard, 0)
         _, _, khi = _model_encode(m, p, shard, kmax)
-        # 2. tiny exchange
-        mine = torch.tensor([bits, klo, khi], dtype=torch.int64)
+        t64 = tail64_host(s0, bits)
+        # 2. the only exchange
+        mine = torch.tensor([bits, klo, khi, t64 - (1 << 64) if t64 >= (1 << 63) else t64], dtype=torch.int64)
         allv = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allv, mine)
-        plan = plan_shards([tuple(v.tolist()) for v in allv])[rank]
-        # 3. re-code with the true incoming k
+        infos = [(v[0], v[1], v[2], v[3] & 0xFFFFFFFFFFFFFFFF) for v in (t.tolist() for t in allv)]
+        plan = plan_shards(infos)[rank]
+        # 3. re-code with the true incoming k (the tail never changes: lengths do not depend on k
+        #    and only the leading plateau blocks can change their bits)
         stream, bits2, _ = _model_encode(m, p, shard, plan.k_in)
         assert bits2 == bits
-        # 4. place at the global phase
-        placed = place_bits_host(stream, bits, plan.bit_offset)
+        # 4. place at the global phase, first word completed with the predecessor's tail
+        placed = place_bits_host(stream, bits, plan.bit_offset, plan.head_or)
         words = placed.view(">u4").astype(np.int64)
-        # 5. boundary words
-        edge = torch.tensor([int(words[0]), int(words[-1])], dtype=torch.int64)
-        alle = [torch.zeros_like(edge) for _ in range(world)]
-        dist.all_gather(alle, edge)
-        if rank > 0:
-            words[0] = merge_boundary(int(words[0]), int(alle[rank - 1][1]), plan)
         owned = words[: plan.word_hi - plan.word_lo].astype(">u4").view(np.uint8)
         if rank == world - 1:
             owned = owned[: (plan.total_bits + 7) // 8 - plan.word_lo * 4]
@@ -117,7 +114,8 @@ def test_two_rank_stitch_equals_single_stream():
 
 
 def test_plan_shards_chain():
-    plans = plan_shards([(100, 3, 5), (64, 0, 29), (7, 9, 9), (50, 2, 4)])
+    plans = plan_shards([(100, 3, 5, 0xFFFFFFFFFFFFFFFF), (64, 0, 29, 0), (7, 9, 9, 0), (50, 2, 4, 0)])
+    assert plans[1].head_or == 0xF0000000          # 100 % 32 = 4 tail bits of shard 0
     assert [p.bit_offset for p in plans] == [0, 100, 164, 171]
     assert [p.k_in for p in plans] == [0, 3, 3, 9]
     assert plans[-1].end_bit == plans[-1].total_bits == 221
