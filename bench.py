@@ -261,9 +261,10 @@ def run_ours(args):
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record()
         if sharded is not None:
-            sharded.encode(d_raw, raw.size)
+            sharded.encode_local(d_raw, raw.size)       # independent shard encode
             b.record()
-            sharded.decode_enqueue(d_back, raw.size)
+            sharded.decode_enqueue(d_back, raw.size)    # decode needs no exchange
+            sharded.stitch()                            # 32-byte all_gather, k repair, placement
         else:
             codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs, d_grp=d_grp)
             b.record()

@@ -142,22 +142,29 @@ class ShardedCodec:
             self.offsets = torch.empty(max(nrsi, 1), dtype=torch.int64, device="cuda")
             self.grp = torch.zeros(max(nrsi, 1) * 32, dtype=torch.int64, device="cuda")
 
-    def encode(self, d_raw, nbytes: int):
-        """Steps 1-4 for this rank's shard `d_raw` (uint8 CUDA tensor).  Returns
-        the ShardPlan; self.placed then holds this rank's words of the global
-        stream starting at word plan.word_lo."""
-        torch = self.torch
-        import torch.distributed as dist
-        from .api import Carry
+    def encode_local(self, d_raw, nbytes: int):
+        """Step 1: code this rank's shard on its own (no communication)."""
         p = self.p
         R = p.rsi * p.block_size
         nrsi = (nbytes // p.bytes_per_sample + R - 1) // R
         self._ensure(nbytes, nrsi)
-        # 1. independent shard encode (also records the RSI and group indexes for the decoder)
+        self._raw, self._nbytes = d_raw, nbytes
+        # also records the RSI and group indexes for the decoder
         self.codec.encode_enqueue(p, d_raw, nbytes, self.local, self.offsets, d_grp=self.grp)
         st, bits, kend = self.codec.encode_finish()
         assert st == 0
-        klo, khi, first_const, tail64 = self.codec.shard_info()
+        self.bits = bits
+        self._info = self.codec.shard_info()
+        return bits
+
+    def stitch(self):
+        """Steps 2-4: the 32-byte exchange, k repair, placement at the global bit phase.
+        Independent of decoding the local shard, so callers may enqueue that first."""
+        import torch.distributed as dist
+        from .api import Carry
+        p = self.p
+        bits = self.bits
+        klo, khi, first_const, tail64 = self._info
         # 2. the only exchange: 32 bytes per rank
         if self.world > 1:
             h = self._mine_h
@@ -171,14 +178,22 @@ class ShardedCodec:
             infos = [(bits, klo, khi, tail64)]
         plan = plan_shards(infos)[self.rank]
         # 3. k repair of the leading tiles
-        if plan.k_in != 0 and nbytes:
+        if plan.k_in != 0 and self._nbytes:
             self.codec.set_tile_limit(first_const + 1)
-            self.codec.encode_enqueue(p, d_raw, nbytes, self.local, None, Carry(0, plan.k_in, 0))
+            self.codec.encode_enqueue(p, self._raw, self._nbytes, self.local, None, Carry(0, plan.k_in, 0))
         # 4. move to the global bit phase (placed[0] is global word floor(bit_offset / 32)) and
         #    complete the first word with the predecessor's tail
         self.codec.place_bits(self.local, bits, self.placed, plan.bit_offset & 31, plan.head_or)
         self.plan = plan
-        self.bits = bits
+        return plan
+
+    def encode(self, d_raw, nbytes: int):
+        """Steps 1-4 for this rank's shard `d_raw` (uint8 CUDA tensor).  Returns
+        the ShardPlan; self.placed then holds this rank's words of the global
+        stream starting at word plan.word_lo."""
+        self.encode_local(d_raw, nbytes)
+        plan = self.stitch()
+        self.torch.cuda.current_stream().synchronize()
         return plan
 
     def owned_bytes(self):
