@@ -215,6 +215,7 @@ def run_ours(args):
     st, written = codec.decode_finish()
     assert st == 0 and written == raw.size
     assert torch.equal(d_back[:raw.size], d_raw), "round trip differs"
+    handover = codec.last_handover
 
     # multi-GPU: shards are independent RSI ranges; the only exchange is the
     # tiny all-gather of per-shard (bits, k) that places each shard in the
@@ -370,7 +371,8 @@ def run_ours(args):
         "config": {"workload": workload_name(args), "raw_bytes_per_gpu": raw.size,
                    "compressed_bytes_per_gpu": comp_bytes, "ratio": raw.size / comp_bytes,
                    "l2": "inputs larger than L2 (%.0f MiB raw per step vs 126 MB L2), no explicit flush" % (raw.size / 2**20),
-                   "parallelism": "rsi-shards x%d" % world, "shard_bits": shard_bits},
+                   "parallelism": "rsi-shards x%d" % world, "shard_bits": shard_bits,
+                   "decode_rsis_handed_to_careful_kernel": handover, "rsis_per_gpu": nrsi},
         "encode_gbs": enc_gbs * world, "decode_gbs": dec_gbs * world,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT,

@@ -135,6 +135,8 @@ int aecb200_decode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
                                   void *d_out, size_t out_bytes);
 /* Force the lane-per-RSI ("careful") decode kernel for everything (testing). */
 void aecb200_ctx_set_careful_decode(aecb200_ctx *ctx, int on);
+/* RSIs the fast kernel handed to the careful kernel in the last finished decode (diagnostics). */
+uint64_t aecb200_ctx_last_handover(aecb200_ctx *ctx);
 /* Wait for the last enqueued decode; *out_written = bytes of samples delivered. */
 int aecb200_decode_finish(aecb200_ctx *ctx, size_t *out_written);
 

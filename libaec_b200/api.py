@@ -94,7 +94,7 @@ DEVICE_SYMBOLS = ["aecb200_device_count", "aecb200_ctx_create", "aecb200_ctx_des
                   "aecb200_decode_host", "aecb200_decode_host_resume", "aecb200_ctx_set_shard_mode",
                   "aecb200_encode_shard_info", "aecb200_ctx_set_tile_limit", "aecb200_place_bits_device",
                   "aecb200_encode_device_indexed", "aecb200_decode_device_indexed", "aecb200_group_index_entries",
-                  "aecb200_ctx_set_careful_decode"]
+                  "aecb200_ctx_set_careful_decode", "aecb200_ctx_last_handover"]
 SZ_SYMBOLS = ["SZ_BufftoBuffCompress", "SZ_BufftoBuffDecompress", "SZ_encoder_enabled", "SZ_Compress"]
 
 
@@ -116,6 +116,7 @@ def load_library() -> C.CDLL:
         lib.aecb200_ctx_set_shard_mode.restype = None
         lib.aecb200_ctx_set_careful_decode.restype = None
         lib.aecb200_group_index_entries.restype = C.c_size_t
+        lib.aecb200_ctx_last_handover.restype = C.c_uint64
         lib.aecb200_ctx_set_tile_limit.restype = None
         _lib = lib
     return _lib
@@ -368,6 +369,10 @@ class DeviceCodec:
     def group_index_entries(self, p: Params, in_bytes: int) -> int:
         prm = _Params(p.bits_per_sample, p.block_size, p.rsi, p.flags)
         return int(self.lib.aecb200_group_index_entries(C.byref(prm), C.c_size_t(in_bytes)))
+
+    @property
+    def last_handover(self) -> int:
+        return int(self.lib.aecb200_ctx_last_handover(self.ctx))
 
     def set_careful_decode(self, on: bool = True):
         self.lib.aecb200_ctx_set_careful_decode(self.ctx, C.c_int(int(on)))

@@ -329,13 +329,16 @@ aec_decode_warp_kernel(const AecDecArgs a)
 
     const uint64_t r = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (r >= a.nrsi) return;
-    /* only whole RSIs inside the requested output are handled here */
+    /* samples this RSI has to deliver (the last RSI may be short, the caller may ask for less) */
     const uint64_t startS = r * (uint64_t)c.R;
-    bool whole = a.out_samples >= startS + c.R;
-    uint32_t bad = whole ? 0u : 1u;
+    const uint64_t want = a.out_samples > startS ? a.out_samples - startS : 0;
+    const uint32_t limit = want < c.R ? (uint32_t)want : c.R;
+    const uint32_t nblk_rsi = (limit + J - 1) / J;         /* blocks that have to be decoded */
+    const bool whole = limit > 0;
+    uint32_t bad = 0u;
 
     const uint32_t b0 = lane * G;
-    const uint32_t nblk = b0 < c.rsi ? (c.rsi - b0 < G ? c.rsi - b0 : G) : 0u;
+    const uint32_t nblk = b0 < nblk_rsi ? (nblk_rsi - b0 < G ? nblk_rsi - b0 : G) : 0u;
     uint32_t sum = 0;                                  /* wrapping sum of my deltas */
     uint32_t uref = 0;
     uint64_t endpos = 0, startpos = 0;
@@ -440,7 +443,8 @@ aec_decode_warp_kernel(const AecDecArgs a)
     /* ---- cooperative store of the RSI's R samples (contiguous in the output) ---- */
     uint32_t *wrows = rows + (size_t)warp * 32u * stride;
     const bool sxt = c.sext && c.n < 32;
-    if (JT != 0 && a.out_aligned && (GJ % 4u) == 0) {
+    if (!whole) return;
+    if (JT != 0 && a.out_aligned && (GJ % 4u) == 0 && limit == c.R) {
         constexpr int SPG = (B == 4) ? 1 : ((B == 2) ? 2 : 4);
         const uint32_t ngroups = c.R / SPG;
         const bool pow2 = (GJ & (GJ - 1u)) == 0;
@@ -462,7 +466,7 @@ aec_decode_warp_kernel(const AecDecArgs a)
             store_group<B>(a.out, startS + s0, sv, c.msb);
         }
     } else {
-        for (uint32_t s0 = lane; s0 < c.R; s0 += 32) {
+        for (uint32_t s0 = lane; s0 < limit; s0 += 32) {
             uint32_t rowi = s0 / GJ, col = s0 % GJ;
             uint32_t x = wrows[(size_t)rowi * stride + col];
             if (c.pp) { x ^= sflip; if (sxt && ((x >> (c.n - 1)) & 1u)) x |= ~c.mask; }

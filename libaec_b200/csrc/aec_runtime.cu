@@ -400,6 +400,9 @@ int aecb200_decode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
 
 void aecb200_ctx_set_careful_decode(aecb200_ctx *ctx, int on) { if (ctx) ctx->careful_only = on != 0; }
 
+/* RSIs the fast decode kernel handed to the careful kernel in the last finished decode */
+uint64_t aecb200_ctx_last_handover(aecb200_ctx *ctx) { return ctx ? (ctx->h_res[6] & 0xFFFFFFFFull) : 0; }
+
 int aecb200_decode_finish(aecb200_ctx *ctx, size_t *out_written)
 {
     if (!ctx || !ctx->dec_pending) return AEC_CONF_ERROR;
