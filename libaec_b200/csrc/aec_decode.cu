@@ -302,6 +302,18 @@ __device__ __forceinline__ uint32_t warp_decode_block(const AecCfg &c, Rd64 &rd,
     return dsum;
 }
 
+/* First guess of a lane's start value: reference + sum of the deltas before the lane, which is
+ * exact when nothing clips.  When samples sit on a range boundary (imagery near zero) the
+ * clipped steps make that sum leave [0, M]; the nearest boundary is then the better guess.
+ * Only a heuristic for the first walk: the iteration that follows is exact either way. */
+__device__ __forceinline__ uint32_t project_start(uint32_t uref, uint32_t off, uint32_t M)
+{
+    long long v = (long long)uref + (long long)(int32_t)off;
+    if (v < 0) v = 0;
+    if (v > (long long)M) v = (long long)M;
+    return (uint32_t)v;
+}
+
 /* exact inverse mapper step on normalised values; sets clip when the clipped branch was taken */
 __device__ __forceinline__ uint32_t unmap_step(uint32_t u, uint32_t d, uint32_t M, uint32_t &clip)
 {
@@ -393,7 +405,7 @@ aec_decode_warp_kernel(const AecDecArgs a)
         }
         /* speculated value before my first sample; kept inside [0, M] so that every walk stays in the
          * mapper's domain and the mapped values can be recovered exactly after a wrong guess */
-        uint32_t us = (uref + (inc - sum)) & c.mask;
+        uint32_t us = project_start(uref, inc - sum, c.mask);
         const uint32_t n_s = nblk * J;
         const uint32_t i_first = (lane == 0) ? 1u : 0u;
         if (lane == 0) us = uref;
@@ -407,26 +419,50 @@ aec_decode_warp_kernel(const AecDecArgs a)
             /* recover the mapped values from the (wrongly started) samples */
             uint32_t pv = us;
             for (uint32_t i = i_first; i < n_s; i++) { uint32_t cur = row[i]; row[i] = aec_map_delta(pv, cur, c.mask); pv = cur; }
-            for (int iter = 0; iter < 34; iter++) {
-                /* new start values: absolute after a lane that clipped, relative otherwise
-                 * (segmented inclusive scan of (reset, value)) */
-                uint32_t val = clip ? u : (u - us);    /* absolute end, or my net offset */
-                uint32_t rst = clip;
-                if (lane == 0) { val = u; rst = 1u; }
+            for (int iter = 0; iter < 36; iter++) {
+                /* Which lanes start where their predecessor ended?  The leftmost lane that does not
+                 * is repaired exactly every round (everything before it is final), so the loop ends
+                 * after at most 32 rounds; the two update rules below only differ in how boldly they
+                 * also move the lanes further right (measured on imagery-like, clipped-walk and noise
+                 * data: DESIGN.md 4.2). */
+                uprev = __shfl_up_sync(FULL, u, 1);
+                const bool cons = (lane == 0) || (n_s == 0) || (uprev == us);
+                const uint32_t incons = __ballot_sync(FULL, !cons);
+                if (incons == 0) break;
+                if (iter == 35) { bad = 1u; break; }
+                if (__popc(incons) > 4) {
+                    /* many lanes off (noise-like data: nearly every lane clips and forgets its start):
+                     * chain the lanes' results, absolute after a lane that clipped, relative otherwise */
+                    uint32_t val = clip ? u : (u - us);
+                    uint32_t rst = clip;
+                    if (lane == 0) { val = u; rst = 1u; }
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    uint32_t ov = __shfl_up_sync(FULL, val, off);
-                    uint32_t orst = __shfl_up_sync(FULL, rst, off);
-                    if (lane >= (uint32_t)off && !rst) { val += ov; rst = orst; }
+                    for (int off = 1; off < 32; off <<= 1) {
+                        uint32_t ov = __shfl_up_sync(FULL, val, off);
+                        uint32_t orst = __shfl_up_sync(FULL, rst, off);
+                        if (lane >= (uint32_t)off && !rst) { val += ov; rst = orst; }
+                    }
+                    uint32_t nus = __shfl_up_sync(FULL, val, 1);
+                    if (lane > 0) us = nus & c.mask;
+                } else {
+                    /* few lanes off (a start value guessed wrong here and there): move a lane to its
+                     * predecessor's end only if that predecessor itself started consistently, and carry
+                     * the same correction through the clip-free lanes that follow it */
+                    const bool cons_m1 = __shfl_up_sync(FULL, (int)cons, 1) != 0 || lane == 0;
+                    const bool clip_m1 = __shfl_up_sync(FULL, clip, 1) != 0 && lane != 0;
+                    const bool fix = !cons && cons_m1;
+                    uint32_t val = fix ? (uprev - us) : 0u;
+                    uint32_t stop = (fix || !(cons && !clip_m1)) ? 1u : 0u;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        uint32_t ov = __shfl_up_sync(FULL, val, off);
+                        uint32_t ostop = __shfl_up_sync(FULL, stop, off);
+                        if (lane >= (uint32_t)off && !stop) { val += ov; stop = ostop; }
+                    }
+                    us = (us + val) & c.mask;
                 }
-                uint32_t nus = __shfl_up_sync(FULL, val, 1);   /* predecessor's (speculated) end */
-                if (lane > 0) us = nus & c.mask;
                 u = us; clip = 0;
                 for (uint32_t i = i_first; i < n_s; i++) u = unmap_step(u, row[i], c.mask, clip);
-                uprev = __shfl_up_sync(FULL, u, 1);
-                ok = (lane == 0) || (n_s == 0) || (uprev == us);
-                if (__all_sync(FULL, ok)) break;
-                if (iter == 33) bad = 1u;              /* cannot happen: at least one more lane settles per round */
             }
             bad = __any_sync(FULL, bad) ? 1u : 0u;
             if (!bad) {
