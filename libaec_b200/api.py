@@ -102,7 +102,7 @@ def load_library() -> C.CDLL:
     """Load libaec.so.0; raises when it has not been built (no fallback)."""
     global _lib
     if _lib is None:
-        path = os.path.join(LIBDIR, "libaec.so.0")
+        path = os.environ.get("AECB200_LIB") or os.path.join(LIBDIR, "libaec.so.0")
         if not os.path.exists(path):
             raise RuntimeError(f"{path} missing: run `python -m libaec_b200.build` (needs nvcc)")
         lib = C.CDLL(path)

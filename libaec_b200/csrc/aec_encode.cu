@@ -179,7 +179,7 @@ __device__ __noinline__ void aec_encode_scanner(const AecEncArgs &a, uint64_t *s
         uint64_t dv = ST_AGG | ((uint64_t)c.kmax << 7);           /* identity beyond the last tile */
         if (t < a.ntiles) {
             dv = ld_volatile_u64(&a.desc[t]);
-            while ((dv & 3) == 0) { __nanosleep(100); dv = ld_volatile_u64(&a.desc[t]); }
+            while ((dv & 3) == 0) dv = ld_volatile_u64(&a.desc[t]);
         }
         __syncwarp();
         PosFn f; uint32_t kj;
@@ -210,7 +210,7 @@ __device__ __noinline__ void aec_encode_scanner(const AecEncArgs &a, uint64_t *s
         uint32_t ke = __shfl_up_sync(FULL, ki, 1);
         if (lane == 0) { fe.has_end = 0; fe.a = 0; fe.rest = 0; ke = kident; }
         /* carry of everything before this batch */
-        while (*s_done != (uint32_t)b) __nanosleep(20);
+        while (*s_done != (uint32_t)b) { }                     /* hand-over spin: a sleep quantum here would serialise the chain */
         const uint64_t P = *reinterpret_cast<volatile uint64_t *>(&s_carry_pos[b & 1]);
         const uint32_t kc = *reinterpret_cast<volatile uint32_t *>(&s_carry_k[b & 1]);
         const uint64_t pos = aec_papply(fe, P);
@@ -237,11 +237,17 @@ __device__ __noinline__ void aec_encode_scanner(const AecEncArgs &a, uint64_t *s
 
 template <int JT>
 struct TileCfg {
-    static constexpr int TB = (JT == 0 || JT == 64) ? 128 : 256;
+#ifndef AEC_TB16
+#define AEC_TB16 256
+#endif
+    static constexpr int TB = (JT == 0 || JT == 64) ? 128 : ((JT == 16) ? AEC_TB16 : 256);
     static constexpr int NWARP = TB / 32;
     static constexpr int JMAX = JT ? JT : AEC_MAX_J;
     /* resident CTAs per SM the register allocation aims for */
-    static constexpr int MINB = (JT == 8 || JT == 16) ? 4 : ((JT == 32) ? 3 : ((JT == 64) ? 4 : 2));
+#ifndef AEC_MINB16
+#define AEC_MINB16 4
+#endif
+    static constexpr int MINB = (JT == 8 || JT == 16) ? AEC_MINB16 : ((JT == 32) ? 3 : ((JT == 64) ? 4 : 2));
 };
 
 __device__ __forceinline__ void pair_barrier(uint32_t warp)
@@ -456,7 +462,7 @@ aec_encode_kernel(const AecEncArgs a)
                 /* the scanner's exclusive prefix of this tile: absolute bit offset and incoming k */
                 if (tid == 0) {
                     uint64_t pv = ld_volatile_u64(&a.pref[tile]);
-                    while ((pv & 3) == 0) { __nanosleep(40); pv = ld_volatile_u64(&a.pref[tile]); }
+                    while ((pv & 3) == 0) pv = ld_volatile_u64(&a.pref[tile]);
                     s_base = pv >> 12;
                     s_kin = (uint32_t)(pv >> 2) & 0x1Fu;
                     __threadfence_block();
@@ -692,7 +698,8 @@ cudaError_t launch_j(const AecEncArgs &a, uint32_t smem, int sms, cudaStream_t s
 
 uint32_t aec_encode_tile_blocks(uint32_t J)
 {
-    return (J == 8 || J == 16 || J == 32) ? 256u : 128u;
+    if (J == 16) return AEC_TB16;
+    return (J == 8 || J == 32) ? 256u : 128u;
 }
 
 uint32_t aec_encode_staging_words(const AecCfg &c)
