@@ -256,6 +256,14 @@ __device__ __forceinline__ void pair_barrier(uint32_t warp)
     asm volatile("bar.sync %0, 64;" :: "r"(1u + (warp >> 1)) : "memory");
 }
 
+/* Per-thread facts about a tile whose words still have to be streamed out. */
+struct PendingBlock {
+    uint64_t myoff;      /* bit offset inside the tile's staging area */
+    uint32_t len;        /* CDS bits */
+    uint32_t zrun;       /* zero-run length when this block owns a run */
+    uint32_t flags;      /* bit0 valid, bit1 all-zero block, bit2 inherits a zero run */
+};
+
 template <int JT, int B>
 __global__ void __launch_bounds__(TileCfg<JT>::TB, TileCfg<JT>::MINB)
 aec_encode_kernel(const AecEncArgs a)
@@ -268,18 +276,17 @@ aec_encode_kernel(const AecEncArgs a)
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t kident = aec_kpair(0, c.kmax);
     /* RSIs longer than a tile with RSI padding: a tile may start at an unknown
-     * bit phase mod 8, so its bits can only be laid out after the look-back */
+     * bit phase mod 8, so its bits can only be laid out once its prefix is known */
     const bool late = c.pad && a.RP > (uint32_t)TB;
 
-    extern __shared__ uint32_t staging[];
+    extern __shared__ uint32_t staging_all[];      /* two staging areas: tile it packs while tile it-1 streams out */
     __shared__ uint32_t s_ticket[2];
     __shared__ uint32_t s_zb[NWARP + 1];
     __shared__ uint32_t s_wlen[NWARP];       /* per-warp sums (no-pad mode) */
     __shared__ uint32_t s_wend[NWARP], s_wa[NWARP], s_wrest[NWARP];   /* per-warp PosFn (pad mode) */
     __shared__ uint32_t s_wk[NWARP];
-    __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_kin;
-    __shared__ uint32_t s_kready;            /* iteration (+1) for which s_base/s_kin are valid */
+    __shared__ unsigned long long s_base;    /* absolute bit offset of the tile being streamed out */
+    __shared__ unsigned long long s_base_cur;/* late mode: absolute bit offset of the tile being packed */
 
     if (blockIdx.x == 0) {                  /* CTA 0 is the scanner */
         __shared__ unsigned long long s_cpos[2];
@@ -288,202 +295,190 @@ aec_encode_kernel(const AecEncArgs a)
         aec_encode_scanner<NWARP>(a, reinterpret_cast<uint64_t *>(s_cpos), s_ck, &s_sdone);
         return;
     }
-    for (uint32_t i = tid; i < a.staging_words; i += TB) staging[i] = 0;
-    if (tid == 0) { s_ticket[0] = atomicAdd(a.ticket, 1u); s_kready = 0; }
+    for (uint32_t i = tid; i < 2u * a.staging_words; i += TB) staging_all[i] = 0;
+    if (tid == 0) s_ticket[0] = atomicAdd(a.ticket, 1u);
     __syncthreads();
+
+    /* the previous tile of this CTA: packed, aggregate published, words not yet written */
+    bool prev_have = false;
+    uint64_t prev_tile = 0;
+    PosFn prev_ptile; prev_ptile.has_end = 0; prev_ptile.a = 0; prev_ptile.rest = 0;
+    PendingBlock pend; pend.myoff = 0; pend.len = 0; pend.zrun = 0; pend.flags = 0;
 
     for (uint32_t it = 0;; it++) {
         const uint64_t tile = s_ticket[it & 1u];
-        if (tile >= a.ntiles) break;
+        const bool have = tile < a.ntiles;
+        uint32_t *staging = staging_all + (it & 1u) * a.staging_words;
+        PosFn ptile; ptile.has_end = 0; ptile.a = 0; ptile.rest = 0;
+        PendingBlock cur; cur.myoff = 0; cur.len = 0; cur.zrun = 0; cur.flags = 0;
 
-        /* ---- which block is mine ---- */
-        uint64_t rsi_idx; uint32_t b;
-        if (a.RP >= (uint32_t)TB) {
-            uint32_t tpr = a.RP / TB;
-            rsi_idx = tile / tpr;
-            b = (uint32_t)(tile % tpr) * TB + tid;
-        } else {
-            rsi_idx = tile * (TB / a.RP) + tid / a.RP;
-            b = tid % a.RP;
-        }
-        uint32_t nblk = 0;
-        if (rsi_idx + 1 < a.nrsi) nblk = c.rsi;
-        else if (rsi_idx + 1 == a.nrsi) nblk = a.last_nblk;
-        const bool valid = b < nblk;
-        const uint32_t ref = (valid && c.pp && b == 0) ? 1u : 0u;
-
-        /* ---- load, map, cost ---- */
-        uint32_t d[JMAX];
-        uint32_t refs = 0;
-        BlockInfo bi; bi.opt = OPT_NONE; bi.klo = 0; bi.khi = c.kmax; bi.len = 0;
-        {
-            const uint64_t first = rsi_idx * (uint64_t)c.R + (uint64_t)b * J;
-            const bool fast = valid && a.aligned && (first + J <= a.nsamples);
-            if (valid) load_block<JT, B>(c, a.in, first, a.nsamples, fast, d);
-            /* last raw sample of the previous block = last sample of the lane below */
-            uint32_t prev = __shfl_up_sync(FULL, valid ? d[J - 1] : 0u, 1);
-            if (valid && c.pp) {
-                if (b == 0) { refs = d[0]; prev = d[0]; }
-                else if (lane == 0) {
-                    uint64_t pi = first - 1;
-                    if (pi >= a.nsamples) pi = a.nsamples - 1;
-                    prev = aec_load_sample(a.in + pi * c.B, c.B, c.msb);
-                }
-                prev ^= c.sflip;
-#pragma unroll
-                for (uint32_t i = 0; i < (JT ? (uint32_t)JT : J); i++) {
-                    uint32_t u = d[i] ^ c.sflip;
-                    d[i] = aec_map_delta(prev, u, c.mask);
-                    prev = u;
-                }
-                if (b == 0) d[0] = 0;
-            }
-            if (valid) bi = aec_analyze_block<JT>(c, d, ref);
-        }
-        const bool is_zero = valid && bi.opt == OPT_ZERO;
-
-        /* ---- zero-run structure of my 64-block segment ---- */
-        uint32_t ball = __ballot_sync(FULL, is_zero);
-        if (lane == 0) s_zb[warp] = ball;
-        pair_barrier(warp);
-        uint32_t len = bi.len, zcode = 0, zref = 0, zrun = 0;
-        bool zinherit = false;              /* zero block that is not the first of its run */
-        if (is_zero) {
-            uint64_t m64 = (uint64_t)s_zb[warp & ~1u] | ((uint64_t)s_zb[warp | 1u] << 32);
-            uint32_t q = tid & 63u;                       /* position in the aligned 64-slot group */
-            uint32_t g0 = q - (b & 63u);                  /* where my segment starts in the group */
-            uint32_t seg = b >> 6;
-            uint32_t V = nblk - seg * 64u; if (V > 64u) V = 64u;
-            uint64_t segmask = (m64 >> g0);
-            if (V < 64u) segmask &= ((1ull << V) - 1ull);
-            len = aec_zero_run(c, segmask, V, b, &zcode, &zref, &zrun);
-            zinherit = (b & 63u) != 0 && ((segmask >> ((b & 63u) - 1u)) & 1ull);
-        }
-        if (zref) {   /* run owner needs the reference sample of block 0 of the RSI */
-            uint64_t f0 = rsi_idx * (uint64_t)c.R;
-            refs = aec_load_sample(a.in + f0 * c.B, c.B, c.msb);
-        }
-        const bool rsi_end = valid && (b + 1 == nblk);
-
-        /* ---- intra-warp inclusive scans: CDS lengths and the k clamp chain ---- */
-        const uint32_t kp = aec_kpair(bi.klo, bi.khi);    /* identity for zero/invalid/idl<=1 */
-        uint32_t kinc = kp;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            uint32_t o = __shfl_up_sync(FULL, kinc, off);
-            if (lane >= (uint32_t)off) kinc = aec_kcompose(o, kinc);
-        }
-        uint32_t kexc = __shfl_up_sync(FULL, kinc, 1);
-        if (lane == 0) kexc = kident;
-
-        PosFn pinc; pinc.has_end = 0; pinc.a = 0; pinc.rest = 0;   /* pad mode */
-        uint32_t linc = len;                                      /* no-pad mode */
-        if (c.pad) {
-            pinc.has_end = rsi_end ? 1u : 0u; pinc.a = len; pinc.rest = 0;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                PosFn o = shfl_posfn(pinc, (int)lane - off);
-                if (lane >= (uint32_t)off) pinc = aec_pcompose(o, pinc);
-            }
-        } else {
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                uint32_t o = __shfl_up_sync(FULL, linc, off);
-                if (lane >= (uint32_t)off) linc += o;
-            }
-        }
-        if (lane == 31) {
-            s_wk[warp] = kinc;
-            s_wlen[warp] = linc;
-            if (c.pad) { s_wend[warp] = pinc.has_end; s_wa[warp] = (uint32_t)pinc.a; s_wrest[warp] = (uint32_t)pinc.rest; }
-        }
-        __syncthreads();                                           /* S2 */
-
-        /* ---- cross-warp: every warp scans the NWARP warp totals with its first lanes ---- */
-        PosFn pexc; pexc.has_end = 0; pexc.a = 0; pexc.rest = 0;  /* everything before me in the tile */
-        PosFn ptile = pexc;
-        uint32_t kbefore, ktile;
-        {
-            uint32_t wk = lane < (uint32_t)NWARP ? s_wk[lane] : kident;
-#pragma unroll
-            for (int off = 1; off < NWARP; off <<= 1) {
-                uint32_t o = __shfl_up_sync(FULL, wk, off);
-                if (lane >= (uint32_t)off) wk = aec_kcompose(o, wk);
-            }
-            kbefore = __shfl_sync(FULL, wk, warp ? warp - 1 : 0);
-            if (warp == 0) kbefore = kident;
-            ktile = __shfl_sync(FULL, wk, NWARP - 1);
-            kbefore = aec_kcompose(kbefore, kexc);
-            if (c.pad) {
-                PosFn w; w.has_end = 0; w.a = 0; w.rest = 0;
-                if (lane < (uint32_t)NWARP) { w.has_end = s_wend[lane]; w.a = s_wa[lane]; w.rest = s_wrest[lane]; }
-#pragma unroll
-                for (int off = 1; off < NWARP; off <<= 1) {
-                    PosFn o = shfl_posfn(w, (int)lane - off);
-                    if (lane >= (uint32_t)off) w = aec_pcompose(o, w);
-                }
-                PosFn bw = shfl_posfn(w, warp ? (int)warp - 1 : 0);
-                ptile = shfl_posfn(w, NWARP - 1);
-                if (warp) pexc = bw;
-                PosFn f = shfl_posfn(pinc, (int)lane - 1);          /* the lanes before me in my own warp */
-                if (lane > 0) pexc = aec_pcompose(pexc, f);
+        if (have) {
+            /* ---- which block is mine ---- */
+            uint64_t rsi_idx; uint32_t b;
+            if (a.RP >= (uint32_t)TB) {
+                uint32_t tpr = a.RP / TB;
+                rsi_idx = tile / tpr;
+                b = (uint32_t)(tile % tpr) * TB + tid;
             } else {
-                uint32_t wl = lane < (uint32_t)NWARP ? s_wlen[lane] : 0u;
+                rsi_idx = tile * (TB / a.RP) + tid / a.RP;
+                b = tid % a.RP;
+            }
+            uint32_t nblk = 0;
+            if (rsi_idx + 1 < a.nrsi) nblk = c.rsi;
+            else if (rsi_idx + 1 == a.nrsi) nblk = a.last_nblk;
+            const bool valid = b < nblk;
+            const uint32_t ref = (valid && c.pp && b == 0) ? 1u : 0u;
+
+            /* ---- load, map, cost ---- */
+            uint32_t d[JMAX];
+            uint32_t refs = 0;
+            BlockInfo bi; bi.opt = OPT_NONE; bi.klo = 0; bi.khi = c.kmax; bi.len = 0;
+            {
+                const uint64_t first = rsi_idx * (uint64_t)c.R + (uint64_t)b * J;
+                const bool fast = valid && a.aligned && (first + J <= a.nsamples);
+                if (valid) load_block<JT, B>(c, a.in, first, a.nsamples, fast, d);
+                /* last raw sample of the previous block = last sample of the lane below */
+                uint32_t prev = __shfl_up_sync(FULL, valid ? d[J - 1] : 0u, 1);
+                if (valid && c.pp) {
+                    if (b == 0) { refs = d[0]; prev = d[0]; }
+                    else if (lane == 0) {
+                        uint64_t pi = first - 1;
+                        if (pi >= a.nsamples) pi = a.nsamples - 1;
+                        prev = aec_load_sample(a.in + pi * c.B, c.B, c.msb);
+                    }
+                    prev ^= c.sflip;
+#pragma unroll
+                    for (uint32_t i = 0; i < (JT ? (uint32_t)JT : J); i++) {
+                        uint32_t u = d[i] ^ c.sflip;
+                        d[i] = aec_map_delta(prev, u, c.mask);
+                        prev = u;
+                    }
+                    if (b == 0) d[0] = 0;
+                }
+                if (valid) bi = aec_analyze_block<JT>(c, d, ref);
+            }
+            const bool is_zero = valid && bi.opt == OPT_ZERO;
+
+            /* ---- zero-run structure of my 64-block segment ---- */
+            uint32_t ball = __ballot_sync(FULL, is_zero);
+            if (lane == 0) s_zb[warp] = ball;
+            pair_barrier(warp);
+            uint32_t len = bi.len, zcode = 0, zref = 0, zrun = 0;
+            bool zinherit = false;              /* zero block that is not the first of its run */
+            if (is_zero) {
+                uint64_t m64 = (uint64_t)s_zb[warp & ~1u] | ((uint64_t)s_zb[warp | 1u] << 32);
+                uint32_t q = tid & 63u;                       /* position in the aligned 64-slot group */
+                uint32_t g0 = q - (b & 63u);                  /* where my segment starts in the group */
+                uint32_t seg = b >> 6;
+                uint32_t V = nblk - seg * 64u; if (V > 64u) V = 64u;
+                uint64_t segmask = (m64 >> g0);
+                if (V < 64u) segmask &= ((1ull << V) - 1ull);
+                len = aec_zero_run(c, segmask, V, b, &zcode, &zref, &zrun);
+                zinherit = (b & 63u) != 0 && ((segmask >> ((b & 63u) - 1u)) & 1ull);
+            }
+            if (zref) {   /* run owner needs the reference sample of block 0 of the RSI */
+                uint64_t f0 = rsi_idx * (uint64_t)c.R;
+                refs = aec_load_sample(a.in + f0 * c.B, c.B, c.msb);
+            }
+            const bool rsi_end = valid && (b + 1 == nblk);
+
+            /* ---- intra-warp inclusive scans: CDS lengths and the k clamp chain ---- */
+            const uint32_t kp = aec_kpair(bi.klo, bi.khi);    /* identity for zero/invalid/idl<=1 */
+            uint32_t kinc = kp;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t o = __shfl_up_sync(FULL, kinc, off);
+                if (lane >= (uint32_t)off) kinc = aec_kcompose(o, kinc);
+            }
+            uint32_t kexc = __shfl_up_sync(FULL, kinc, 1);
+            if (lane == 0) kexc = kident;
+
+            PosFn pinc; pinc.has_end = 0; pinc.a = 0; pinc.rest = 0;   /* pad mode */
+            uint32_t linc = len;                                      /* no-pad mode */
+            if (c.pad) {
+                pinc.has_end = rsi_end ? 1u : 0u; pinc.a = len; pinc.rest = 0;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    PosFn o = shfl_posfn(pinc, (int)lane - off);
+                    if (lane >= (uint32_t)off) pinc = aec_pcompose(o, pinc);
+                }
+            } else {
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    uint32_t o = __shfl_up_sync(FULL, linc, off);
+                    if (lane >= (uint32_t)off) linc += o;
+                }
+            }
+            if (lane == 31) {
+                s_wk[warp] = kinc;
+                s_wlen[warp] = linc;
+                if (c.pad) { s_wend[warp] = pinc.has_end; s_wa[warp] = (uint32_t)pinc.a; s_wrest[warp] = (uint32_t)pinc.rest; }
+            }
+            __syncthreads();                                           /* S2 */
+
+            /* ---- cross-warp: every warp scans the NWARP warp totals with its first lanes ---- */
+            PosFn pexc; pexc.has_end = 0; pexc.a = 0; pexc.rest = 0;  /* everything before me in the tile */
+            uint32_t kbefore, ktile;
+            {
+                uint32_t wk = lane < (uint32_t)NWARP ? s_wk[lane] : kident;
 #pragma unroll
                 for (int off = 1; off < NWARP; off <<= 1) {
-                    uint32_t o = __shfl_up_sync(FULL, wl, off);
-                    if (lane >= (uint32_t)off) wl += o;
+                    uint32_t o = __shfl_up_sync(FULL, wk, off);
+                    if (lane >= (uint32_t)off) wk = aec_kcompose(o, wk);
                 }
-                uint32_t before = __shfl_sync(FULL, wl, warp ? warp - 1 : 0);
-                if (warp == 0) before = 0;
-                ptile.a = __shfl_sync(FULL, wl, NWARP - 1);
-                pexc.a = before + (linc - len);
+                kbefore = __shfl_sync(FULL, wk, warp ? warp - 1 : 0);
+                if (warp == 0) kbefore = kident;
+                ktile = __shfl_sync(FULL, wk, NWARP - 1);
+                kbefore = aec_kcompose(kbefore, kexc);
+                if (c.pad) {
+                    PosFn w; w.has_end = 0; w.a = 0; w.rest = 0;
+                    if (lane < (uint32_t)NWARP) { w.has_end = s_wend[lane]; w.a = s_wa[lane]; w.rest = s_wrest[lane]; }
+#pragma unroll
+                    for (int off = 1; off < NWARP; off <<= 1) {
+                        PosFn o = shfl_posfn(w, (int)lane - off);
+                        if (lane >= (uint32_t)off) w = aec_pcompose(o, w);
+                    }
+                    PosFn bw = shfl_posfn(w, warp ? (int)warp - 1 : 0);
+                    ptile = shfl_posfn(w, NWARP - 1);
+                    if (warp) pexc = bw;
+                    PosFn f = shfl_posfn(pinc, (int)lane - 1);          /* the lanes before me in my own warp */
+                    if (lane > 0) pexc = aec_pcompose(pexc, f);
+                } else {
+                    uint32_t wl = lane < (uint32_t)NWARP ? s_wlen[lane] : 0u;
+#pragma unroll
+                    for (int off = 1; off < NWARP; off <<= 1) {
+                        uint32_t o = __shfl_up_sync(FULL, wl, off);
+                        if (lane >= (uint32_t)off) wl += o;
+                    }
+                    uint32_t before = __shfl_sync(FULL, wl, warp ? warp - 1 : 0);
+                    if (warp == 0) before = 0;
+                    ptile.a = __shfl_sync(FULL, wl, NWARP - 1);
+                    pexc.a = before + (linc - len);
+                }
             }
-        }
 
-        /* publish this tile's aggregate for the scanner */
-        if (tid == 0) {
-            st_volatile_u64(&a.desc[tile], desc_pack_agg(ptile, ktile));
-            a.tile_kagg[tile] = ktile;
-        }
+            /* publish this tile's aggregate for the scanner */
+            if (tid == 0) {
+                st_volatile_u64(&a.desc[tile], desc_pack_agg(ptile, ktile));
+                a.tile_kagg[tile] = ktile;
+            }
 
-        /* Packing happens in two passes around the look-back: pass 0 packs every
-         * CDS that needs nothing from preceding tiles (all of them in the common
-         * case) while the predecessors are still publishing; pass 1, after warp 0
-         * has resolved the tile's bit offset and incoming k, packs the few CDSs
-         * whose split position depends on that k (or everything in `late` mode). */
-        const bool need_kin = valid && len && !is_zero && bi.opt == OPT_SPLIT && bi.klo != bi.khi &&
-                              (kbefore & 0xFFu) != (kbefore >> 8);
-        uint64_t myoff = pexc.a;            /* bit offset inside staging (early mode: local phase 0) */
-        uint64_t base_l = 0;                /* staging bit 0 <-> this absolute bit (late mode) */
-#pragma unroll 1
-        for (int pass = 0; pass < 2; pass++) {
-            if (pass == 1) {
-                /* the scanner's exclusive prefix of this tile: absolute bit offset and incoming k */
+            /* ---- pack my CDS into this tile's staging area, at local bit phase 0 ---- */
+            uint64_t myoff = pexc.a;
+            if (late) {
+                /* bit layout needs the absolute phase: wait for this tile's prefix */
                 if (tid == 0) {
                     uint64_t pv = ld_volatile_u64(&a.pref[tile]);
                     while ((pv & 3) == 0) pv = ld_volatile_u64(&a.pref[tile]);
-                    s_base = pv >> 12;
-                    s_kin = (uint32_t)(pv >> 2) & 0x1Fu;
-                    __threadfence_block();
-                    *reinterpret_cast<volatile uint32_t *>(&s_kready) = it + 1u;
-                    /* Claim the next tile only now: a claimed tile must never wait for
-                     * anything but earlier tiles, or the scanner's fixed batches of 32
-                     * could wait for a tile whose CTA is itself waiting for that batch.
-                     * Visible to the CTA after barrier S3. */
-                    s_ticket[(it + 1u) & 1u] = atomicAdd(a.ticket, 1u);
+                    s_base_cur = pv >> 12;
                 }
-                if (late) {
-                    __syncthreads();        /* bit layout needs the absolute phase */
-                    uint64_t bs = s_base;
-                    base_l = (bs >> 5) << 5;
-                    myoff = aec_papply(pexc, bs) - base_l;
-                }
-            } else if (c.pad && !late) {
+                __syncthreads();
+                const uint64_t bs = s_base_cur;
+                myoff = aec_papply(pexc, bs) - ((bs >> 5) << 5);
+            } else if (c.pad) {
                 myoff = aec_papply(pexc, 0);
             }
-            const bool doit = valid && len && (pass == 0 ? (!late && !need_kin) : (late || need_kin));
-            if (doit) {
+            if (valid && len) {
                 BitPack bp;
                 bp.init(staging, myoff);
                 if (is_zero) {
@@ -493,9 +488,11 @@ aec_encode_kernel(const AecEncArgs a)
                     if (bi.opt == OPT_SPLIT && bi.klo != bi.khi) {
                         uint32_t kprev = kbefore & 0xFFu;
                         if (kprev != (kbefore >> 8)) {
-                            /* depends on the k carried into this tile: wait for the look-back */
-                            while (*reinterpret_cast<volatile uint32_t *>(&s_kready) != it + 1u) __nanosleep(32);
-                            kprev = aec_clampu(*reinterpret_cast<volatile uint32_t *>(&s_kin), kbefore & 0xFFu, kbefore >> 8);
+                            /* a plateau block before the tile's first fixed k: its split position depends on
+                             * the k carried into the tile, i.e. on this tile's prefix (rare) */
+                            uint64_t pv = ld_volatile_u64(&a.pref[tile]);
+                            while ((pv & 3) == 0) pv = ld_volatile_u64(&a.pref[tile]);
+                            kprev = aec_clampu((uint32_t)(pv >> 2) & 0x1Fu, kbefore & 0xFFu, kbefore >> 8);
                         }
                         k = aec_clampu(kprev, bi.klo, bi.khi);
                     }
@@ -503,54 +500,82 @@ aec_encode_kernel(const AecEncArgs a)
                 }
                 bp.finish();
             }
+            cur.myoff = myoff; cur.len = len; cur.zrun = zrun;
+            cur.flags = (valid ? 1u : 0u) | (is_zero ? 2u : 0u) | (zinherit ? 4u : 0u);
         }
-        __syncthreads();                                           /* S3 */
 
-        /* ---- stream the tile's words out, shifted to the absolute bit phase ---- */
-        const uint64_t base = s_base;
-        const uint64_t myabs = late ? myoff + base_l : base + myoff;
-        if (valid && b == 0 && a.rsi_offsets) a.rsi_offsets[rsi_idx] = myabs;
-        if (a.grp_index && valid) {
-            /* group index for the warp-per-RSI decoder (aec_device.h) */
-            const uint32_t G = a.grp_G;
-            if (b % G == 0 && !zinherit) a.grp_index[rsi_idx * 32ull + b / G] = myabs;
-            if (is_zero && len && zrun > 1) {
-                /* I own a zero run: group starts inside it inherit their leading blocks from me */
-                uint32_t b0 = b + 1u - zrun;
-                for (uint32_t g = (b0 / G + 1u) * G; g <= b; g += G)
-                    a.grp_index[rsi_idx * 32ull + g / G] = ((uint64_t)(b - g + 1u) << 56) | (myabs + len);
+        /* The previous tile's prefix has had a whole tile time to arrive.  Only now claim the next
+         * tile: a claimed tile never waits for anything but earlier tiles, so the scanner's fixed
+         * batches of 32 tiles always complete. */
+        if (tid == 0) {
+            if (prev_have) {
+                uint64_t pv = ld_volatile_u64(&a.pref[prev_tile]);
+                while ((pv & 3) == 0) pv = ld_volatile_u64(&a.pref[prev_tile]);
+                s_base = pv >> 12;
             }
+            s_ticket[(it + 1u) & 1u] = have ? atomicAdd(a.ticket, 1u) : 0xFFFFFFFFu;
         }
-        uint32_t nsl;
-        {
-            const uint64_t end = aec_papply(ptile, late ? base : 0ull) + (late ? 0ull : base);
+        __syncthreads();                                               /* S3 */
+
+        /* ---- stream the previous tile's words out, shifted to the absolute bit phase ---- */
+        if (prev_have) {
+            uint32_t *pstage = staging_all + ((it + 1u) & 1u) * a.staging_words;
+            const uint64_t base = s_base;
+            const uint64_t base_l = late ? ((base >> 5) << 5) : base;
+            const uint64_t myabs = base_l + pend.myoff;
+            if (pend.flags & 1u) {
+                uint64_t rsi_idx; uint32_t b;
+                if (a.RP >= (uint32_t)TB) {
+                    uint32_t tpr = a.RP / TB;
+                    rsi_idx = prev_tile / tpr;
+                    b = (uint32_t)(prev_tile % tpr) * TB + tid;
+                } else {
+                    rsi_idx = prev_tile * (TB / a.RP) + tid / a.RP;
+                    b = tid % a.RP;
+                }
+                if (b == 0 && a.rsi_offsets) a.rsi_offsets[rsi_idx] = myabs;
+                if (a.grp_index) {
+                    /* group index for the warp-per-RSI decoder (aec_device.h) */
+                    const uint32_t G = a.grp_G;
+                    if (b % G == 0 && !(pend.flags & 4u)) a.grp_index[rsi_idx * 32ull + b / G] = myabs;
+                    if ((pend.flags & 2u) && pend.len && pend.zrun > 1) {
+                        /* I own a zero run: group starts inside it inherit their leading blocks from me */
+                        uint32_t b0 = b + 1u - pend.zrun;
+                        for (uint32_t g = (b0 / G + 1u) * G; g <= b; g += G)
+                            a.grp_index[rsi_idx * 32ull + g / G] = ((uint64_t)(b - g + 1u) << 56) | (myabs + pend.len);
+                    }
+                }
+            }
+            const uint64_t end = aec_papply(prev_ptile, late ? base : 0ull) + (late ? 0ull : base);
             const uint64_t w0 = base >> 5, we = end >> 5;
             const uint32_t ph = late ? (uint32_t)(base & 31u) : 0u;
             const uint32_t sh = (uint32_t)(base & 31u) - ph;
             const uint32_t tbits = (uint32_t)(end - base);
             const uint32_t nw = (uint32_t)(we - w0) + ((end & 31u) ? 1u : 0u);
-            nsl = (ph + tbits + 31u) >> 5;
+            const uint32_t nsl = (ph + tbits + 31u) >> 5;
             const bool head_partial = (base & 31u) != 0;
             const bool tail_partial = (end & 31u) != 0 && (we > w0 || !head_partial);
             for (uint32_t i = tid; i < nw; i += TB) {
-                uint32_t lo = i < nsl ? staging[i] : 0u;
+                uint32_t lo = i < nsl ? pstage[i] : 0u;
                 uint32_t v = lo;
                 if (sh) {
-                    uint32_t hi = (i >= 1u && i - 1u < nsl) ? staging[i - 1u] : 0u;
+                    uint32_t hi = (i >= 1u && i - 1u < nsl) ? pstage[i - 1u] : 0u;
                     v = (hi << (32u - sh)) | (lo >> sh);
                 }
                 uint64_t wi = w0 + i;
-                if (i == 0 && head_partial) { a.head_c[tile] = (end > base) ? v : 0u; continue; }
-                if (wi == we) { if (tail_partial) a.tail_c[tile] = v; continue; }
+                if (i == 0 && head_partial) { a.head_c[prev_tile] = (end > base) ? v : 0u; continue; }
+                if (wi == we) { if (tail_partial) a.tail_c[prev_tile] = v; continue; }
                 if (wi < a.out_cap_words) a.out_words[wi] = __byte_perm(v, 0, 0x0123);
             }
             if (tid == 0) {
-                if (!head_partial || nw == 0) a.head_c[tile] = 0u;
-                if (!tail_partial) a.tail_c[tile] = 0u;
+                if (!head_partial || nw == 0) a.head_c[prev_tile] = 0u;
+                if (!tail_partial) a.tail_c[prev_tile] = 0u;
             }
+            __syncthreads();                                           /* S4: everyone has read the words */
+            for (uint32_t i = tid; i < nsl + 1u && i < a.staging_words; i += TB) pstage[i] = 0;
         }
-        __syncthreads();                                           /* S4 */
-        for (uint32_t i = tid; i < nsl + 1u && i < a.staging_words; i += TB) staging[i] = 0;
+        if (!have) break;
+        prev_have = true; prev_tile = tile; prev_ptile = ptile; pend = cur;
     }
 }
 
@@ -663,7 +688,9 @@ template <int JT, int B>
 cudaError_t launch_variant(const AecEncArgs &a, uint32_t smem_bytes, int num_sms, cudaStream_t st)
 {
     auto kern = aec_encode_kernel<JT, B>;
-    static uint32_t attr_smem = 48 * 1024;      /* opt in to large dynamic shared memory once */
+    /* opt in to large dynamic shared memory once; the 48 KiB default limit counts the kernel's
+     * static shared variables as well, so leave room for them */
+    static uint32_t attr_smem = 40 * 1024;
     cudaError_t e;
     if (smem_bytes > attr_smem) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
@@ -728,7 +755,7 @@ cudaError_t aec_place_bits_launch(const uint32_t *src, uint64_t nbits, uint32_t 
 
 cudaError_t aec_encode_launch(const AecEncArgs &a, int num_sms, cudaStream_t st)
 {
-    uint32_t smem = a.staging_words * 4u;
+    uint32_t smem = 2u * a.staging_words * 4u;     /* two staging areas (aec_encode_kernel) */
     cudaError_t e;
     switch (a.cfg.J) {
     case 8:  e = launch_j<8>(a, smem, num_sms, st); break;

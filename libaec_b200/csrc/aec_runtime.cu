@@ -74,6 +74,7 @@ namespace {
 int fail_cuda(aecb200_ctx *c, cudaError_t e, const char *what)
 {
     snprintf(c->err, sizeof c->err, "%s: %s", what, cudaGetErrorString(e));
+    fprintf(stderr, "aecb200: CUDA failure in %s\n", c->err);     /* never silent: there is no fallback path */
     return AECB200_CUDA_ERROR;
 }
 #define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(ctx, e_, what); } while (0)
