@@ -17,9 +17,11 @@
 #if defined(__CUDACC__)
 #define AEC_HD __host__ __device__ __forceinline__
 #define AEC_HDM __host__ __device__ __forceinline__      /* member functions */
+#define AEC_HDM_COLD __host__ __device__ __noinline__     /* rare paths kept out of the unrolled code */
 #else
 #define AEC_HD static inline
 #define AEC_HDM inline
+#define AEC_HDM_COLD inline
 #endif
 
 /* flag bits: same values as include/libaec.h */
@@ -123,6 +125,18 @@ AEC_HD uint32_t aec_funnel(uint32_t hi, uint32_t lo, uint32_t sh)
 #endif
 }
 
+/* x << s for s in 0..2^32-1 (zero when s >= 32) */
+AEC_HD uint32_t aec_shl(uint32_t x, uint32_t s)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
+    return r;
+#else
+    return s < 32u ? x << s : 0u;
+#endif
+}
+
 /* One sample from `B` storage bytes (results of encode_accessors.c:61-143). */
 AEC_HD uint32_t aec_load_sample(const uint8_t *p, uint32_t B, uint32_t msb)
 {
@@ -192,13 +206,20 @@ AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t 
     BlockInfo bi;
     bi.klo = 0; bi.khi = c.kmax; bi.len = 0; bi.opt = OPT_ZERO;
 
-    uint32_t orv = 0;
-    uint64_t S0 = 0;
+    uint32_t orv = 0, s32 = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (uint32_t i = 0; i < J; i++) { orv |= d[i]; S0 += d[i]; }
+    for (uint32_t i = 0; i < J; i++) { orv |= d[i]; s32 += d[i]; }
     if (orv == 0) return bi;
+    uint64_t S0 = s32;
+    if (orv >> 25) {       /* J <= 64 values below 2^25 cannot overflow 32 bits; otherwise add again in 64 */
+        S0 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t i = 0; i < J; i++) S0 += d[i];
+    }
 
     const uint32_t thisbs = J - ref;
     const uint32_t unc = thisbs * c.n;                 /* encode.c:270, :746 */
@@ -289,21 +310,9 @@ AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t 
 
     /* ---- second extension (encode.c:412-434) ---- */
     uint32_t se = 0xFFFFFFFFu;
-    if (S0 <= unc) {       /* se >= 1 + J/2 + S0, so larger S0 can never win */
-        uint64_t len = 1;
-        bool inf = false;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (uint32_t i = 0; i < J; i += 2) {
-            uint64_t s = (uint64_t)d[i] + (uint64_t)d[i + 1];
-            len += s * (s + 1) / 2 + d[i + 1] + 1;
-            if (len > unc) { inf = true; break; }
-        }
-        if (!inf) se = (uint32_t)len;
-    } else if (orv >= 0x80000000u) {
-        /* the reference adds in u64 with wrap-around: only
-         * reachable when a pair sum reaches 2^32; replicate exactly */
+    /* se >= 1 + J/2 + S0, so a larger S0 can never win -- except that the reference adds in u64
+     * with wrap-around, reachable only when a pair sum reaches 2^32 */
+    if (S0 <= unc || orv >= 0x80000000u) {
         uint64_t len = 1;
         bool inf = false;
 #if defined(__CUDA_ARCH__)
@@ -367,11 +376,21 @@ AEC_HD uint32_t aec_clampu(uint32_t v, uint32_t lo, uint32_t hi)
 {
     return v < lo ? lo : (v > hi ? hi : v);
 }
-AEC_HD uint32_t aec_kpair(uint32_t lo, uint32_t hi) { return lo | (hi << 8); }
+/* pair layout: lo in bits 15..0, hi in bits 31..16 (two u16 lanes, so that the device
+ * composes both bounds with one VIMNMX.U16x2 max and one min) */
+AEC_HD uint32_t aec_kpair(uint32_t lo, uint32_t hi) { return lo | (hi << 16); }
+AEC_HD uint32_t aec_klo(uint32_t p) { return p & 0xFFFFu; }
+AEC_HD uint32_t aec_khi(uint32_t p) { return p >> 16; }
+AEC_HD uint32_t aec_kapply(uint32_t k, uint32_t p) { return aec_clampu(k, aec_klo(p), aec_khi(p)); }
 AEC_HD uint32_t aec_kcompose(uint32_t x, uint32_t y)
 {
-    uint32_t ylo = y & 0xFFu, yhi = y >> 8;
-    return aec_kpair(aec_clampu(x & 0xFFu, ylo, yhi), aec_clampu(x >> 8, ylo, yhi));
+#if defined(__CUDA_ARCH__)
+    const uint32_t ylo = __byte_perm(y, 0, 0x1010), yhi = __byte_perm(y, 0, 0x3232);
+    return __vminu2(__vmaxu2(x, ylo), yhi);
+#else
+    uint32_t ylo = aec_klo(y), yhi = aec_khi(y);
+    return aec_kpair(aec_clampu(aec_klo(x), ylo, yhi), aec_clampu(aec_khi(x), ylo, yhi));
+#endif
 }
 
 /* Position monoid for AEC_PAD_RSI: f(p) = has_end ? roundup8(p + a) + rest : p + a. */
@@ -401,96 +420,102 @@ AEC_HD uint64_t aec_papply(const PosFn &f, uint64_t p)
 /* The buffer holds big-endian-bit-order 32-bit words (bit 31 of word 0 is the
  * first stream bit).  A CDS shares its first and last word with its
  * neighbours, so those two are merged with OR (atomic on the GPU, where the
- * buffer is shared memory written by 256 threads); interior words are owned
- * exclusively and stored plainly. */
+ * buffer is shared memory written by all threads of the CTA); interior words
+ * are owned exclusively and stored plainly.
+ *
+ * The bits wait in a right-aligned 64-bit accumulator (hi:lo, `fill` valid
+ * bits, fill < 32 between calls); a put shifts the field in and writes one
+ * word out when 32 bits are complete.  There is no data-dependent branch in
+ * put(): the word store is predicated. */
 struct BitPack {
     uint32_t *buf;
-    uint32_t sbase;   /* device: shared-window byte address of buf[0] */
-    uint32_t cur;     /* bits accumulated for word widx, MSB first */
-    uint32_t fill;    /* bits of cur in use (may reach 32 transiently) */
-    uint32_t widx;
-    uint32_t wfirst;  /* index of the CDS's first word (shared with the previous CDS) */
+    uint32_t lo, hi;  /* accumulator, valid bits [0, fill) */
+    uint32_t fill;
+    uint32_t wcur;    /* device: shared-window byte address of the word being filled; host: word index */
+    uint32_t wfirst;  /* the CDS's first word (shared with the previous CDS) */
 
-    AEC_HDM void merge(uint32_t idx, uint32_t v)
+    AEC_HDM void merge(uint32_t v)
     {
 #if defined(__CUDA_ARCH__)
-        asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(sbase + idx * 4u), "r"(v) : "memory");
+        asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(wcur), "r"(v) : "memory");
 #else
-        buf[idx] |= v;
+        buf[wcur] |= v;
 #endif
     }
-    AEC_HDM void store(uint32_t idx, uint32_t v)
+    AEC_HDM void init(uint32_t *b, uint32_t bitpos)
     {
+        buf = b; lo = 0; hi = 0; fill = bitpos & 31u;
 #if defined(__CUDA_ARCH__)
-        asm volatile("st.shared.u32 [%0], %1;" :: "r"(sbase + idx * 4u), "r"(v) : "memory");
+        wcur = (uint32_t)__cvta_generic_to_shared(b) + ((bitpos >> 5) << 2);
 #else
-        buf[idx] = v;
+        wcur = bitpos >> 5;
 #endif
+        wfirst = wcur;
     }
-    AEC_HDM void init(uint32_t *b, uint64_t bitpos)
-    {
-        buf = b; cur = 0; fill = (uint32_t)(bitpos & 31u); widx = (uint32_t)(bitpos >> 5);
-        wfirst = widx;
-#if defined(__CUDA_ARCH__)
-        sbase = (uint32_t)__cvta_generic_to_shared(b);
-#else
-        sbase = 0;
-#endif
-    }
-    AEC_HDM void flush_word()
-    {
-        if (widx == wfirst) merge(widx, cur);
-        else store(widx, cur);
-        cur = 0;
-    }
-    /* append len (1..32) bits of v (v < 2^len) */
+    /* append len (0..32) bits of v (v < 2^len) */
     AEC_HDM void put(uint32_t v, uint32_t len)
     {
-        if (fill >= 32) { flush_word(); widx += fill >> 5; fill &= 31u; }
-        uint32_t space = 32u - fill;
-        if (len < space) {
-            cur |= v << (space - len);
-            fill += len;
-        } else {
-            uint32_t rem = len - space;
-            cur |= v >> rem;
-            flush_word();
-            widx++;
-            cur = rem ? (v << (32u - rem)) : 0u;
-            fill = rem;
+#if defined(__CUDA_ARCH__)
+        hi = __funnelshift_lc(lo, hi, len);
+        asm("shl.b32 %0, %1, %2;" : "=r"(lo) : "r"(lo), "r"(len));     /* PTX shifts clamp: len == 32 gives 0 */
+        lo |= v;
+        fill += len;
+        if (fill >= 32u) {
+            const uint32_t w = __funnelshift_r(lo, hi, fill);             /* bits [fill-32, fill) */
+            if (wcur == wfirst) asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(wcur), "r"(w) : "memory");
+            else                asm volatile("st.shared.u32 [%0], %1;" :: "r"(wcur), "r"(w) : "memory");
+            wcur += 4u;
         }
+        fill &= 31u;
+#else
+        uint64_t acc = ((uint64_t)hi << 32) | lo;
+        acc = (len >= 32u ? (acc << 16) << 16 : acc << len) | v;
+        fill += len;
+        if (fill >= 32u) {
+            const uint32_t w = (uint32_t)(acc >> (fill - 32u));
+            if (wcur == wfirst) buf[wcur] |= w; else buf[wcur] = w;
+            wcur++;
+            fill -= 32u;
+        }
+        lo = (uint32_t)acc; hi = (uint32_t)(acc >> 32);
+#endif
     }
     /* fundamental sequence: fs zeros then a one */
+    AEC_HDM_COLD void put_fs_long(uint32_t fs)
+    {
+        while (fs >= 32u) { put(0u, 32u); fs -= 32u; }
+        put(1u, fs + 1u);
+    }
     AEC_HDM void put_fs(uint32_t fs)
     {
-        fill += fs;
-        if (fill >= 32) { flush_word(); widx += fill >> 5; fill &= 31u; }
-        cur |= 0x80000000u >> fill;
-        fill++;
+        if (fs < 32u) put(1u, fs + 1u);
+        else put_fs_long(fs);
     }
     AEC_HDM void finish()
     {
-        if (cur) merge(widx, cur);
+        if (fill) merge(lo << (32u - fill));
     }
 };
 
 /*
  * Emit the CDS of one non-zero block (results of encode.c:520-563).
- *   d      mapped samples; refs: raw reference sample when ref
+ *   d      mapped samples (d[0] == 0 in a reference block); refs: raw reference sample when ref
  *   k      split position (already clamp(k_prev, klo, khi))
  * Fields are combined four samples at a time before they go through the
  * word packer: a group's unary codes (or its k-bit remainders) usually fit
- * one 32-bit field, which cuts the data-dependent word-flush branches 4x.
+ * one 32-bit field.
  */
 template <int JT>
 AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint32_t opt,
                            uint32_t k, uint32_t ref, uint32_t refs)
 {
     const uint32_t J = JT ? (uint32_t)JT : c.J;
+    constexpr int NQ = (JT ? JT : AEC_MAX_J) / 4 + ((JT ? JT : AEC_MAX_J) % 4 ? 1 : 0);
     if (opt == OPT_SPLIT) {
         bp.put(k + 1, c.idl);
-        if (ref) bp.put(refs, c.n);
-        /* unary part */
+        bp.put(ref ? refs : 0u, ref ? c.n : 0u);
+        /* unary part: the codes of four samples as one field when they fit 32 bits */
+        uint32_t qa[NQ], ql[NQ], lmax = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -500,24 +525,27 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
 #pragma unroll
 #endif
             for (uint32_t j = 0; j < 4; j++) {
-                uint32_t i = g + j;
-                if (i < ref || i >= J) continue;
-                uint32_t s1 = (d[i] >> k) + 1u;
-                acc = (acc << (s1 > 31u ? 31u : s1)) | 1u;
-                len += s1 > 64u ? 64u : s1;
+                const uint32_t i = g + j;
+                if (i >= J) continue;
+                uint32_t s1 = (d[i] >> k) + 1u, one = 1u;
+                if (i == 0) { s1 -= ref; one -= ref; }        /* d[0] == 0 in a reference block: nothing to emit */
+                acc = aec_shl(acc, s1) | one;
+                len += s1;                                     /* a chosen option has sum(fs) < J*n: no overflow */
             }
-            if (len <= 32u) {
-                if (len) bp.put(acc, len);
-            } else {
+            qa[g >> 2] = acc; ql[g >> 2] = len;
+            lmax = len > lmax ? len : lmax;
+        }
+        if (lmax <= 32u) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-                for (uint32_t j = 0; j < 4; j++) {
-                    uint32_t i = g + j;
-                    if (i < ref || i >= J) continue;
-                    bp.put_fs(d[i] >> k);
-                }
-            }
+            for (uint32_t g = 0; g < J; g += 4) bp.put(qa[g >> 2], ql[g >> 2]);
+        } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (uint32_t i = 0; i < J; i++)
+                if (i >= ref) bp.put_fs_long(d[i] >> k);
         }
         /* binary part: k low bits of every sample */
         if (k) {
@@ -532,41 +560,32 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
 #pragma unroll
 #endif
                     for (uint32_t j = 0; j < 4; j++) {
-                        uint32_t i = g + j;
-                        if (i < ref || i >= J) continue;
+                        const uint32_t i = g + j;
+                        if (i >= J) continue;
                         acc = (acc << k) | (d[i] & m);
                         len += k;
                     }
-                    if (len) bp.put(acc, len);
+                    if (g == 0) len -= ref * k;
+                    bp.put(acc, len);
                 }
             } else if (k <= 16) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
                 for (uint32_t g = 0; g < J; g += 2) {
-                    uint32_t acc = 0, len = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                    for (uint32_t j = 0; j < 2; j++) {
-                        uint32_t i = g + j;
-                        if (i < ref || i >= J) continue;
-                        acc = (acc << k) | (d[i] & m);
-                        len += k;
-                    }
-                    if (len) bp.put(acc, len);
+                    const uint32_t acc = ((d[g] & m) << k) | (d[g + 1] & m);
+                    bp.put(acc, (g == 0 && ref) ? k : 2u * k);
                 }
             } else {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-                for (uint32_t i = 0; i < J; i++)
-                    if (i >= ref) bp.put(d[i] & m, k);
+                for (uint32_t i = 0; i < J; i++) bp.put(d[i] & m, (i == 0 && ref) ? 0u : k);
             }
         }
     } else if (opt == OPT_SE) {
         bp.put(1, c.idl + 1);
-        if (ref) bp.put(refs, c.n);
+        bp.put(ref ? refs : 0u, ref ? c.n : 0u);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -588,7 +607,7 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
 AEC_HD void aec_pack_zero(const AecCfg &c, BitPack &bp, uint32_t fs_code, uint32_t zref, uint32_t refs)
 {
     bp.put(0, c.idl + 1);
-    if (zref) bp.put(refs, c.n);
+    bp.put(zref ? refs : 0u, zref ? c.n : 0u);
     bp.put_fs(fs_code);
 }
 

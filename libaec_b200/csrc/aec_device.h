@@ -38,6 +38,11 @@ struct AecEncArgs {
     uint64_t *rsi_offsets;      /* optional [nrsi] absolute start bit of each RSI */
     uint64_t *grp_index;        /* optional [nrsi*32] group index for the warp-per-RSI decoder (see AecDecArgs) */
     uint32_t grp_G;             /* blocks per group = ceil(rsi / 32) */
+    /* filled by aec_encode_launch */
+    uint32_t tpr;               /* tiles per RSI when RP >= TB, else 0 */
+    uint32_t rp_shift;          /* log2(RP) when RP < TB */
+    uint32_t tile_rsi_shift;    /* log2(TB / RP) when RP < TB */
+    uint32_t grp_magic;         /* floor(2^32 / grp_G) + 1: b / grp_G == umulhi(b, grp_magic) for b < 4096; 0 when grp_G == 1 */
     uint64_t *result;           /* [0] end bit, [1] k after the last block, [2..5] shard summary (lo, hi, first constant tile, last 64 bits) */
 };
 

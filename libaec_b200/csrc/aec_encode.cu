@@ -41,7 +41,7 @@ constexpr uint64_t ST_AGG = 1, ST_PREFIX = 2;
 
 __device__ __forceinline__ uint64_t desc_pack_agg(const PosFn &f, uint32_t kp)
 {
-    return ST_AGG | ((uint64_t)(kp & 0x1Fu) << 2) | ((uint64_t)((kp >> 8) & 0x1Fu) << 7) |
+    return ST_AGG | ((uint64_t)(aec_klo(kp) & 0x1Fu) << 2) | ((uint64_t)(aec_khi(kp) & 0x1Fu) << 7) |
            ((uint64_t)(f.has_end & 1u) << 12) | ((f.a & 0x1FFFFFull) << 13) | ((f.rest & 0x1FFFFFull) << 34);
 }
 __device__ __forceinline__ uint64_t desc_pack_prefix(uint64_t bits, uint32_t k)
@@ -214,16 +214,16 @@ __device__ __noinline__ void aec_encode_scanner(const AecEncArgs &a, uint64_t *s
         const uint64_t P = *reinterpret_cast<volatile uint64_t *>(&s_carry_pos[b & 1]);
         const uint32_t kc = *reinterpret_cast<volatile uint32_t *>(&s_carry_k[b & 1]);
         const uint64_t pos = aec_papply(fe, P);
-        const uint32_t k = aec_clampu(kc, ke & 0xFFu, ke >> 8);
+        const uint32_t k = aec_kapply(kc, ke);
         const uint64_t end = aec_papply(f, pos);
         if (lane == 31) {
             *reinterpret_cast<volatile uint64_t *>(&s_carry_pos[(b + 1) & 1]) = end;
-            *reinterpret_cast<volatile uint32_t *>(&s_carry_k[(b + 1) & 1]) = aec_clampu(k, kj & 0xFFu, kj >> 8);
+            *reinterpret_cast<volatile uint32_t *>(&s_carry_k[(b + 1) & 1]) = aec_kapply(k, kj);
             __threadfence_block();
             *s_done = (uint32_t)(b + 1);
             if (b + 1 == nbatch && a.ntiles == a.ntiles_total) {
                 /* lane 31 of the last batch: identity tiles beyond the end keep the totals */
-                a.result[0] = end; a.result[1] = aec_clampu(k, kj & 0xFFu, kj >> 8);
+                a.result[0] = end; a.result[1] = aec_kapply(k, kj);
             }
         }
         if (t < a.ntiles) {
@@ -256,9 +256,27 @@ __device__ __forceinline__ void pair_barrier(uint32_t warp)
     asm volatile("bar.sync %0, 64;" :: "r"(1u + (warp >> 1)) : "memory");
 }
 
+/* One sample at index idx (the lane-0 look-back and the zero-run reference). */
+template <int B>
+__device__ __forceinline__ uint32_t load_one(const uint8_t *in, uint64_t idx, uint32_t msb, uint32_t aligned)
+{
+    if (B == 4 && aligned) {
+        uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(in) + idx);
+        return msb ? __byte_perm(v, 0, 0x0123) : v;
+    }
+    if (B == 2 && aligned) {
+        uint32_t v = __ldg(reinterpret_cast<const uint16_t *>(in) + idx);
+        return msb ? __byte_perm(v, 0, 0x4401) : v;
+    }
+    if (B == 1) return __ldg(in + idx);
+    return aec_load_sample(in + idx * B, B, msb);
+}
+
 /* Per-thread facts about a tile whose words still have to be streamed out. */
 struct PendingBlock {
-    uint64_t myoff;      /* bit offset inside the tile's staging area */
+    uint64_t rsi;        /* RSI of my block */
+    uint32_t b;          /* block index inside the RSI */
+    uint32_t myoff;      /* bit offset inside the tile's staging area */
     uint32_t len;        /* CDS bits */
     uint32_t zrun;       /* zero-run length when this block owns a run */
     uint32_t flags;      /* bit0 valid, bit1 all-zero block, bit2 inherits a zero run */
@@ -279,8 +297,14 @@ aec_encode_kernel(const AecEncArgs a)
      * bit phase mod 8, so its bits can only be laid out once its prefix is known */
     const bool late = c.pad && a.RP > (uint32_t)TB;
 
-    extern __shared__ uint32_t staging_all[];      /* two staging areas: tile it packs while tile it-1 streams out */
+    /* two staging areas of SW words: tile `it` packs into one while tile it-1 streams out of the
+     * other; word 0 of an area stays zero (the word "before" the tile for the funnel shift) */
+    extern __shared__ uint4 staging_raw[];
+    uint32_t *const staging_all = reinterpret_cast<uint32_t *>(staging_raw);
+    const uint32_t SW = a.staging_words;
     __shared__ uint32_t s_ticket[2];
+    __shared__ unsigned long long s_rsi0[2]; /* first RSI of the claimed tile */
+    __shared__ uint32_t s_b0[2];             /* first block slot of the tile inside that RSI (RP >= TB) */
     __shared__ uint32_t s_zb[NWARP + 1];
     __shared__ uint32_t s_wlen[NWARP];       /* per-warp sums (no-pad mode) */
     __shared__ uint32_t s_wend[NWARP], s_wa[NWARP], s_wrest[NWARP];   /* per-warp PosFn (pad mode) */
@@ -295,34 +319,36 @@ aec_encode_kernel(const AecEncArgs a)
         aec_encode_scanner<NWARP>(a, reinterpret_cast<uint64_t *>(s_cpos), s_ck, &s_sdone);
         return;
     }
-    for (uint32_t i = tid; i < 2u * a.staging_words; i += TB) staging_all[i] = 0;
-    if (tid == 0) s_ticket[0] = atomicAdd(a.ticket, 1u);
+    /* claim the next tile in order and work out where it sits (thread 0 only) */
+    auto claim = [&](uint32_t slot) {
+        const uint32_t t = atomicAdd(a.ticket, 1u);
+        s_ticket[slot] = t;
+        if (a.tpr) { const uint32_t q = t / a.tpr; s_rsi0[slot] = q; s_b0[slot] = (t - q * a.tpr) * (uint32_t)TB; }
+        else { s_rsi0[slot] = (unsigned long long)t << a.tile_rsi_shift; s_b0[slot] = 0; }
+    };
+    for (uint32_t i = tid; i < 2u * SW; i += TB) staging_all[i] = 0;
+    if (tid == 0) claim(0);
     __syncthreads();
 
     /* the previous tile of this CTA: packed, aggregate published, words not yet written */
     bool prev_have = false;
-    uint64_t prev_tile = 0;
+    uint32_t prev_tile = 0;
     PosFn prev_ptile; prev_ptile.has_end = 0; prev_ptile.a = 0; prev_ptile.rest = 0;
-    PendingBlock pend; pend.myoff = 0; pend.len = 0; pend.zrun = 0; pend.flags = 0;
+    PendingBlock pend; pend.rsi = 0; pend.b = 0; pend.myoff = 0; pend.len = 0; pend.zrun = 0; pend.flags = 0;
 
     for (uint32_t it = 0;; it++) {
-        const uint64_t tile = s_ticket[it & 1u];
+        const uint32_t slot = it & 1u;
+        const uint32_t tile = s_ticket[slot];
         const bool have = tile < a.ntiles;
-        uint32_t *staging = staging_all + (it & 1u) * a.staging_words;
+        uint32_t *staging = staging_all + slot * SW + 1u;
         PosFn ptile; ptile.has_end = 0; ptile.a = 0; ptile.rest = 0;
-        PendingBlock cur; cur.myoff = 0; cur.len = 0; cur.zrun = 0; cur.flags = 0;
+        PendingBlock cur; cur.rsi = 0; cur.b = 0; cur.myoff = 0; cur.len = 0; cur.zrun = 0; cur.flags = 0;
 
         if (have) {
             /* ---- which block is mine ---- */
-            uint64_t rsi_idx; uint32_t b;
-            if (a.RP >= (uint32_t)TB) {
-                uint32_t tpr = a.RP / TB;
-                rsi_idx = tile / tpr;
-                b = (uint32_t)(tile % tpr) * TB + tid;
-            } else {
-                rsi_idx = tile * (TB / a.RP) + tid / a.RP;
-                b = tid % a.RP;
-            }
+            uint64_t rsi_idx = s_rsi0[slot]; uint32_t b;
+            if (a.tpr) b = s_b0[slot] + tid;
+            else { rsi_idx += tid >> a.rp_shift; b = tid & (a.RP - 1u); }
             uint32_t nblk = 0;
             if (rsi_idx + 1 < a.nrsi) nblk = c.rsi;
             else if (rsi_idx + 1 == a.nrsi) nblk = a.last_nblk;
@@ -344,7 +370,7 @@ aec_encode_kernel(const AecEncArgs a)
                     else if (lane == 0) {
                         uint64_t pi = first - 1;
                         if (pi >= a.nsamples) pi = a.nsamples - 1;
-                        prev = aec_load_sample(a.in + pi * c.B, c.B, c.msb);
+                        prev = load_one<B>(a.in, pi, c.msb, a.aligned);
                     }
                     prev ^= c.sflip;
 #pragma unroll
@@ -376,10 +402,8 @@ aec_encode_kernel(const AecEncArgs a)
                 len = aec_zero_run(c, segmask, V, b, &zcode, &zref, &zrun);
                 zinherit = (b & 63u) != 0 && ((segmask >> ((b & 63u) - 1u)) & 1ull);
             }
-            if (zref) {   /* run owner needs the reference sample of block 0 of the RSI */
-                uint64_t f0 = rsi_idx * (uint64_t)c.R;
-                refs = aec_load_sample(a.in + f0 * c.B, c.B, c.msb);
-            }
+            if (zref)     /* run owner needs the reference sample of block 0 of the RSI */
+                refs = load_one<B>(a.in, rsi_idx * (uint64_t)c.R, c.msb, a.aligned);
             const bool rsi_end = valid && (b + 1 == nblk);
 
             /* ---- intra-warp inclusive scans: CDS lengths and the k clamp chain ---- */
@@ -464,7 +488,7 @@ aec_encode_kernel(const AecEncArgs a)
             }
 
             /* ---- pack my CDS into this tile's staging area, at local bit phase 0 ---- */
-            uint64_t myoff = pexc.a;
+            uint32_t myoff = (uint32_t)pexc.a;
             if (late) {
                 /* bit layout needs the absolute phase: wait for this tile's prefix */
                 if (tid == 0) {
@@ -474,9 +498,9 @@ aec_encode_kernel(const AecEncArgs a)
                 }
                 __syncthreads();
                 const uint64_t bs = s_base_cur;
-                myoff = aec_papply(pexc, bs) - ((bs >> 5) << 5);
+                myoff = (uint32_t)(aec_papply(pexc, bs) - ((bs >> 5) << 5));
             } else if (c.pad) {
-                myoff = aec_papply(pexc, 0);
+                myoff = (uint32_t)aec_papply(pexc, 0);
             }
             if (valid && len) {
                 BitPack bp;
@@ -486,13 +510,13 @@ aec_encode_kernel(const AecEncArgs a)
                 } else {
                     uint32_t k = bi.klo;
                     if (bi.opt == OPT_SPLIT && bi.klo != bi.khi) {
-                        uint32_t kprev = kbefore & 0xFFu;
-                        if (kprev != (kbefore >> 8)) {
+                        uint32_t kprev = aec_klo(kbefore);
+                        if (kprev != aec_khi(kbefore)) {
                             /* a plateau block before the tile's first fixed k: its split position depends on
                              * the k carried into the tile, i.e. on this tile's prefix (rare) */
                             uint64_t pv = ld_volatile_u64(&a.pref[tile]);
                             while ((pv & 3) == 0) pv = ld_volatile_u64(&a.pref[tile]);
-                            kprev = aec_clampu((uint32_t)(pv >> 2) & 0x1Fu, kbefore & 0xFFu, kbefore >> 8);
+                            kprev = aec_kapply((uint32_t)(pv >> 2) & 0x1Fu, kbefore);
                         }
                         k = aec_clampu(kprev, bi.klo, bi.khi);
                     }
@@ -500,7 +524,7 @@ aec_encode_kernel(const AecEncArgs a)
                 }
                 bp.finish();
             }
-            cur.myoff = myoff; cur.len = len; cur.zrun = zrun;
+            cur.rsi = rsi_idx; cur.b = b; cur.myoff = myoff; cur.len = len; cur.zrun = zrun;
             cur.flags = (valid ? 1u : 0u) | (is_zero ? 2u : 0u) | (zinherit ? 4u : 0u);
         }
 
@@ -513,66 +537,59 @@ aec_encode_kernel(const AecEncArgs a)
                 while ((pv & 3) == 0) pv = ld_volatile_u64(&a.pref[prev_tile]);
                 s_base = pv >> 12;
             }
-            s_ticket[(it + 1u) & 1u] = have ? atomicAdd(a.ticket, 1u) : 0xFFFFFFFFu;
+            if (have) claim(slot ^ 1u); else s_ticket[slot ^ 1u] = 0xFFFFFFFFu;
         }
         __syncthreads();                                               /* S3 */
 
         /* ---- stream the previous tile's words out, shifted to the absolute bit phase ---- */
         if (prev_have) {
-            uint32_t *pstage = staging_all + ((it + 1u) & 1u) * a.staging_words;
+            uint32_t *pstage = staging_all + (slot ^ 1u) * SW + 1u;
             const uint64_t base = s_base;
-            const uint64_t base_l = late ? ((base >> 5) << 5) : base;
-            const uint64_t myabs = base_l + pend.myoff;
             if (pend.flags & 1u) {
-                uint64_t rsi_idx; uint32_t b;
-                if (a.RP >= (uint32_t)TB) {
-                    uint32_t tpr = a.RP / TB;
-                    rsi_idx = prev_tile / tpr;
-                    b = (uint32_t)(prev_tile % tpr) * TB + tid;
-                } else {
-                    rsi_idx = prev_tile * (TB / a.RP) + tid / a.RP;
-                    b = tid % a.RP;
-                }
-                if (b == 0 && a.rsi_offsets) a.rsi_offsets[rsi_idx] = myabs;
+                const uint64_t myabs = (late ? ((base >> 5) << 5) : base) + pend.myoff;
+                if (pend.b == 0 && a.rsi_offsets) a.rsi_offsets[pend.rsi] = myabs;
                 if (a.grp_index) {
                     /* group index for the warp-per-RSI decoder (aec_device.h) */
                     const uint32_t G = a.grp_G;
-                    if (b % G == 0 && !(pend.flags & 4u)) a.grp_index[rsi_idx * 32ull + b / G] = myabs;
+                    const uint32_t q = a.grp_magic ? __umulhi(pend.b, a.grp_magic) : pend.b;    /* b / G */
+                    if (q * G == pend.b && !(pend.flags & 4u)) a.grp_index[pend.rsi * 32ull + q] = myabs;
                     if ((pend.flags & 2u) && pend.len && pend.zrun > 1) {
                         /* I own a zero run: group starts inside it inherit their leading blocks from me */
-                        uint32_t b0 = b + 1u - pend.zrun;
-                        for (uint32_t g = (b0 / G + 1u) * G; g <= b; g += G)
-                            a.grp_index[rsi_idx * 32ull + g / G] = ((uint64_t)(b - g + 1u) << 56) | (myabs + pend.len);
+                        uint32_t b0 = pend.b + 1u - pend.zrun;
+                        for (uint32_t g = (b0 / G + 1u) * G; g <= pend.b; g += G)
+                            a.grp_index[pend.rsi * 32ull + g / G] = ((uint64_t)(pend.b - g + 1u) << 56) | (myabs + pend.len);
                     }
                 }
             }
             const uint64_t end = aec_papply(prev_ptile, late ? base : 0ull) + (late ? 0ull : base);
             const uint64_t w0 = base >> 5, we = end >> 5;
-            const uint32_t ph = late ? (uint32_t)(base & 31u) : 0u;
-            const uint32_t sh = (uint32_t)(base & 31u) - ph;
-            const uint32_t tbits = (uint32_t)(end - base);
-            const uint32_t nw = (uint32_t)(we - w0) + ((end & 31u) ? 1u : 0u);
-            const uint32_t nsl = (ph + tbits + 31u) >> 5;
+            const uint32_t sh = late ? 0u : (uint32_t)(base & 31u);      /* staging is at phase 0 unless late */
+            const uint32_t nsl = ((late ? (uint32_t)(base & 31u) : 0u) + (uint32_t)(end - base) + 31u) >> 5;
             const bool head_partial = (base & 31u) != 0;
             const bool tail_partial = (end & 31u) != 0 && (we > w0 || !head_partial);
-            for (uint32_t i = tid; i < nw; i += TB) {
-                uint32_t lo = i < nsl ? pstage[i] : 0u;
-                uint32_t v = lo;
-                if (sh) {
-                    uint32_t hi = (i >= 1u && i - 1u < nsl) ? pstage[i - 1u] : 0u;
-                    v = (hi << (32u - sh)) | (lo >> sh);
-                }
-                uint64_t wi = w0 + i;
-                if (i == 0 && head_partial) { a.head_c[prev_tile] = (end > base) ? v : 0u; continue; }
-                if (wi == we) { if (tail_partial) a.tail_c[prev_tile] = v; continue; }
-                if (wi < a.out_cap_words) a.out_words[wi] = __byte_perm(v, 0, 0x0123);
+            /* output word w0+i = staging bits [32 i - sh, 32 i - sh + 32); words [i_lo, i_hi) belong to this
+             * tile alone, the partial ones at either end go to the side arrays for the fix-up kernel */
+            const uint32_t nwhole = (uint32_t)(we - w0);
+            uint32_t i_hi = nwhole;
+            {
+                const uint64_t capw = a.out_cap_words > w0 ? a.out_cap_words - w0 : 0ull;
+                if ((uint64_t)i_hi > capw) i_hi = (uint32_t)capw;
             }
-            if (tid == 0) {
-                if (!head_partial || nw == 0) a.head_c[prev_tile] = 0u;
-                if (!tail_partial) a.tail_c[prev_tile] = 0u;
+            uint32_t *dst = a.out_words + w0;
+            for (uint32_t i = (head_partial ? 1u : 0u) + tid; i < i_hi; i += TB) {
+                const uint32_t v = __funnelshift_r(pstage[i], pstage[(int)i - 1], sh);
+                dst[i] = __byte_perm(v, 0, 0x0123);
             }
+            if (tid == 0)
+                a.head_c[prev_tile] = (head_partial && end > base) ? (pstage[0] >> sh) : 0u;
+            if (tid == 32)
+                a.tail_c[prev_tile] = tail_partial ? __funnelshift_r(pstage[nwhole], pstage[(int)nwhole - 1], sh) : 0u;
             __syncthreads();                                           /* S4: everyone has read the words */
-            for (uint32_t i = tid; i < nsl + 1u && i < a.staging_words; i += TB) pstage[i] = 0;
+            {
+                uint4 *z = reinterpret_cast<uint4 *>(staging_all + (slot ^ 1u) * SW);
+                const uint32_t n4 = (nsl + 5u) >> 2;                   /* pad word + nsl words + one spare */
+                for (uint32_t i = tid; i < n4; i += TB) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
         if (!have) break;
         prev_have = true; prev_tile = tile; prev_ptile = ptile; pend = cur;
@@ -629,7 +646,7 @@ __global__ void aec_encode_summary_kernel(const AecEncArgs a)
     unsigned long long firstc = ~0ull;
     for (uint64_t t = b0; t < b1; t++) {
         acc = aec_kcompose(acc, a.tile_kagg[t]);
-        if (firstc == ~0ull && (acc & 0xFFu) == (acc >> 8)) firstc = t;
+        if (firstc == ~0ull && aec_klo(acc) == aec_khi(acc)) firstc = t;
     }
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -642,8 +659,8 @@ __global__ void aec_encode_summary_kernel(const AecEncArgs a)
         if (o < firstc) firstc = o;
     }
     if (lane == 31) {
-        a.result[2] = acc & 0xFFu;
-        a.result[3] = acc >> 8;
+        a.result[2] = aec_klo(acc);
+        a.result[3] = aec_khi(acc);
         a.result[4] = (firstc == ~0ull) ? n : firstc;
         /* last 64 bits of the stream, right-aligned: what the next shard needs to complete the
          * word its own first bits share with this shard's last bits */
@@ -732,9 +749,10 @@ uint32_t aec_encode_tile_blocks(uint32_t J)
 uint32_t aec_encode_staging_words(const AecCfg &c)
 {
     uint32_t TB = aec_encode_tile_blocks(c.J);
-    /* every CDS is at most idl + 1 + n + J*n bits, plus RSI padding */
+    /* every CDS is at most idl + 1 + n + J*n bits, plus RSI padding; one zero pad word in
+     * front, spare words behind, a multiple of four words so that both areas stay 16-byte aligned */
     uint64_t bits = 31ull + (uint64_t)TB * (c.idl + 1ull + (uint64_t)c.J * c.n + c.n + 8ull) + 64ull;
-    return (uint32_t)(bits / 32ull + 4ull);
+    return (uint32_t)((bits / 32ull + 8ull + 3ull) & ~3ull);
 }
 
 cudaError_t aec_encode_summary_launch(const AecEncArgs &a, cudaStream_t st)
@@ -753,8 +771,16 @@ cudaError_t aec_place_bits_launch(const uint32_t *src, uint64_t nbits, uint32_t 
     return cudaGetLastError();
 }
 
-cudaError_t aec_encode_launch(const AecEncArgs &a, int num_sms, cudaStream_t st)
+cudaError_t aec_encode_launch(const AecEncArgs &args, int num_sms, cudaStream_t st)
 {
+    AecEncArgs a = args;
+    {   /* derived geometry the kernel would otherwise divide for */
+        const uint32_t TB = aec_encode_tile_blocks(a.cfg.J);
+        a.tpr = a.RP >= TB ? a.RP / TB : 0u;
+        a.rp_shift = 0; while ((1u << a.rp_shift) < a.RP) a.rp_shift++;
+        a.tile_rsi_shift = 0; while (a.RP < TB && ((a.RP << a.tile_rsi_shift) < TB)) a.tile_rsi_shift++;
+        a.grp_magic = a.grp_G > 1u ? (uint32_t)((1ull << 32) / a.grp_G + 1ull) : 0u;
+    }
     uint32_t smem = 2u * a.staging_words * 4u;     /* two staging areas (aec_encode_kernel) */
     cudaError_t e;
     switch (a.cfg.J) {

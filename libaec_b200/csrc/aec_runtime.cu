@@ -235,6 +235,10 @@ int aecb200_encode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
         return AEC_OK;
     }
 
+    if (g.ntiles >= 0xFFFFFFF0ull) {
+        snprintf(ctx->err, sizeof ctx->err, "input too large for one launch (%llu tiles)", (unsigned long long)g.ntiles);
+        return AEC_CONF_ERROR;
+    }
     CK(ctx->desc.ensure(g.ntiles * 8), "cudaMalloc(desc)");
     CK(ctx->pref.ensure(g.ntiles * 8), "cudaMalloc(pref)");
     CK(ctx->headc.ensure(g.ntiles * 4), "cudaMalloc(head)");

@@ -121,7 +121,7 @@ extern "C" int model_encode(uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags
             kacc = aec_kcompose(kacc, aec_kpair(S[tid].bi.klo, S[tid].bi.khi));
         }
         const uint64_t end = aec_papply(acc, base);
-        const uint32_t kout = aec_clampu(kin, kacc & 0xFFu, kacc >> 8);
+        const uint32_t kout = aec_kapply(kin, kacc);
         tile_end[tile] = end;
         const uint64_t w0 = base >> 5, we = end >> 5;
         staging.assign((size_t)(we - w0) + 4, 0);
@@ -130,10 +130,10 @@ extern "C" int model_encode(uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags
             uint64_t myoff = aec_papply(pexc[tid], base);
             if (s.valid && s.b == 0 && offsets) offsets[s.rsi_idx] = myoff;
             if (s.valid && s.len) {
-                BitPack bp; bp.init(staging.data(), myoff - (w0 << 5));
+                BitPack bp; bp.init(staging.data(), (uint32_t)(myoff - (w0 << 5)));
                 if (s.is_zero) aec_pack_zero(c, bp, s.zcode, s.zref, s.refs);
                 else {
-                    uint32_t kprev = aec_clampu(kin, kbefore[tid] & 0xFFu, kbefore[tid] >> 8);
+                    uint32_t kprev = aec_kapply(kin, kbefore[tid]);
                     uint32_t k = aec_clampu(kprev, s.bi.klo, s.bi.khi);
                     aec_pack_block<0>(c, bp, s.d, s.bi.opt, k, s.ref, s.refs);
                 }

@@ -1,6 +1,8 @@
+# scratch job runner for gpurun (edited per experiment)
 set -x
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/e_pytest.txt
-timeout 300 python bench.py --device-only --steps 10 --warmup 3 > gpurun_out/e_bench.json 2> gpurun_out/e_bench.err
-for w in c2 c3 c4 c5_noise c5_restricted; do timeout 200 python bench.py --device-only --steps 5 --warmup 3 --workload $w --mib 128 2>&1 | tail -1 >> gpurun_out/e_bench_others.json; done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"aec_(encode|decode_warp)_kernel" -s 6 -c 2 -f -o gpurun_out/prof_e python bench.py --device-only --steps 1 --warmup 3 > gpurun_out/e_ncu.log 2>&1
+T=${TAG:-x}
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/${T}_pytest.txt
+timeout 300 python bench.py --device-only --steps 10 --warmup 3 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
+for w in c2 c3 c4 c5_noise c5_restricted; do timeout 200 python bench.py --device-only --steps 5 --warmup 3 --workload $w --mib 128 2>&1 | tail -1 >> gpurun_out/${T}_bench_others.json; done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"aec_(encode|decode_warp)_kernel" -s 6 -c 2 -f -o gpurun_out/prof_${T} python bench.py --device-only --steps 1 --warmup 3 > gpurun_out/${T}_ncu.log 2>&1
