@@ -460,13 +460,20 @@ struct BitPack {
         asm("shl.b32 %0, %1, %2;" : "=r"(lo) : "r"(lo), "r"(len));     /* PTX shifts clamp: len == 32 gives 0 */
         lo |= v;
         fill += len;
-        if (fill >= 32u) {
-            const uint32_t w = __funnelshift_r(lo, hi, fill);             /* bits [fill-32, fill) */
-            if (wcur == wfirst) asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(wcur), "r"(w) : "memory");
-            else                asm volatile("st.shared.u32 [%0], %1;" :: "r"(wcur), "r"(w) : "memory");
-            wcur += 4u;
-        }
-        fill &= 31u;
+        /* predicated, not branched: whether a put completes a word differs from lane to lane */
+        asm volatile("{\n\t"
+                     ".reg .pred p, q, r;\n\t"
+                     ".reg .b32 w;\n\t"
+                     "setp.ge.u32 p, %0, 32;\n\t"
+                     "shf.r.wrap.b32 w, %2, %3, %0;\n\t"            /* bits [fill-32, fill) */
+                     "setp.eq.and.u32 q, %1, %4, p;\n\t"            /* the CDS's first word is shared */
+                     "setp.ne.and.u32 r, %1, %4, p;\n\t"
+                     "@q red.shared.or.b32 [%1], w;\n\t"
+                     "@r st.shared.b32 [%1], w;\n\t"
+                     "@p add.u32 %1, %1, 4;\n\t"
+                     "and.b32 %0, %0, 31;\n\t"
+                     "}"
+                     : "+r"(fill), "+r"(wcur) : "r"(lo), "r"(hi), "r"(wfirst) : "memory");
 #else
         uint64_t acc = ((uint64_t)hi << 32) | lo;
         acc = (len >= 32u ? (acc << 16) << 16 : acc << len) | v;
@@ -480,16 +487,11 @@ struct BitPack {
         lo = (uint32_t)acc; hi = (uint32_t)(acc >> 32);
 #endif
     }
-    /* fundamental sequence: fs zeros then a one */
-    AEC_HDM_COLD void put_fs_long(uint32_t fs)
+    /* fundamental sequence: fs zeros then a one (the loop only runs for codes longer than 32 bits) */
+    AEC_HDM void put_fs(uint32_t fs)
     {
         while (fs >= 32u) { put(0u, 32u); fs -= 32u; }
         put(1u, fs + 1u);
-    }
-    AEC_HDM void put_fs(uint32_t fs)
-    {
-        if (fs < 32u) put(1u, fs + 1u);
-        else put_fs_long(fs);
     }
     AEC_HDM void finish()
     {
@@ -545,7 +547,7 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
 #pragma unroll
 #endif
             for (uint32_t i = 0; i < J; i++)
-                if (i >= ref) bp.put_fs_long(d[i] >> k);
+                if (i >= ref) bp.put_fs(d[i] >> k);
         }
         /* binary part: k low bits of every sample */
         if (k) {

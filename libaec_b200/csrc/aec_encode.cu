@@ -284,7 +284,7 @@ struct PendingBlock {
 
 template <int JT, int B>
 __global__ void __launch_bounds__(TileCfg<JT>::TB, TileCfg<JT>::MINB)
-aec_encode_kernel(const AecEncArgs a)
+aec_encode_kernel(const __grid_constant__ AecEncArgs a)
 {
     constexpr int TB = TileCfg<JT>::TB;
     constexpr int NWARP = TileCfg<JT>::NWARP;
