@@ -151,10 +151,17 @@ AEC_HD uint32_t aec_load_sample(const uint8_t *p, uint32_t B, uint32_t msb)
  * signedness variants collapse to this single unsigned form). */
 AEC_HD uint32_t aec_map_delta(uint32_t u0, uint32_t u1, uint32_t M)
 {
+#if defined(__CUDA_ARCH__)
+    const uint32_t D = __usad(u1, u0, 0u);                 /* |u1 - u0| in one instruction */
+    const uint32_t zig = D + D - (u1 < u0 ? 1u : 0u);      /* only used when D <= th <= M/2: no overflow */
+    const uint32_t th = min(u0, M - u0);
+    return (D <= th) ? zig : th + D;
+#else
     uint32_t ge = u1 >= u0;
     uint32_t D = ge ? (u1 - u0) : (u0 - u1);
     uint32_t th = (u0 < M - u0) ? u0 : (M - u0);
     return (D <= th) ? (2u * D - (ge ? 0u : 1u)) : (th + D);
+#endif
 }
 
 /* Inverse of aec_map_delta (results of decode.c:89-135). */
@@ -515,9 +522,10 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
     constexpr int NQ = (JT ? JT : AEC_MAX_J) / 4 + ((JT ? JT : AEC_MAX_J) % 4 ? 1 : 0);
     if (opt == OPT_SPLIT) {
         bp.put(k + 1, c.idl);
-        bp.put(ref ? refs : 0u, ref ? c.n : 0u);
+        if (ref) bp.put(refs, c.n);
         /* unary part: the codes of four samples as one field when they fit 32 bits */
         uint32_t qa[NQ], ql[NQ], lmax = 0;
+        if (JT == 0) { for (int q = 0; q < NQ; q++) { qa[q] = 0; ql[q] = 0; } }   /* quads beyond J stay empty */
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -537,7 +545,23 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
             qa[g >> 2] = acc; ql[g >> 2] = len;
             lmax = len > lmax ? len : lmax;
         }
-        if (lmax <= 32u) {
+        /* two quads as one field when every such pair fits 32 bits (the usual case: a put costs
+         * about as much as packing three samples) */
+        uint32_t pmax = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q + 1 < NQ; q += 2) { const uint32_t l2 = ql[q] + ql[q + 1]; pmax = l2 > pmax ? l2 : pmax; }
+        if (NQ > 1 && pmax <= 32u && lmax <= 32u) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int q = 0; q < NQ; q += 2) {
+                if ((uint32_t)q * 4u >= J) continue;
+                if (q + 1 < NQ) bp.put(aec_shl(qa[q], ql[q + 1]) | qa[q + 1], ql[q] + ql[q + 1]);
+                else bp.put(qa[q], ql[q]);
+            }
+        } else if (lmax <= 32u) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -587,7 +611,7 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
         }
     } else if (opt == OPT_SE) {
         bp.put(1, c.idl + 1);
-        bp.put(ref ? refs : 0u, ref ? c.n : 0u);
+        if (ref) bp.put(refs, c.n);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -609,7 +633,7 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
 AEC_HD void aec_pack_zero(const AecCfg &c, BitPack &bp, uint32_t fs_code, uint32_t zref, uint32_t refs)
 {
     bp.put(0, c.idl + 1);
-    bp.put(zref ? refs : 0u, zref ? c.n : 0u);
+    if (zref) bp.put(refs, c.n);
     bp.put_fs(fs_code);
 }
 

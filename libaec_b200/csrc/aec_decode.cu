@@ -201,23 +201,40 @@ struct Rd64 {
     }
 };
 
-/* One block of J mapped values into row[0..J): fast restatement of
- * aec_decode_block for clean streams (anything unusual sets *bad and the RSI
- * is handed to the careful kernel). */
+/* One block of the lane's group: fast restatement of aec_decode_block for clean streams (anything
+ * unusual sets *bad and the RSI is handed to the careful kernel).
+ *
+ * The row does not receive the mapped values d themselves but the lane's running sum of the signed
+ * steps they stand for when nothing clips (d even: +d/2, d odd: -(d+1)/2): with the lane's start
+ * value added, that already is the sample, so clip-free data needs no inverse-predictor pass at all
+ * (DESIGN.md 4.2).  d is recoverable from consecutive sums (the step <-> d map is a bijection on 32
+ * bits), which is what the exact path does when a clip cannot be ruled out.
+ *   pfx        running sum of the lane (wrapping)
+ *   pmin/pmax  lowest / highest running sum so far (how far the lane moves from its start value)
+ *   big        OR of the lane's d (bounds the largest single step) */
 __device__ __forceinline__ uint32_t delta_of(uint32_t dv) { return (dv >> 1) ^ (0u - (dv & 1u)); }   /* +h even, -h odd */
 
-/* returns the wrapping sum of the block's deltas (reference sample excluded) */
+struct LaneAcc {
+    uint32_t pfx, big;
+    int32_t pmin, pmax;
+    __device__ __forceinline__ uint32_t add(uint32_t v)
+    {
+        pfx += delta_of(v); big |= v;
+        pmin = min(pmin, (int32_t)pfx); pmax = max(pmax, (int32_t)pfx);
+        return pfx;
+    }
+};
+
 template <int JT>
-__device__ __forceinline__ uint32_t warp_decode_block(const AecCfg &c, Rd64 &rd, uint32_t b, uint32_t *row,
-                                                      uint32_t &zero_left, uint32_t *bad)
+__device__ __forceinline__ void warp_decode_block(const AecCfg &c, Rd64 &rd, uint32_t b, uint32_t *row,
+                                                  uint32_t &zero_left, uint32_t *bad, LaneAcc &la)
 {
     const uint32_t J = JT ? (uint32_t)JT : c.J;
-    uint32_t dsum = 0;
     if (zero_left) {
         zero_left--;
 #pragma unroll 4
-        for (uint32_t i = 0; i < J; i++) row[i] = 0;
-        return 0;
+        for (uint32_t i = 0; i < J; i++) row[i] = la.pfx;
+        return;
     }
     const uint32_t ref = (c.pp && b == 0) ? 1u : 0u;
     const uint32_t id = rd.get(c.idl);
@@ -231,8 +248,8 @@ __device__ __forceinline__ uint32_t warp_decode_block(const AecCfg &c, Rd64 &rd,
             if (zb > c.rsi - b) { *bad = 1u; zb = 1; }
             zero_left = zb - 1u;
 #pragma unroll 4
-            for (uint32_t i = ref; i < J; i++) row[i] = 0;
-            return 0;
+            for (uint32_t i = ref; i < J; i++) row[i] = la.pfx;
+            return;
         }
         uint32_t i = ref;
         while (i < J) {
@@ -242,15 +259,15 @@ __device__ __forceinline__ uint32_t warp_decode_block(const AecCfg &c, Rd64 &rd,
             while (s * (s + 1u) / 2u > m) s--;
             while ((s + 1u) * (s + 2u) / 2u <= m) s++;
             uint32_t d1 = m - s * (s + 1u) / 2u;
-            if ((i & 1u) == 0) { row[i] = s - d1; dsum += delta_of(s - d1); i++; }
-            row[i] = d1; dsum += delta_of(d1); i++;
+            if ((i & 1u) == 0) { row[i] = la.add(s - d1); i++; }
+            row[i] = la.add(d1); i++;
         }
-        return dsum;
+        return;
     }
     if (id == (1u << c.idl) - 1u) {
 #pragma unroll 4
-        for (uint32_t i = 0; i < J; i++) { uint32_t v = rd.get(c.n); row[i] = v; if (i >= ref) dsum += delta_of(v); }
-        return dsum;
+        for (uint32_t i = 0; i < J; i++) { uint32_t v = rd.get(c.n); row[i] = (i >= ref) ? la.add(v) : v; }
+        return;
     }
     const uint32_t k = id - 1u;
     if (ref) row[0] = rd.get(c.n);
@@ -276,8 +293,8 @@ __device__ __forceinline__ uint32_t warp_decode_block(const AecCfg &c, Rd64 &rd,
     }
     if (k == 0) {
 #pragma unroll 4
-        for (uint32_t i = ref; i < J; i++) dsum += delta_of(row[i]);
-        return dsum;
+        for (uint32_t i = ref; i < J; i++) row[i] = la.add(row[i]);
+        return;
     }
     /* binary part: k low bits per sample, fetched four (k <= 8) or two (k <= 16) samples at a time */
     uint32_t i = ref;
@@ -287,19 +304,16 @@ __device__ __forceinline__ uint32_t warp_decode_block(const AecCfg &c, Rd64 &rd,
             uint32_t q = rd.get(4u * k);
             uint32_t v0 = row[i] + (q >> (3u * k)), v1 = row[i + 1] + ((q >> (2u * k)) & m);
             uint32_t v2 = row[i + 2] + ((q >> k) & m), v3 = row[i + 3] + (q & m);
-            row[i] = v0; row[i + 1] = v1; row[i + 2] = v2; row[i + 3] = v3;
-            dsum += delta_of(v0) + delta_of(v1) + delta_of(v2) + delta_of(v3);
+            row[i] = la.add(v0); row[i + 1] = la.add(v1); row[i + 2] = la.add(v2); row[i + 3] = la.add(v3);
         }
     } else if (k <= 16) {
         for (; i + 2 <= J; i += 2) {
             uint32_t q = rd.get(2u * k);
             uint32_t v0 = row[i] + (q >> k), v1 = row[i + 1] + (q & m);
-            row[i] = v0; row[i + 1] = v1;
-            dsum += delta_of(v0) + delta_of(v1);
+            row[i] = la.add(v0); row[i + 1] = la.add(v1);
         }
     }
-    for (; i < J; i++) { uint32_t v = row[i] + rd.get(k); row[i] = v; dsum += delta_of(v); }
-    return dsum;
+    for (; i < J; i++) row[i] = la.add(row[i] + rd.get(k));
 }
 
 /* First guess of a lane's start value: reference + sum of the deltas before the lane, which is
@@ -351,7 +365,7 @@ aec_decode_warp_kernel(const AecDecArgs a)
 
     const uint32_t b0 = lane * G;
     const uint32_t nblk = b0 < nblk_rsi ? (nblk_rsi - b0 < G ? nblk_rsi - b0 : G) : 0u;
-    uint32_t sum = 0;                                  /* wrapping sum of my deltas */
+    LaneAcc la; la.pfx = 0; la.big = 0; la.pmin = 0; la.pmax = 0;   /* running sum of my steps, how far they reach */
     uint32_t uref = 0;
     uint64_t endpos = 0, startpos = 0;
     uint32_t lead0 = 0, zl_end = 0;
@@ -369,16 +383,20 @@ aec_decode_warp_kernel(const AecDecArgs a)
             uint32_t *rw = row + q * J;
             if (lead) {
                 lead--;
-                for (uint32_t i = 0; i < J; i++) rw[i] = 0;
+                for (uint32_t i = 0; i < J; i++) rw[i] = la.pfx;
             } else {
-                sum += warp_decode_block<JT>(c, rd, b0 + q, rw, zero_left, &bad);
+                warp_decode_block<JT>(c, rd, b0 + q, rw, zero_left, &bad, la);
             }
         }
         endpos = rd.pos();
         zl_end = zero_left;
         if (endpos > a.in_bytes * 8ull) bad = 1u;
-        if (lane == 0 && c.pp) uref = (row[0] ^ (c.sext ? (1u << (c.n - 1)) : 0u)) & c.mask;
+        if (lane == 0 && c.pp) {
+            uref = (row[0] ^ (c.sext ? (1u << (c.n - 1)) : 0u)) & c.mask;
+            row[0] = 0;                                /* the reference sample itself: start value + 0 */
+        }
     }
+    const uint32_t sum = la.pfx;
     /* index sanity: the next lane's group must start where mine ended, unless it inherits a zero run */
     {
         unsigned long long nstart = __shfl_down_sync(FULL, (unsigned long long)startpos, 1);
@@ -389,14 +407,48 @@ aec_decode_warp_kernel(const AecDecArgs a)
     bad = __any_sync(FULL, bad) ? 1u : 0u;
 
     const uint32_t sflip = c.sext ? (1u << (c.n - 1)) : 0u;
+    const uint32_t n_s = nblk * J;
+    uint32_t usadd = 0;                                /* what the store pass adds to my row */
+    bool exact_walk = !bad;
     if (!bad && c.pp) {
-        /* ---- unit-delay predictor undone in parallel: every lane walks its samples with the
+        /* ---- unit-delay predictor undone in parallel.  A lane's start value is the reference
+         * sample plus the steps of all lanes before it, provided nothing clipped.  A lane that
+         * starts at us, stays inside [us+pmin, us+pmax] and never steps by more than big cannot
+         * clip when us+pmin >= big and us+pmax <= M-big (steps below 2^20 and rows of at most a
+         * few thousand samples keep the running sums far from wrapping); if that holds for every
+         * lane, the start values are exact by induction over the lanes and the rows (running sums)
+         * only need their start value added when they are stored. ---- */
+        uref = __shfl_sync(FULL, uref, 0);
+        uint32_t inc = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t o = __shfl_up_sync(FULL, inc, off);
+            if (lane >= (uint32_t)off) inc += o;
+        }
+        const uint32_t us0 = uref + (inc - sum);
+        const long long lo = (long long)us0 + la.pmin, hi = (long long)us0 + la.pmax;
+        const bool calm = n_s == 0 ||
+                          (la.big < (1u << 21) && us0 <= c.mask && lo >= (long long)la.big &&
+                           hi <= (long long)c.mask - (long long)la.big);
+        if (__all_sync(FULL, calm)) { usadd = us0; exact_walk = false; }
+    }
+    if (exact_walk && !c.pp) {
+        /* no predictor: the rows have to hold the values themselves; recover them from the running sums */
+        uint32_t prev = 0;
+        for (uint32_t i = 0; i < n_s; i++) {
+            const uint32_t cur = row[i];
+            const uint32_t dl = cur - prev;
+            prev = cur;
+            row[i] = (dl << 1) ^ (uint32_t)((int32_t)dl >> 31);
+        }
+    }
+    if (exact_walk && c.pp) {
+        /* ---- some sample may clip: every lane walks its samples with the
          * exact inverse map from a speculated start value.  The first walk is optimistic (start
          * values from the prefix sum of the deltas, exact whenever no sample clips) and writes
          * the normalised samples in place; if a lane did not start where its predecessor ended,
          * the mapped values are recovered (the map is a bijection) and the start values are
          * re-derived from the lanes' results until they agree. ---- */
-        uref = __shfl_sync(FULL, uref, 0);
         uint32_t inc = sum;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -406,13 +458,22 @@ aec_decode_warp_kernel(const AecDecArgs a)
         /* speculated value before my first sample; kept inside [0, M] so that every walk stays in the
          * mapper's domain and the mapped values can be recovered exactly after a wrong guess */
         uint32_t us = project_start(uref, inc - sum, c.mask);
-        const uint32_t n_s = nblk * J;
         const uint32_t i_first = (lane == 0) ? 1u : 0u;
         if (lane == 0) us = uref;
         uint32_t u = us, clip = 0;
         if (lane == 0 && n_s) row[0] = uref;
+        {
+            /* the rows still hold running sums: the mapped value is the zigzag of their difference */
+            uint32_t pprev = 0;
 #pragma unroll 4
-        for (uint32_t i = i_first; i < n_s; i++) { u = unmap_step(u, row[i], c.mask, clip); row[i] = u; }
+            for (uint32_t i = i_first; i < n_s; i++) {
+                const uint32_t cur = row[i];
+                const uint32_t dl = cur - pprev;
+                pprev = cur;
+                u = unmap_step(u, (dl << 1) ^ (uint32_t)((int32_t)dl >> 31), c.mask, clip);
+                row[i] = u;
+            }
+        }
         uint32_t uprev = __shfl_up_sync(FULL, u, 1);
         bool ok = (lane == 0) || (n_s == 0) || (uprev == us);
         if (!__all_sync(FULL, ok)) {
@@ -480,32 +541,59 @@ aec_decode_warp_kernel(const AecDecArgs a)
     uint32_t *wrows = rows + (size_t)warp * 32u * stride;
     const bool sxt = c.sext && c.n < 32;
     if (!whole) return;
-    if (JT != 0 && a.out_aligned && (GJ % 4u) == 0 && limit == c.R) {
-        constexpr int SPG = (B == 4) ? 1 : ((B == 2) ? 2 : 4);
-        const uint32_t ngroups = c.R / SPG;
-        const bool pow2 = (GJ & (GJ - 1u)) == 0;
-        const uint32_t gsh = 31u - (uint32_t)__clz((int)GJ);
-        for (uint32_t g = lane; g < ngroups; g += 32) {
-            uint32_t s0 = g * SPG;
-            uint32_t rowi = pow2 ? (s0 >> gsh) : (s0 / GJ);
-            uint32_t col = pow2 ? (s0 & (GJ - 1u)) : (s0 % GJ);
-            const uint32_t *src = wrows + (size_t)rowi * stride + col;
-            uint32_t sv[4] = {src[0], SPG > 1 ? src[1] : 0u, SPG > 2 ? src[2] : 0u, SPG > 2 ? src[3] : 0u};
-            if (c.pp) {
+    /* row r of the warp belongs to lane r; its samples are row value + usadd of that lane (the start
+     * value when the rows hold running sums, 0 after the exact walk), then back to the n-bit pattern
+     * and sign-extended to the storage width (decode.c:78-84, :131) */
+    const uint32_t xorv = c.pp ? sflip : 0u;
+    const uint32_t sxsh = (c.pp && sxt) ? 32u - c.n : 0u;
+    constexpr int SPG = (B == 4) ? 1 : ((B == 2) ? 2 : 4);      /* samples per 32-bit store group */
+    if (JT != 0 && a.out_aligned && limit == c.R && (GJ % (32u * SPG)) == 0 && (c.rsi % G) == 0) {
+        /* every lane owns G whole blocks: GJ / (32*SPG) warp steps per row, the row's lane is warp-uniform */
+        const uint32_t nrows = c.R / GJ, steps = GJ / (32u * SPG);
+        const uint32_t *src = wrows + lane * SPG;
+        uint64_t sidx = startS + lane * SPG;
+        for (uint32_t rowi = 0; rowi < nrows; rowi++, src += stride - GJ) {
+            const uint32_t ua = __shfl_sync(FULL, usadd, rowi);
+#pragma unroll 2
+            for (uint32_t q = 0; q < steps; q++, src += 32 * SPG, sidx += 32 * SPG) {
+                uint32_t sv[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                 for (int j = 0; j < SPG; j++) {
-                    uint32_t x = sv[j] ^ sflip;                     /* back to the n-bit pattern */
-                    if (sxt && ((x >> (c.n - 1)) & 1u)) x |= ~c.mask; /* decode.c:78-84, :131 */
+                    uint32_t x = (src[j] + ua) ^ xorv;
+                    if (sxsh) x = (uint32_t)((int32_t)(x << sxsh) >> sxsh);
                     sv[j] = x;
                 }
+                store_group<B>(a.out, sidx, sv, c.msb);
+            }
+        }
+    } else if (JT != 0 && a.out_aligned && (GJ % 4u) == 0 && limit == c.R) {
+        const uint32_t ngroups = c.R / SPG;
+        for (uint32_t g0 = 0; g0 < ngroups; g0 += 32) {
+            const uint32_t g = g0 + lane;
+            const bool ok = g < ngroups;
+            const uint32_t s0 = ok ? g * SPG : 0u;
+            const uint32_t rowi = s0 / GJ, col = s0 - rowi * GJ;
+            const uint32_t ua = __shfl_sync(FULL, usadd, rowi);
+            if (!ok) continue;
+            const uint32_t *src = wrows + (size_t)rowi * stride + col;
+            uint32_t sv[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < SPG; j++) {
+                uint32_t x = (src[j] + ua) ^ xorv;
+                if (sxsh) x = (uint32_t)((int32_t)(x << sxsh) >> sxsh);
+                sv[j] = x;
             }
             store_group<B>(a.out, startS + s0, sv, c.msb);
         }
     } else {
-        for (uint32_t s0 = lane; s0 < limit; s0 += 32) {
-            uint32_t rowi = s0 / GJ, col = s0 % GJ;
-            uint32_t x = wrows[(size_t)rowi * stride + col];
-            if (c.pp) { x ^= sflip; if (sxt && ((x >> (c.n - 1)) & 1u)) x |= ~c.mask; }
+        for (uint32_t sb = 0; sb < limit; sb += 32) {
+            const uint32_t s0 = sb + lane;
+            const bool ok = s0 < limit;
+            const uint32_t rowi = ok ? s0 / GJ : 0u, col = ok ? s0 - rowi * GJ : 0u;
+            const uint32_t ua = __shfl_sync(FULL, usadd, rowi);
+            if (!ok) continue;
+            uint32_t x = (wrows[(size_t)rowi * stride + col] + ua) ^ xorv;
+            if (sxsh) x = (uint32_t)((int32_t)(x << sxsh) >> sxsh);
             aec_store_sample(a.out + (startS + s0) * c.B, x, c.B, c.msb);
         }
     }
