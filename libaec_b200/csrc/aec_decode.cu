@@ -143,7 +143,7 @@ aec_decode_kernel(const AecDecArgs a)
 /* Fast path: one warp per RSI                                               */
 /* ======================================================================== */
 
-constexpr int DW_MAX_WARPS = 4;      /* warps (= RSIs) per CTA; fewer when rows are long */
+constexpr int DW_MAX_WARPS = 12;     /* most warps (= RSIs) per CTA; the host picks the count that fills an SM's shared memory best */
 
 /* Bit reader with a 64-bit left-aligned window refilled one word at a time. */
 struct Rd64 {
@@ -271,24 +271,36 @@ __device__ __forceinline__ void warp_decode_block(const AecCfg &c, Rd64 &rd, uin
     }
     const uint32_t k = id - 1u;
     if (ref) row[0] = rd.get(c.n);
-    /* unary part: after a refill the window holds >= 32 valid bits; decode every code that
-     * completes inside it before touching the 64-bit accumulator again */
+    /* unary part: after a refill the window holds >= 32 valid bits; the ones in it are the codes
+     * that complete inside it (popc), decoded before the 64-bit accumulator is touched again */
     {
         uint32_t i = ref, pend = 0;
         while (i < J) {
             rd.refill();
             uint32_t wnd = (uint32_t)(rd.acc >> 32);
-            uint32_t left = 32;
-            while (wnd != 0 && i < J) {
+            const uint32_t left = J - i;
+            uint32_t n = (uint32_t)__popc(wnd);
+            n = n < left ? n : left;
+            uint32_t cons = 0;
+            if (n) {
                 uint32_t z = (uint32_t)__clz((int)wnd);
-                row[i++] = (pend + z) << k;
+                row[i] = (pend + z) << k;
                 pend = 0;
                 wnd = (wnd << z) << 1;
-                left -= z + 1u;
+                cons = z + 1u;
+                for (uint32_t q = 1; q < n; q++) {
+                    z = (uint32_t)__clz((int)wnd);
+                    row[i + q] = z << k;
+                    wnd = (wnd << z) << 1;
+                    cons += z + 1u;
+                }
+                i += n;
             }
-            uint32_t used = 32u - left;
-            if (i < J) { pend += left; used = 32u; if (rd.widx > rd.nwords + 2u) { *bad = 1u; break; } }
-            rd.acc <<= used; rd.nb -= (int)used;
+            if (i < J) {                          /* the rest of the window is the start of the next code */
+                pend += 32u - cons; cons = 32u;
+                if (rd.widx > rd.nwords + 2u) { *bad = 1u; break; }
+            }
+            rd.acc <<= cons; rd.nb -= (int)cons;
         }
     }
     if (k == 0) {
@@ -725,13 +737,26 @@ cudaError_t launch_decw_j(const AecDecArgs &a, cudaStream_t st)
 
 uint32_t aec_decode_group_blocks(const AecCfg &c) { return (c.rsi + 31u) / 32u; }
 
-/* warps per CTA of the warp-per-RSI kernel (0: an RSI's rows do not fit shared memory -> careful kernel only) */
+/* warps per CTA of the warp-per-RSI kernel (0: an RSI's rows do not fit shared memory -> careful kernel only).
+ * The kernel is bound by instruction issue, so what matters is how many warps an SM holds: shared
+ * memory is the limit (228 KiB per SM, 1 KiB of it reserved per resident CTA, 227 KiB at most per CTA). */
 uint32_t aec_decode_warp_warps(const AecCfg &c)
 {
-    uint32_t stride = (aec_decode_group_blocks(c) * c.J) | 1u;
-    for (uint32_t w = 4; w >= 1; w >>= 1)
-        if ((uint64_t)w * 32u * stride * 4u <= 96u * 1024u) return w;
-    return 0;
+    const uint64_t stride = (aec_decode_group_blocks(c) * c.J) | 1u;
+    const uint64_t per_warp = 32u * stride * 4u;
+    if (per_warp > 96u * 1024u) return 0;
+    uint32_t best_w = 0, best_total = 0;
+    for (uint32_t w = 1; w <= (uint32_t)DW_MAX_WARPS; w++) {
+        const uint64_t cta = w * per_warp;
+        if (cta > 227u * 1024u) break;
+        uint64_t ctas = (228u * 1024u) / (cta + 1024u);
+        if (ctas > 32u) ctas = 32u;
+        uint64_t total = ctas * w;
+        if (total > 64u) total = 64u;
+        /* ties go to the smaller CTA: less of the SM idles while the last CTAs of the grid finish */
+        if (total > best_total) { best_total = (uint32_t)total; best_w = w; }
+    }
+    return best_w;
 }
 
 cudaError_t aec_decode_warp_launch(const AecDecArgs &a, int num_sms, cudaStream_t st)
