@@ -239,13 +239,23 @@ AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t 
         /* guess kg: smallest k with (S0 >> (k+1)) <= thisbs; the true klo is
          * within one of it on every data set we measured */
         const uint32_t kmax = c.kmax;
-        uint64_t q = S0 >> 1;
         int kg = 0;
-        if (q > thisbs) {
-            kg = (64 - aec_clz64(q)) - (32 - aec_clz32(thisbs));
-            if (kg < 0) kg = 0;
-            while (kg > 0 && (q >> (kg - 1)) <= thisbs) kg--;
-            while ((q >> kg) > thisbs) kg++;
+        if ((orv >> 25) == 0) {
+            /* 32-bit sum: q >> kg0 is as long as thisbs when kg0 is the difference of their bit
+             * lengths, so the answer is kg0 or kg0 + 1 */
+            const uint32_t q = s32 >> 1;
+            if (q > thisbs) {
+                const int kg0 = aec_clz32(thisbs) - aec_clz32(q);
+                kg = kg0 + ((q >> kg0) > thisbs ? 1 : 0);
+            }
+        } else {
+            const uint64_t q = S0 >> 1;
+            if (q > thisbs) {
+                kg = (64 - aec_clz64(q)) - (32 - aec_clz32(thisbs));
+                if (kg < 0) kg = 0;
+                while (kg > 0 && (q >> (kg - 1)) <= thisbs) kg--;
+                while ((q >> kg) > thisbs) kg++;
+            }
         }
         uint32_t kgc = (uint32_t)kg > kmax ? kmax : (uint32_t)kg;
         uint32_t kb = kgc >= 2 ? kgc - 2 : 0;               /* window base: T known for kb..kb+3 */

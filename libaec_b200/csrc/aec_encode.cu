@@ -155,6 +155,14 @@ __device__ __forceinline__ void load_block(const AecCfg &c, const uint8_t *in, u
     }
 }
 
+/* A spin that has not been answered after this many polls means a broken protocol: abort the
+ * launch (the host sees a launch failure) instead of hanging the device. */
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
+__device__ __forceinline__ void spin_guard(uint32_t &n)
+{
+    if (++n > SPIN_LIMIT) __trap();
+}
+
 /* ---- dedicated scanner ------------------------------------------------------
  * CTA 0 turns the per-tile aggregates into exclusive prefixes (absolute bit
  * offset + incoming k of every tile).  Worker CTAs never look back: they
@@ -179,7 +187,8 @@ __device__ __noinline__ void aec_encode_scanner(const AecEncArgs &a, uint64_t *s
         uint64_t dv = ST_AGG | ((uint64_t)c.kmax << 7);           /* identity beyond the last tile */
         if (t < a.ntiles) {
             dv = ld_volatile_u64(&a.desc[t]);
-            while ((dv & 3) == 0) dv = ld_volatile_u64(&a.desc[t]);
+            uint32_t spins = 0;
+            while ((dv & 3) == 0) { dv = ld_volatile_u64(&a.desc[t]); spin_guard(spins); }
         }
         __syncwarp();
         PosFn f; uint32_t kj;
@@ -210,7 +219,10 @@ __device__ __noinline__ void aec_encode_scanner(const AecEncArgs &a, uint64_t *s
         uint32_t ke = __shfl_up_sync(FULL, ki, 1);
         if (lane == 0) { fe.has_end = 0; fe.a = 0; fe.rest = 0; ke = kident; }
         /* carry of everything before this batch */
-        while (*s_done != (uint32_t)b) { }                     /* hand-over spin: a sleep quantum here would serialise the chain */
+        {   /* hand-over spin: a sleep quantum here would serialise the chain */
+            uint32_t spins = 0;
+            while (*s_done != (uint32_t)b) spin_guard(spins);
+        }
         const uint64_t P = *reinterpret_cast<volatile uint64_t *>(&s_carry_pos[b & 1]);
         const uint32_t kc = *reinterpret_cast<volatile uint32_t *>(&s_carry_k[b & 1]);
         const uint64_t pos = aec_papply(fe, P);
@@ -272,16 +284,6 @@ __device__ __forceinline__ uint32_t load_one(const uint8_t *in, uint64_t idx, ui
     return aec_load_sample(in + idx * B, B, msb);
 }
 
-/* Per-thread facts about a tile whose words still have to be streamed out. */
-struct PendingBlock {
-    uint64_t rsi;        /* RSI of my block */
-    uint32_t b;          /* block index inside the RSI */
-    uint32_t myoff;      /* bit offset inside the tile's staging area */
-    uint32_t len;        /* CDS bits */
-    uint32_t zrun;       /* zero-run length when this block owns a run */
-    uint32_t flags;      /* bit0 valid, bit1 all-zero block, bit2 inherits a zero run */
-};
-
 template <int JT, int B>
 __global__ void __launch_bounds__(TileCfg<JT>::TB, TileCfg<JT>::MINB)
 aec_encode_kernel(const __grid_constant__ AecEncArgs a)
@@ -296,19 +298,26 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
     /* RSIs longer than a tile with RSI padding: a tile may start at an unknown
      * bit phase mod 8, so its bits can only be laid out once its prefix is known */
     const bool late = c.pad && a.RP > (uint32_t)TB;
+    const bool want_index = a.rsi_offsets != nullptr || a.grp_index != nullptr;
 
     /* two staging areas of SW words: tile `it` packs into one while tile it-1 streams out of the
-     * other; word 0 of an area stays zero (the word "before" the tile for the funnel shift) */
+     * other; word 0 of an area stays zero (the word "before" the tile for the funnel shift).  Behind
+     * them two areas of TB x 2 words: what each thread has to remember about its block of the tile
+     * that still waits for its prefix (bit offset in the tile; CDS length, zero-run length, flags) */
     extern __shared__ uint4 staging_raw[];
     uint32_t *const staging_all = reinterpret_cast<uint32_t *>(staging_raw);
     const uint32_t SW = a.staging_words;
-    __shared__ uint32_t s_ticket[2];
-    __shared__ unsigned long long s_rsi0[2]; /* first RSI of the claimed tile */
-    __shared__ uint32_t s_b0[2];             /* first block slot of the tile inside that RSI (RP >= TB) */
+    uint2 *const pend_all = reinterpret_cast<uint2 *>(staging_all + 2u * SW);
+    /* tickets and tile geometry live in a ring of three: the tile being streamed out, the tile being
+     * packed and the tile claimed ahead */
+    __shared__ uint32_t s_ticket[3];
+    __shared__ unsigned long long s_rsi0[3]; /* first RSI of the claimed tile */
+    __shared__ uint32_t s_b0[3];             /* first block slot of the tile inside that RSI (RP >= TB) */
     __shared__ uint32_t s_zb[NWARP + 1];
     __shared__ uint32_t s_wlen[NWARP];       /* per-warp sums (no-pad mode) */
     __shared__ uint32_t s_wend[NWARP], s_wa[NWARP], s_wrest[NWARP];   /* per-warp PosFn (pad mode) */
     __shared__ uint32_t s_wk[NWARP];
+    __shared__ uint32_t s_tend[2], s_ta[2], s_trest[2];   /* position map of the packed tile, per staging area */
     __shared__ unsigned long long s_base;    /* absolute bit offset of the tile being streamed out */
     __shared__ unsigned long long s_base_cur;/* late mode: absolute bit offset of the tile being packed */
 
@@ -319,36 +328,38 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
         aec_encode_scanner<NWARP>(a, reinterpret_cast<uint64_t *>(s_cpos), s_ck, &s_sdone);
         return;
     }
-    /* claim the next tile in order and work out where it sits (thread 0 only) */
-    auto claim = [&](uint32_t slot) {
-        const uint32_t t = atomicAdd(a.ticket, 1u);
-        s_ticket[slot] = t;
-        if (a.tpr) { const uint32_t q = t / a.tpr; s_rsi0[slot] = q; s_b0[slot] = (t - q * a.tpr) * (uint32_t)TB; }
-        else { s_rsi0[slot] = (unsigned long long)t << a.tile_rsi_shift; s_b0[slot] = 0; }
+    /* where a claimed tile sits (thread 0 only) */
+    auto place = [&](uint32_t g, uint32_t t) {
+        s_ticket[g] = t;
+        if (a.tpr) { const uint32_t q = t / a.tpr; s_rsi0[g] = q; s_b0[g] = (t - q * a.tpr) * (uint32_t)TB; }
+        else { s_rsi0[g] = (unsigned long long)t << a.tile_rsi_shift; s_b0[g] = 0; }
+    };
+    /* which block of the tile in ring entry g belongs to this thread */
+    auto my_block = [&](uint32_t g, uint64_t &rsi_idx, uint32_t &b) {
+        rsi_idx = s_rsi0[g];
+        if (a.tpr) b = s_b0[g] + tid;
+        else { rsi_idx += tid >> a.rp_shift; b = tid & (a.RP - 1u); }
     };
     for (uint32_t i = tid; i < 2u * SW; i += TB) staging_all[i] = 0;
-    if (tid == 0) claim(0);
+    if (tid == 0) place(0, atomicAdd(a.ticket, 1u));
     __syncthreads();
 
-    /* the previous tile of this CTA: packed, aggregate published, words not yet written */
-    bool prev_have = false;
-    uint32_t prev_tile = 0;
-    PosFn prev_ptile; prev_ptile.has_end = 0; prev_ptile.a = 0; prev_ptile.rest = 0;
-    PendingBlock pend; pend.rsi = 0; pend.b = 0; pend.myoff = 0; pend.len = 0; pend.zrun = 0; pend.flags = 0;
+    bool prev_have = false;                 /* the previous tile is packed and waits to be streamed out */
+    uint32_t g = 0;                         /* ring entry of the current tile */
 
     for (uint32_t it = 0;; it++) {
         const uint32_t slot = it & 1u;
-        const uint32_t tile = s_ticket[slot];
+        const uint32_t gp = g == 0 ? 2u : g - 1u, gn = g == 2 ? 0u : g + 1u;
+        const uint32_t tile = s_ticket[g];
         const bool have = tile < a.ntiles;
         uint32_t *staging = staging_all + slot * SW + 1u;
-        PosFn ptile; ptile.has_end = 0; ptile.a = 0; ptile.rest = 0;
-        PendingBlock cur; cur.rsi = 0; cur.b = 0; cur.myoff = 0; cur.len = 0; cur.zrun = 0; cur.flags = 0;
+        uint64_t pv0 = 0;                   /* thread 0: the previous tile's prefix word, probed before packing */
 
         if (have) {
+            PosFn ptile; ptile.has_end = 0; ptile.a = 0; ptile.rest = 0;      /* position map of the whole tile */
             /* ---- which block is mine ---- */
-            uint64_t rsi_idx = s_rsi0[slot]; uint32_t b;
-            if (a.tpr) b = s_b0[slot] + tid;
-            else { rsi_idx += tid >> a.rp_shift; b = tid & (a.RP - 1u); }
+            uint64_t rsi_idx; uint32_t b;
+            my_block(g, rsi_idx, b);
             uint32_t nblk = 0;
             if (rsi_idx + 1 < a.nrsi) nblk = c.rsi;
             else if (rsi_idx + 1 == a.nrsi) nblk = a.last_nblk;
@@ -485,6 +496,8 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
             if (tid == 0) {
                 st_volatile_u64(&a.desc[tile], desc_pack_agg(ptile, ktile));
                 a.tile_kagg[tile] = ktile;
+                /* first look at the previous tile's prefix: the answer travels while this tile is packed */
+                if (prev_have) pv0 = ld_volatile_u64(&a.pref[s_ticket[gp]]);
             }
 
             /* ---- pack my CDS into this tile's staging area, at local bit phase 0 ---- */
@@ -493,7 +506,8 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                 /* bit layout needs the absolute phase: wait for this tile's prefix */
                 if (tid == 0) {
                     uint64_t pv = ld_volatile_u64(&a.pref[tile]);
-                    while ((pv & 3) == 0) pv = ld_volatile_u64(&a.pref[tile]);
+                    uint32_t spins = 0;
+                    while ((pv & 3) == 0) { pv = ld_volatile_u64(&a.pref[tile]); spin_guard(spins); }
                     s_base_cur = pv >> 12;
                 }
                 __syncthreads();
@@ -515,7 +529,8 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                             /* a plateau block before the tile's first fixed k: its split position depends on
                              * the k carried into the tile, i.e. on this tile's prefix (rare) */
                             uint64_t pv = ld_volatile_u64(&a.pref[tile]);
-                            while ((pv & 3) == 0) pv = ld_volatile_u64(&a.pref[tile]);
+                            uint32_t spins = 0;
+                            while ((pv & 3) == 0) { pv = ld_volatile_u64(&a.pref[tile]); spin_guard(spins); }
                             kprev = aec_kapply((uint32_t)(pv >> 2) & 0x1Fu, kbefore);
                         }
                         k = aec_clampu(kprev, bi.klo, bi.khi);
@@ -524,20 +539,28 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                 }
                 bp.finish();
             }
-            cur.rsi = rsi_idx; cur.b = b; cur.myoff = myoff; cur.len = len; cur.zrun = zrun;
-            cur.flags = (valid ? 1u : 0u) | (is_zero ? 2u : 0u) | (zinherit ? 4u : 0u);
+            if (want_index)
+                pend_all[slot * TB + tid] = make_uint2(myoff, len | (zrun << 12) | ((valid ? 1u : 0u) << 20) |
+                                                              ((is_zero ? 1u : 0u) << 21) | ((zinherit ? 1u : 0u) << 22));
+            if (tid == 0) { s_tend[slot] = ptile.has_end; s_ta[slot] = (uint32_t)ptile.a; s_trest[slot] = (uint32_t)ptile.rest; }
         }
 
         /* The previous tile's prefix has had a whole tile time to arrive.  Only now claim the next
          * tile: a claimed tile never waits for anything but earlier tiles, so the scanner's fixed
-         * batches of 32 tiles always complete. */
+         * batches of 32 tiles always complete, and a tile always goes to the CTA that is ready for it
+         * first (claiming ahead pins tiles to CTAs and lets one late CTA hold up the whole chain:
+         * profiles/r1_g).  The ticket itself is only needed after the copy-out, so its round trip
+         * overlaps the copy-out instead of the barrier. */
+        uint32_t nxt = 0xFFFFFFFFu;
         if (tid == 0) {
             if (prev_have) {
-                uint64_t pv = ld_volatile_u64(&a.pref[prev_tile]);
-                while ((pv & 3) == 0) pv = ld_volatile_u64(&a.pref[prev_tile]);
-                s_base = pv >> 12;
+                uint32_t spins = 0;
+                if (!have) pv0 = ld_volatile_u64(&a.pref[s_ticket[gp]]);
+                while ((pv0 & 3) == 0) { pv0 = ld_volatile_u64(&a.pref[s_ticket[gp]]); spin_guard(spins); }
+                s_base = pv0 >> 12;
             }
-            if (have) claim(slot ^ 1u); else s_ticket[slot ^ 1u] = 0xFFFFFFFFu;
+            if (have) nxt = atomicAdd(a.ticket, 1u);
+            if (!prev_have || !have) { if (have) place(gn, nxt); else s_ticket[gn] = 0xFFFFFFFFu; }
         }
         __syncthreads();                                               /* S3 */
 
@@ -545,22 +568,28 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
         if (prev_have) {
             uint32_t *pstage = staging_all + (slot ^ 1u) * SW + 1u;
             const uint64_t base = s_base;
-            if (pend.flags & 1u) {
-                const uint64_t myabs = (late ? ((base >> 5) << 5) : base) + pend.myoff;
-                if (pend.b == 0 && a.rsi_offsets) a.rsi_offsets[pend.rsi] = myabs;
+            const uint32_t prev_tile = s_ticket[gp];
+            const uint2 pe = want_index ? pend_all[(slot ^ 1u) * TB + tid] : make_uint2(0u, 0u);
+            if (pe.y & (1u << 20)) {
+                uint64_t p_rsi; uint32_t p_b;
+                my_block(gp, p_rsi, p_b);
+                const uint32_t p_len = pe.y & 0xFFFu, p_zrun = (pe.y >> 12) & 0xFFu;
+                const uint64_t myabs = (late ? ((base >> 5) << 5) : base) + pe.x;
+                if (p_b == 0 && a.rsi_offsets) a.rsi_offsets[p_rsi] = myabs;
                 if (a.grp_index) {
                     /* group index for the warp-per-RSI decoder (aec_device.h) */
                     const uint32_t G = a.grp_G;
-                    const uint32_t q = a.grp_magic ? __umulhi(pend.b, a.grp_magic) : pend.b;    /* b / G */
-                    if (q * G == pend.b && !(pend.flags & 4u)) a.grp_index[pend.rsi * 32ull + q] = myabs;
-                    if ((pend.flags & 2u) && pend.len && pend.zrun > 1) {
+                    const uint32_t q = a.grp_magic ? __umulhi(p_b, a.grp_magic) : p_b;    /* b / G */
+                    if (q * G == p_b && !(pe.y & (1u << 22))) a.grp_index[p_rsi * 32ull + q] = myabs;
+                    if ((pe.y & (1u << 21)) && p_len && p_zrun > 1) {
                         /* I own a zero run: group starts inside it inherit their leading blocks from me */
-                        uint32_t b0 = pend.b + 1u - pend.zrun;
-                        for (uint32_t g = (b0 / G + 1u) * G; g <= pend.b; g += G)
-                            a.grp_index[pend.rsi * 32ull + g / G] = ((uint64_t)(pend.b - g + 1u) << 56) | (myabs + pend.len);
+                        uint32_t b0 = p_b + 1u - p_zrun;
+                        for (uint32_t gs = (b0 / G + 1u) * G; gs <= p_b; gs += G)
+                            a.grp_index[p_rsi * 32ull + gs / G] = ((uint64_t)(p_b - gs + 1u) << 56) | (myabs + p_len);
                     }
                 }
             }
+            PosFn prev_ptile; prev_ptile.has_end = s_tend[slot ^ 1u]; prev_ptile.a = s_ta[slot ^ 1u]; prev_ptile.rest = s_trest[slot ^ 1u];
             const uint64_t end = aec_papply(prev_ptile, late ? base : 0ull) + (late ? 0ull : base);
             const uint64_t w0 = base >> 5, we = end >> 5;
             const uint32_t sh = late ? 0u : (uint32_t)(base & 31u);      /* staging is at phase 0 unless late */
@@ -576,6 +605,7 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                 if ((uint64_t)i_hi > capw) i_hi = (uint32_t)capw;
             }
             uint32_t *dst = a.out_words + w0;
+#pragma unroll 1
             for (uint32_t i = (head_partial ? 1u : 0u) + tid; i < i_hi; i += TB) {
                 const uint32_t v = __funnelshift_r(pstage[i], pstage[(int)i - 1], sh);
                 dst[i] = __byte_perm(v, 0, 0x0123);
@@ -584,15 +614,18 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                 a.head_c[prev_tile] = (head_partial && end > base) ? (pstage[0] >> sh) : 0u;
             if (tid == 32)
                 a.tail_c[prev_tile] = tail_partial ? __funnelshift_r(pstage[nwhole], pstage[(int)nwhole - 1], sh) : 0u;
+            if (tid == 0 && have) place(gn, nxt);                      /* the ticket claimed before S3 has arrived by now */
             __syncthreads();                                           /* S4: everyone has read the words */
             {
                 uint4 *z = reinterpret_cast<uint4 *>(staging_all + (slot ^ 1u) * SW);
                 const uint32_t n4 = (nsl + 5u) >> 2;                   /* pad word + nsl words + one spare */
+#pragma unroll 1
                 for (uint32_t i = tid; i < n4; i += TB) z[i] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
         if (!have) break;
-        prev_have = true; prev_tile = tile; prev_ptile = ptile; pend = cur;
+        prev_have = true;
+        g = gn;
     }
 }
 
@@ -781,7 +814,8 @@ cudaError_t aec_encode_launch(const AecEncArgs &args, int num_sms, cudaStream_t 
         a.tile_rsi_shift = 0; while (a.RP < TB && ((a.RP << a.tile_rsi_shift) < TB)) a.tile_rsi_shift++;
         a.grp_magic = a.grp_G > 1u ? (uint32_t)((1ull << 32) / a.grp_G + 1ull) : 0u;
     }
-    uint32_t smem = 2u * a.staging_words * 4u;     /* two staging areas (aec_encode_kernel) */
+    /* two staging areas and two areas of per-thread notes (aec_encode_kernel) */
+    uint32_t smem = 2u * a.staging_words * 4u + 2u * aec_encode_tile_blocks(a.cfg.J) * 8u;
     cudaError_t e;
     switch (a.cfg.J) {
     case 8:  e = launch_j<8>(a, smem, num_sms, st); break;
