@@ -442,32 +442,35 @@ AEC_HD uint64_t aec_papply(const PosFn &f, uint64_t p)
  *
  * The bits wait in a right-aligned 64-bit accumulator (hi:lo, `fill` valid
  * bits, fill < 32 between calls); a put shifts the field in and writes one
- * word out when 32 bits are complete.  There is no data-dependent branch in
- * put(): the word store is predicated. */
+ * word out when 32 bits are complete.  On the device put() has neither a
+ * data-dependent branch nor an atomic: the first completed word goes to a
+ * slot private to the thread (`side`), every later one to the staging word it
+ * owns, all with one predicated store; finish() merges the first word and the
+ * unfinished last one into the staging area. */
 struct BitPack {
-    uint32_t *buf;
     uint32_t lo, hi;  /* accumulator, valid bits [0, fill) */
     uint32_t fill;
-    uint32_t wcur;    /* device: shared-window byte address of the word being filled; host: word index */
     uint32_t wfirst;  /* the CDS's first word (shared with the previous CDS) */
+#if defined(__CUDA_ARCH__)
+    uint32_t wst;     /* shared-window byte address the next completed word is stored to */
+    uint32_t wnext;   /* address of the staging word after the one being filled */
+#else
+    uint32_t *buf;
+    uint32_t wcur;    /* word index of the word being filled */
+#endif
 
-    AEC_HDM void merge(uint32_t v)
+    /* b: staging area, bitpos: where the CDS starts in it; side (device only): shared-window address of a
+     * word private to this thread */
+    AEC_HDM void init(uint32_t *b, uint32_t bitpos, uint32_t side)
     {
+        lo = 0; hi = 0; fill = bitpos & 31u;
 #if defined(__CUDA_ARCH__)
-        asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(wcur), "r"(v) : "memory");
+        wfirst = (uint32_t)__cvta_generic_to_shared(b) + ((bitpos >> 5) << 2);
+        wst = side; wnext = wfirst + 4u;
 #else
-        buf[wcur] |= v;
+        (void)side;
+        buf = b; wcur = bitpos >> 5; wfirst = wcur;
 #endif
-    }
-    AEC_HDM void init(uint32_t *b, uint32_t bitpos)
-    {
-        buf = b; lo = 0; hi = 0; fill = bitpos & 31u;
-#if defined(__CUDA_ARCH__)
-        wcur = (uint32_t)__cvta_generic_to_shared(b) + ((bitpos >> 5) << 2);
-#else
-        wcur = bitpos >> 5;
-#endif
-        wfirst = wcur;
     }
     /* append len (0..32) bits of v (v < 2^len) */
     AEC_HDM void put(uint32_t v, uint32_t len)
@@ -479,18 +482,16 @@ struct BitPack {
         fill += len;
         /* predicated, not branched: whether a put completes a word differs from lane to lane */
         asm volatile("{\n\t"
-                     ".reg .pred p, q, r;\n\t"
+                     ".reg .pred p;\n\t"
                      ".reg .b32 w;\n\t"
                      "setp.ge.u32 p, %0, 32;\n\t"
-                     "shf.r.wrap.b32 w, %2, %3, %0;\n\t"            /* bits [fill-32, fill) */
-                     "setp.eq.and.u32 q, %1, %4, p;\n\t"            /* the CDS's first word is shared */
-                     "setp.ne.and.u32 r, %1, %4, p;\n\t"
-                     "@q red.shared.or.b32 [%1], w;\n\t"
-                     "@r st.shared.b32 [%1], w;\n\t"
-                     "@p add.u32 %1, %1, 4;\n\t"
+                     "shf.r.wrap.b32 w, %3, %4, %0;\n\t"            /* bits [fill-32, fill) */
+                     "@p st.shared.b32 [%1], w;\n\t"
+                     "@p mov.b32 %1, %2;\n\t"
+                     "@p add.u32 %2, %2, 4;\n\t"
                      "and.b32 %0, %0, 31;\n\t"
                      "}"
-                     : "+r"(fill), "+r"(wcur) : "r"(lo), "r"(hi), "r"(wfirst) : "memory");
+                     : "+r"(fill), "+r"(wst), "+r"(wnext) : "r"(lo), "r"(hi) : "memory");
 #else
         uint64_t acc = ((uint64_t)hi << 32) | lo;
         acc = (len >= 32u ? (acc << 16) << 16 : acc << len) | v;
@@ -510,9 +511,19 @@ struct BitPack {
         while (fs >= 32u) { put(0u, 32u); fs -= 32u; }
         put(1u, fs + 1u);
     }
-    AEC_HDM void finish()
+    AEC_HDM void finish(uint32_t side)
     {
-        if (fill) merge(lo << (32u - fill));
+#if defined(__CUDA_ARCH__)
+        if (wnext != wfirst + 4u) {                 /* at least one word was completed: the first sits in the side slot */
+            uint32_t h;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(h) : "r"(side) : "memory");
+            asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(wfirst), "r"(h) : "memory");
+        }
+        if (fill) asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(wnext - 4u), "r"(lo << (32u - fill)) : "memory");
+#else
+        (void)side;
+        if (fill) buf[wcur] |= lo << (32u - fill);
+#endif
     }
 };
 

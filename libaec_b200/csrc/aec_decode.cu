@@ -352,6 +352,58 @@ __device__ __forceinline__ uint32_t unmap_step(uint32_t u, uint32_t d, uint32_t 
     return cl ? cv : step;
 }
 
+/* Four (B = 1, 3), two (B = 2) or one (B = 4) consecutive samples of one RSI -> 32-bit stores; s_local is the
+ * first sample's index inside the RSI whose output starts at rsi_out (4-byte aligned). */
+template <int B>
+__device__ __forceinline__ void store_group_at(uint8_t *rsi_out, uint32_t s_local, const uint32_t *s, uint32_t bsel)
+{
+    uint32_t *o = reinterpret_cast<uint32_t *>(rsi_out);
+    if (B == 4) {
+        o[s_local] = __byte_perm(s[0], 0, bsel);                   /* bsel: 0x3210 as is, 0x0123 byte-swapped */
+    } else if (B == 2) {
+        o[s_local >> 1] = __byte_perm(s[0], s[1], bsel);           /* 0x5410 / 0x4501 */
+    } else if (B == 1) {
+        o[s_local >> 2] = __byte_perm(__byte_perm(s[0], s[1], 0x0040), __byte_perm(s[2], s[3], 0x0040), 0x5410);
+    } else {
+        uint32_t a = s[0] & 0xFFFFFFu, b = s[1] & 0xFFFFFFu, cc = s[2] & 0xFFFFFFu, d = s[3] & 0xFFFFFFu;
+        if (bsel == 0x0123u) {
+            a = __byte_perm(a, 0, 0x4012); b = __byte_perm(b, 0, 0x4012);
+            cc = __byte_perm(cc, 0, 0x4012); d = __byte_perm(d, 0, 0x4012);
+        }
+        o += (s_local >> 2) * 3u;
+        o[0] = a | (b << 24);
+        o[1] = (b >> 8) | (cc << 16);
+        o[2] = (cc >> 16) | (d << 8);
+    }
+}
+
+/* The warp's rows (32 rows of `steps` x 32*SPG samples, one more word between rows) -> the RSI's samples.
+ * Row r gets the start value of lane r added (0 after the exact walk), then back to the n-bit pattern and,
+ * for signed data, sign extension to the storage width (decode.c:78-84, :131). */
+template <int B, bool SXT>
+__device__ __forceinline__ void store_rows(uint8_t *rsi_out, uint32_t sb, uint32_t o, uint32_t nrows, uint32_t steps,
+                                           uint32_t usadd, uint32_t xorv, uint32_t sxsh, uint32_t msb)
+{
+    constexpr int SPG = (B == 4) ? 1 : ((B == 2) ? 2 : 4);
+    const uint32_t bsel = (B == 4) ? (msb ? 0x0123u : 0x3210u) : ((B == 2) ? (msb ? 0x4501u : 0x5410u) : (msb ? 0x0123u : 0x3210u));
+    for (uint32_t rowi = 0; rowi < nrows; rowi++, sb += 4u) {
+        const uint32_t ua = __shfl_sync(FULL, usadd, rowi);
+#pragma unroll 2
+        for (uint32_t q = 0; q < steps; q++, sb += 128u * SPG, o += 32u * SPG) {
+            uint32_t sv[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < SPG; j++) {
+                uint32_t x;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x) : "r"(sb + 4u * j));
+                x = (x + ua) ^ xorv;
+                if (SXT) x = (uint32_t)((int32_t)(x << sxsh) >> sxsh);
+                sv[j] = x;
+            }
+            store_group_at<B>(rsi_out, o, sv, bsel);
+        }
+    }
+}
+
 template <int JT, int B>
 __global__ void __launch_bounds__(DW_MAX_WARPS * 32)
 aec_decode_warp_kernel(const AecDecArgs a)
@@ -562,22 +614,10 @@ aec_decode_warp_kernel(const AecDecArgs a)
     if (JT != 0 && a.out_aligned && limit == c.R && (GJ % (32u * SPG)) == 0 && (c.rsi % G) == 0) {
         /* every lane owns G whole blocks: GJ / (32*SPG) warp steps per row, the row's lane is warp-uniform */
         const uint32_t nrows = c.R / GJ, steps = GJ / (32u * SPG);
-        const uint32_t *src = wrows + lane * SPG;
-        uint64_t sidx = startS + lane * SPG;
-        for (uint32_t rowi = 0; rowi < nrows; rowi++, src += stride - GJ) {
-            const uint32_t ua = __shfl_sync(FULL, usadd, rowi);
-#pragma unroll 2
-            for (uint32_t q = 0; q < steps; q++, src += 32 * SPG, sidx += 32 * SPG) {
-                uint32_t sv[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                for (int j = 0; j < SPG; j++) {
-                    uint32_t x = (src[j] + ua) ^ xorv;
-                    if (sxsh) x = (uint32_t)((int32_t)(x << sxsh) >> sxsh);
-                    sv[j] = x;
-                }
-                store_group<B>(a.out, sidx, sv, c.msb);
-            }
-        }
+        uint8_t *const rsi_out = a.out + startS * B;                          /* 4-byte aligned: R*B is a multiple of 4 here */
+        const uint32_t sb0 = (uint32_t)__cvta_generic_to_shared(wrows) + lane * SPG * 4u;
+        if (sxsh) store_rows<B, true>(rsi_out, sb0, lane * SPG, nrows, steps, usadd, xorv, sxsh, c.msb);
+        else      store_rows<B, false>(rsi_out, sb0, lane * SPG, nrows, steps, usadd, xorv, 0u, c.msb);
     } else if (JT != 0 && a.out_aligned && (GJ % 4u) == 0 && limit == c.R) {
         const uint32_t ngroups = c.R / SPG;
         for (uint32_t g0 = 0; g0 < ngroups; g0 += 32) {

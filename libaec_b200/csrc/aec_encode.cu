@@ -317,6 +317,7 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
     __shared__ uint32_t s_wlen[NWARP];       /* per-warp sums (no-pad mode) */
     __shared__ uint32_t s_wend[NWARP], s_wa[NWARP], s_wrest[NWARP];   /* per-warp PosFn (pad mode) */
     __shared__ uint32_t s_wk[NWARP];
+    __shared__ uint32_t s_side[TB];          /* one word per thread: the first completed word of its CDS (BitPack) */
     __shared__ uint32_t s_tend[2], s_ta[2], s_trest[2];   /* position map of the packed tile, per staging area */
     __shared__ unsigned long long s_base;    /* absolute bit offset of the tile being streamed out */
     __shared__ unsigned long long s_base_cur;/* late mode: absolute bit offset of the tile being packed */
@@ -517,8 +518,9 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                 myoff = (uint32_t)aec_papply(pexc, 0);
             }
             if (valid && len) {
+                const uint32_t side = (uint32_t)__cvta_generic_to_shared(&s_side[tid]);
                 BitPack bp;
-                bp.init(staging, myoff);
+                bp.init(staging, myoff, side);
                 if (is_zero) {
                     aec_pack_zero(c, bp, zcode, zref, refs);
                 } else {
@@ -537,7 +539,7 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                     }
                     aec_pack_block<JT>(c, bp, d, bi.opt, k, ref, refs);
                 }
-                bp.finish();
+                bp.finish(side);
             }
             if (want_index)
                 pend_all[slot * TB + tid] = make_uint2(myoff, len | (zrun << 12) | ((valid ? 1u : 0u) << 20) |

@@ -130,14 +130,14 @@ extern "C" int model_encode(uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags
             uint64_t myoff = aec_papply(pexc[tid], base);
             if (s.valid && s.b == 0 && offsets) offsets[s.rsi_idx] = myoff;
             if (s.valid && s.len) {
-                BitPack bp; bp.init(staging.data(), (uint32_t)(myoff - (w0 << 5)));
+                BitPack bp; bp.init(staging.data(), (uint32_t)(myoff - (w0 << 5)), 0u);
                 if (s.is_zero) aec_pack_zero(c, bp, s.zcode, s.zref, s.refs);
                 else {
                     uint32_t kprev = aec_kapply(kin, kbefore[tid]);
                     uint32_t k = aec_clampu(kprev, s.bi.klo, s.bi.khi);
                     aec_pack_block<0>(c, bp, s.d, s.bi.opt, k, s.ref, s.refs);
                 }
-                bp.finish();
+                bp.finish(0u);
             }
         }
         const uint32_t nw = (uint32_t)(we - w0) + ((end & 31u) ? 1u : 0u);
