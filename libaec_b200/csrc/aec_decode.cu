@@ -379,29 +379,43 @@ __device__ __forceinline__ void store_group_at(uint8_t *rsi_out, uint32_t s_loca
 
 /* The warp's rows (32 rows of `steps` x 32*SPG samples, one more word between rows) -> the RSI's samples.
  * Row r gets the start value of lane r added (0 after the exact walk), then back to the n-bit pattern and,
- * for signed data, sign extension to the storage width (decode.c:78-84, :131). */
-template <int B, bool SXT>
-__device__ __forceinline__ void store_rows(uint8_t *rsi_out, uint32_t sb, uint32_t o, uint32_t nrows, uint32_t steps,
+ * for signed data, sign extension to the storage width (decode.c:78-84, :131).  STEPS > 0: steps known at
+ * compile time (rows are short -- two warp steps on the README workload -- so loop overhead matters). */
+template <int B, bool SXT, int STEPS>
+__device__ __forceinline__ void store_rows(uint8_t *rsi_out, uint32_t sb, uint32_t o, uint32_t nrows, uint32_t steps_rt,
                                            uint32_t usadd, uint32_t xorv, uint32_t sxsh, uint32_t msb)
 {
     constexpr int SPG = (B == 4) ? 1 : ((B == 2) ? 2 : 4);
-    const uint32_t bsel = (B == 4) ? (msb ? 0x0123u : 0x3210u) : ((B == 2) ? (msb ? 0x4501u : 0x5410u) : (msb ? 0x0123u : 0x3210u));
-    for (uint32_t rowi = 0; rowi < nrows; rowi++, sb += 4u) {
+    const uint32_t bsel = (B == 2) ? (msb ? 0x4501u : 0x5410u) : (msb ? 0x0123u : 0x3210u);
+    const uint32_t steps = STEPS ? (uint32_t)STEPS : steps_rt;
+    for (uint32_t rowi = 0; rowi < nrows; rowi++) {
         const uint32_t ua = __shfl_sync(FULL, usadd, rowi);
-#pragma unroll 2
-        for (uint32_t q = 0; q < steps; q++, sb += 128u * SPG, o += 32u * SPG) {
+#pragma unroll
+        for (uint32_t q = 0; q < steps; q++) {
             uint32_t sv[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int j = 0; j < SPG; j++) {
                 uint32_t x;
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x) : "r"(sb + 4u * j));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x) : "r"(sb + q * 128u * SPG + 4u * j));
                 x = (x + ua) ^ xorv;
                 if (SXT) x = (uint32_t)((int32_t)(x << sxsh) >> sxsh);
                 sv[j] = x;
             }
-            store_group_at<B>(rsi_out, o, sv, bsel);
+            store_group_at<B>(rsi_out, o + q * 32u * SPG, sv, bsel);
         }
+        sb += steps * 128u * SPG + 4u;
+        o += steps * 32u * SPG;
     }
+}
+
+template <int B, bool SXT>
+__device__ __forceinline__ void store_rows_any(uint8_t *rsi_out, uint32_t sb, uint32_t o, uint32_t nrows, uint32_t steps,
+                                               uint32_t usadd, uint32_t xorv, uint32_t sxsh, uint32_t msb)
+{
+    if (steps == 2u)      store_rows<B, SXT, 2>(rsi_out, sb, o, nrows, steps, usadd, xorv, sxsh, msb);
+    else if (steps == 1u) store_rows<B, SXT, 1>(rsi_out, sb, o, nrows, steps, usadd, xorv, sxsh, msb);
+    else if (steps == 4u) store_rows<B, SXT, 4>(rsi_out, sb, o, nrows, steps, usadd, xorv, sxsh, msb);
+    else                  store_rows<B, SXT, 0>(rsi_out, sb, o, nrows, steps, usadd, xorv, sxsh, msb);
 }
 
 template <int JT, int B>
@@ -616,8 +630,8 @@ aec_decode_warp_kernel(const AecDecArgs a)
         const uint32_t nrows = c.R / GJ, steps = GJ / (32u * SPG);
         uint8_t *const rsi_out = a.out + startS * B;                          /* 4-byte aligned: R*B is a multiple of 4 here */
         const uint32_t sb0 = (uint32_t)__cvta_generic_to_shared(wrows) + lane * SPG * 4u;
-        if (sxsh) store_rows<B, true>(rsi_out, sb0, lane * SPG, nrows, steps, usadd, xorv, sxsh, c.msb);
-        else      store_rows<B, false>(rsi_out, sb0, lane * SPG, nrows, steps, usadd, xorv, 0u, c.msb);
+        if (sxsh) store_rows_any<B, true>(rsi_out, sb0, lane * SPG, nrows, steps, usadd, xorv, sxsh, c.msb);
+        else      store_rows_any<B, false>(rsi_out, sb0, lane * SPG, nrows, steps, usadd, xorv, 0u, c.msb);
     } else if (JT != 0 && a.out_aligned && (GJ % 4u) == 0 && limit == c.R) {
         const uint32_t ngroups = c.R / SPG;
         for (uint32_t g0 = 0; g0 < ngroups; g0 += 32) {
