@@ -67,6 +67,13 @@ const char *aecb200_last_error(aecb200_ctx *ctx);
 void aecb200_ctx_set_encode_padding(aecb200_ctx *ctx, int on);
 /* Number of kernels this context has launched so far. */
 uint64_t aecb200_ctx_launches(aecb200_ctx *ctx);
+/* Host-pointer calls (aecb200_encode_host*, aecb200_decode_host with an offset index; what
+ * aec_buffer_encode / aec_buffer_decode of the reference, encode.c:929-963 / decode.c:831-854, turn
+ * into) move buffers of at least two pieces as a pipeline: pieces of about `raw_bytes` of samples
+ * (whole RSIs) are uploaded, coded and downloaded on three streams so that both PCIe directions
+ * and the kernels overlap.  The bytes produced do not depend on the piece size.  Default 16 MiB;
+ * 0 = always one piece. */
+void aecb200_ctx_set_pipeline_piece(aecb200_ctx *ctx, size_t raw_bytes);
 
 /* Upper bound of the compressed size of in_bytes of input. */
 size_t aecb200_encode_bound(const aecb200_params *p, size_t in_bytes);

@@ -94,7 +94,8 @@ DEVICE_SYMBOLS = ["aecb200_device_count", "aecb200_ctx_create", "aecb200_ctx_des
                   "aecb200_decode_host", "aecb200_decode_host_resume", "aecb200_ctx_set_shard_mode",
                   "aecb200_encode_shard_info", "aecb200_ctx_set_tile_limit", "aecb200_place_bits_device",
                   "aecb200_encode_device_indexed", "aecb200_decode_device_indexed", "aecb200_group_index_entries",
-                  "aecb200_ctx_set_careful_decode", "aecb200_ctx_last_handover"]
+                  "aecb200_ctx_set_careful_decode", "aecb200_ctx_last_handover",
+                  "aecb200_ctx_set_pipeline_piece"]
 SZ_SYMBOLS = ["SZ_BufftoBuffCompress", "SZ_BufftoBuffDecompress", "SZ_encoder_enabled", "SZ_Compress"]
 
 
@@ -118,6 +119,7 @@ def load_library() -> C.CDLL:
         lib.aecb200_group_index_entries.restype = C.c_size_t
         lib.aecb200_ctx_last_handover.restype = C.c_uint64
         lib.aecb200_ctx_set_tile_limit.restype = None
+        lib.aecb200_ctx_set_pipeline_piece.restype = None
         _lib = lib
     return _lib
 
@@ -376,6 +378,10 @@ class DeviceCodec:
 
     def set_careful_decode(self, on: bool = True):
         self.lib.aecb200_ctx_set_careful_decode(self.ctx, C.c_int(int(on)))
+
+    def set_pipeline_piece(self, raw_bytes: int):
+        """Piece size of the host-pointer pipeline (0 = one piece)."""
+        self.lib.aecb200_ctx_set_pipeline_piece(self.ctx, C.c_size_t(raw_bytes))
 
     def encode_finish(self):
         end = Carry()

@@ -206,8 +206,9 @@ AEC_HD uint32_t aec_sum_shift(const uint32_t *d, uint32_t J, uint32_t k)
  * Returns opt == OPT_ZERO when every sample is zero (caller runs the zero-run
  * logic); then klo/khi are the identity.
  */
+/*   small   the caller knows every d[i] < 2^24 (then the 32-bit sum stands in for the OR of the values) */
 template <int JT>
-AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t ref)
+AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t ref, bool small = false)
 {
     const uint32_t J = JT ? (uint32_t)JT : c.J;
     BlockInfo bi;
@@ -217,7 +218,14 @@ AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t 
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (uint32_t i = 0; i < J; i++) { orv |= d[i]; s32 += d[i]; }
+    for (uint32_t i = 0; i < J; i++) s32 += d[i];
+    if (small) orv = s32 ? 1u : 0u;          /* only "all zero", ">= 2^25" and ">= 2^31" are asked of orv */
+    else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t i = 0; i < J; i++) orv |= d[i];
+    }
     if (orv == 0) return bi;
     uint64_t S0 = s32;
     if (orv >> 25) {       /* J <= 64 values below 2^25 cannot overflow 32 bits; otherwise add again in 64 */
@@ -609,7 +617,11 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
                     for (uint32_t j = 0; j < 4; j++) {
                         const uint32_t i = g + j;
                         if (i >= J) continue;
+#if defined(__CUDA_ARCH__)
+                        acc = acc * (m + 1u) + (d[i] & m);        /* the shift as a multiply-add: FMA pipe */
+#else
                         acc = (acc << k) | (d[i] & m);
+#endif
                         len += k;
                     }
                     if (g == 0) len -= ref * k;
@@ -620,7 +632,11 @@ AEC_HD void aec_pack_block(const AecCfg &c, BitPack &bp, const uint32_t *d, uint
 #pragma unroll
 #endif
                 for (uint32_t g = 0; g < J; g += 2) {
+#if defined(__CUDA_ARCH__)
+                    const uint32_t acc = (d[g] & m) * (m + 1u) + (d[g + 1] & m);
+#else
                     const uint32_t acc = ((d[g] & m) << k) | (d[g + 1] & m);
+#endif
                     bp.put(acc, (g == 0 && ref) ? k : 2u * k);
                 }
             } else {

@@ -370,6 +370,7 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
             /* ---- load, map, cost ---- */
             uint32_t d[JMAX];
             uint32_t refs = 0;
+            bool small = false;                 /* mapped values known to be below 2^24 */
             BlockInfo bi; bi.opt = OPT_NONE; bi.klo = 0; bi.khi = c.kmax; bi.len = 0;
             {
                 const uint64_t first = rsi_idx * (uint64_t)c.R + (uint64_t)b * J;
@@ -384,16 +385,53 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                         if (pi >= a.nsamples) pi = a.nsamples - 1;
                         prev = load_one<B>(a.in, pi, c.msb, a.aligned);
                     }
-                    prev ^= c.sflip;
+                    /* A block whose value range fits between the block and both ends of [0, M] cannot clip
+                     * (every |delta| <= range <= min(u, M - u)): its mapped values are plain zig-zag codes
+                     * of the signed differences.  Smooth data away from the limits always takes this path.
+                     * For unsigned and for signed 32-bit samples the sign flip cancels in the differences
+                     * and the range test can do without it. */
+                    uint32_t umin, umax, sf = c.sflip;   /* sf: flip still to apply on the exact path */
+                    if (c.sflip == 0u) {
+                        umin = prev; umax = prev;
 #pragma unroll
-                    for (uint32_t i = 0; i < (JT ? (uint32_t)JT : J); i++) {
-                        uint32_t u = d[i] ^ c.sflip;
-                        d[i] = aec_map_delta(prev, u, c.mask);
-                        prev = u;
+                        for (uint32_t i = 0; i < (JT ? (uint32_t)JT : J); i++) { umin = min(umin, d[i]); umax = max(umax, d[i]); }
+                    } else if (c.sflip == 0x80000000u) {
+                        int32_t smin = (int32_t)prev, smax = (int32_t)prev;
+#pragma unroll
+                        for (uint32_t i = 0; i < (JT ? (uint32_t)JT : J); i++) { smin = min(smin, (int32_t)d[i]); smax = max(smax, (int32_t)d[i]); }
+                        umin = (uint32_t)smin ^ 0x80000000u; umax = (uint32_t)smax ^ 0x80000000u;
+                    } else {
+                        /* n < 32: the flip only cancels modulo 2^n, so flip in place */
+                        prev ^= c.sflip; sf = 0u;
+                        umin = prev; umax = prev;
+#pragma unroll
+                        for (uint32_t i = 0; i < (JT ? (uint32_t)JT : J); i++) {
+                            d[i] ^= c.sflip;
+                            umin = min(umin, d[i]); umax = max(umax, d[i]);
+                        }
+                    }
+                    const uint32_t range = umax - umin;
+                    if (JT != 0 && range <= umin && umax <= c.mask && range <= c.mask - umax) {
+#pragma unroll
+                        for (uint32_t i = 0; i < (JT ? (uint32_t)JT : J); i++) {
+                            const uint32_t u = d[i];
+                            const int32_t x = (int32_t)(u - prev);
+                            d[i] = ((uint32_t)x << 1) ^ (uint32_t)(x >> 31);
+                            prev = u;
+                        }
+                        small = range < (1u << 23);          /* zig-zag codes below 2^24 */
+                    } else {
+                        prev ^= sf;
+#pragma unroll
+                        for (uint32_t i = 0; i < (JT ? (uint32_t)JT : J); i++) {
+                            const uint32_t u = d[i] ^ sf;
+                            d[i] = aec_map_delta(prev, u, c.mask);
+                            prev = u;
+                        }
                     }
                     if (b == 0) d[0] = 0;
                 }
-                if (valid) bi = aec_analyze_block<JT>(c, d, ref);
+                if (valid) bi = aec_analyze_block<JT>(c, d, ref, small);
             }
             const bool is_zero = valid && bi.opt == OPT_ZERO;
 
@@ -423,8 +461,8 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
             uint32_t kinc = kp;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
-                uint32_t o = __shfl_up_sync(FULL, kinc, off);
-                if (lane >= (uint32_t)off) kinc = aec_kcompose(o, kinc);
+                /* lanes below `off` get their own pair back, and a clamp pair composed with itself is itself */
+                kinc = aec_kcompose(__shfl_up_sync(FULL, kinc, off), kinc);
             }
             uint32_t kexc = __shfl_up_sync(FULL, kinc, 1);
             if (lane == 0) kexc = kident;
@@ -459,8 +497,7 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                 uint32_t wk = lane < (uint32_t)NWARP ? s_wk[lane] : kident;
 #pragma unroll
                 for (int off = 1; off < NWARP; off <<= 1) {
-                    uint32_t o = __shfl_up_sync(FULL, wk, off);
-                    if (lane >= (uint32_t)off) wk = aec_kcompose(o, wk);
+                    wk = aec_kcompose(__shfl_up_sync(FULL, wk, off), wk);
                 }
                 kbefore = __shfl_sync(FULL, wk, warp ? warp - 1 : 0);
                 if (warp == 0) kbefore = kident;
@@ -547,12 +584,11 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
             if (tid == 0) { s_tend[slot] = ptile.has_end; s_ta[slot] = (uint32_t)ptile.a; s_trest[slot] = (uint32_t)ptile.rest; }
         }
 
-        /* The previous tile's prefix has had a whole tile time to arrive.  Only now claim the next
-         * tile: a claimed tile never waits for anything but earlier tiles, so the scanner's fixed
-         * batches of 32 tiles always complete, and a tile always goes to the CTA that is ready for it
-         * first (claiming ahead pins tiles to CTAs and lets one late CTA hold up the whole chain:
-         * profiles/r1_g).  The ticket itself is only needed after the copy-out, so its round trip
-         * overlaps the copy-out instead of the barrier. */
+        /* The previous tile's prefix has had a whole tile time to arrive.  A tile is claimed only when
+         * the CTA is about to work on it, so a claimed tile never waits for anything but earlier tiles:
+         * the scanner's fixed batches of 32 tiles always complete, and a tile always goes to the CTA
+         * that is ready for it first (claiming ahead pins tiles to CTAs and lets one late CTA hold up
+         * the whole chain: profiles/r1_g). */
         uint32_t nxt = 0xFFFFFFFFu;
         if (tid == 0) {
             if (prev_have) {
@@ -561,7 +597,11 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                 while ((pv0 & 3) == 0) { pv0 = ld_volatile_u64(&a.pref[s_ticket[gp]]); spin_guard(spins); }
                 s_base = pv0 >> 12;
             }
-            if (have) nxt = atomicAdd(a.ticket, 1u);
+            /* with a tile to stream out, the next tile is claimed after that (below): the later the
+             * claim, the sooner after it the tile's aggregate is published, and every later tile's prefix
+             * waits for that aggregate (profiles/r1_e: the time from claim to publication plus the scanner's
+             * latency had grown as long as a whole tile time, so every tile waited at S3) */
+            if (have && !prev_have) nxt = atomicAdd(a.ticket, 1u);
             if (!prev_have || !have) { if (have) place(gn, nxt); else s_ticket[gn] = 0xFFFFFFFFu; }
         }
         __syncthreads();                                               /* S3 */
@@ -607,22 +647,50 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                 if ((uint64_t)i_hi > capw) i_hi = (uint32_t)capw;
             }
             uint32_t *dst = a.out_words + w0;
+            {
+                /* words [i_lo, i_hi): 16-byte stores for the part between the first and the last 16-byte
+                 * boundary of the destination, single words (at most six, threads 0..5) for the rest */
+                const uint32_t i_lo = head_partial ? 1u : 0u;
+                const uint32_t mis = ((uint32_t)(uintptr_t)dst >> 2) & 3u;
+                uint32_t i_al = i_lo + ((0u - (mis + i_lo)) & 3u);
+                if (i_al > i_hi) i_al = i_hi;
+                if (i_hi < i_lo) i_al = i_lo;
+                const uint32_t nvec = i_hi > i_al ? (i_hi - i_al) >> 2 : 0u;
+                const uint32_t i_tl = i_al + 4u * nvec;
 #pragma unroll 1
-            for (uint32_t i = (head_partial ? 1u : 0u) + tid; i < i_hi; i += TB) {
-                const uint32_t v = __funnelshift_r(pstage[i], pstage[(int)i - 1], sh);
-                dst[i] = __byte_perm(v, 0, 0x0123);
+                for (uint32_t q = tid; q < nvec; q += TB) {
+                    const uint32_t i = i_al + 4u * q;
+                    const uint32_t p0 = pstage[(int)i - 1], p1 = pstage[i], p2 = pstage[i + 1], p3 = pstage[i + 2],
+                                   p4 = pstage[i + 3];
+                    uint4 o;
+                    o.x = __byte_perm(__funnelshift_r(p1, p0, sh), 0, 0x0123);
+                    o.y = __byte_perm(__funnelshift_r(p2, p1, sh), 0, 0x0123);
+                    o.z = __byte_perm(__funnelshift_r(p3, p2, sh), 0, 0x0123);
+                    o.w = __byte_perm(__funnelshift_r(p4, p3, sh), 0, 0x0123);
+                    *reinterpret_cast<uint4 *>(dst + i) = o;
+                }
+                const uint32_t nh = i_al - i_lo;
+                const uint32_t i = tid < nh ? i_lo + tid : i_tl + (tid - nh);
+                if (i < i_hi && (tid < nh || i >= i_tl)) {
+                    const uint32_t v = __funnelshift_r(pstage[i], pstage[(int)i - 1], sh);
+                    dst[i] = __byte_perm(v, 0, 0x0123);
+                }
             }
             if (tid == 0)
                 a.head_c[prev_tile] = (head_partial && end > base) ? (pstage[0] >> sh) : 0u;
             if (tid == 32)
                 a.tail_c[prev_tile] = tail_partial ? __funnelshift_r(pstage[nwhole], pstage[(int)nwhole - 1], sh) : 0u;
-            if (tid == 0 && have) place(gn, nxt);                      /* the ticket claimed before S3 has arrived by now */
+            if (tid == 0 && have) nxt = atomicAdd(a.ticket, 1u);       /* the answer travels while the area is cleared */
             __syncthreads();                                           /* S4: everyone has read the words */
             {
                 uint4 *z = reinterpret_cast<uint4 *>(staging_all + (slot ^ 1u) * SW);
                 const uint32_t n4 = (nsl + 5u) >> 2;                   /* pad word + nsl words + one spare */
 #pragma unroll 1
                 for (uint32_t i = tid; i < n4; i += TB) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            if (have) {
+                if (tid == 0) place(gn, nxt);
+                __syncthreads();                                       /* S5: the next tile's place is known */
             }
         }
         if (!have) break;
@@ -637,6 +705,9 @@ __global__ void aec_encode_fixup_kernel(const AecEncArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - 1;   /* -1 = the seed */
     if (i >= (int64_t)a.ntiles_total) return;
+    /* leave the control words as the next launch expects them (this kernel runs after the coder) */
+    if (i < 0) *a.ticket = 0u;
+    else { a.desc[i] = 0ull; a.pref[i] = 0ull; }
     const uint64_t total = a.tile_end[a.ntiles_total - 1];
     uint64_t bi = (i <= 0) ? a.seed_bits : a.tile_end[i - 1];
     uint64_t ei = (i < 0) ? a.seed_bits : a.tile_end[i];

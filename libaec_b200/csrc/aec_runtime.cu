@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <vector>
 
 #include "../../include/aec_b200.h"
 #include "aec_device.h"
@@ -40,6 +41,14 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    /* same, and a new allocation starts out as zeros (control words the kernels themselves reset) */
+    cudaError_t ensure_zeroed(size_t n, cudaStream_t st)
+    {
+        if (n <= cap) return cudaSuccess;
+        cudaError_t e = ensure(n);
+        if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, cap, st);
+        return e;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
@@ -59,6 +68,11 @@ struct aecb200_ctx {
     bool want_summary = false;
     bool careful_only = false;           /* decode with the lane-per-RSI kernel only (tests) */
     uint64_t *h_res = nullptr;           /* pinned: [0..3] encode result, [4..7] decode result */
+    /* host-pointer calls on large buffers run as a pipeline of pieces: uploads on s_in, kernels on
+     * `stream`, downloads on s_out (PCIe carries both directions at once) */
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev;
+    size_t pipe_piece = (size_t)16 << 20; /* bytes of raw samples per piece; 0 = never pipeline */
 
     /* bookkeeping of the last enqueued operation */
     uint64_t enc_out_cap_bits = 0;
@@ -113,6 +127,28 @@ EncGeom enc_geometry(const AecCfg &c, size_t in_bytes)
     return g;
 }
 
+/* streams and events of the host-call pipeline (created on first use) */
+int pipe_prepare(aecb200_ctx *ctx, size_t nevents)
+{
+    if (!ctx->s_in) CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking), "cudaStreamCreate(in)");
+    if (!ctx->s_out) CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking), "cudaStreamCreate(out)");
+    while (ctx->ev.size() < nevents) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+        ctx->ev.push_back(e);
+    }
+    return AEC_OK;
+}
+
+/* a failed piece must not leave copies in flight on the side streams */
+int pipe_abort(aecb200_ctx *ctx, int rc)
+{
+    cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_out);
+    return rc;
+}
+
 } // namespace
 
 extern "C" {
@@ -161,6 +197,9 @@ void aecb200_ctx_destroy(aecb200_ctx *ctx)
     ctx->misc.release(); ctx->in_stage.release(); ctx->out_stage.release(); ctx->offs.release();
     ctx->rsi_count.release();
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -176,6 +215,7 @@ int aecb200_ctx_set_stream(aecb200_ctx *ctx, void *cuda_stream)
 const char *aecb200_last_error(aecb200_ctx *ctx) { return ctx ? ctx->err : "no context"; }
 void aecb200_ctx_set_encode_padding(aecb200_ctx *ctx, int on) { if (ctx) ctx->honour_pad = on ? 1 : 0; }
 uint64_t aecb200_ctx_launches(aecb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void aecb200_ctx_set_pipeline_piece(aecb200_ctx *ctx, size_t raw_bytes) { if (ctx) ctx->pipe_piece = raw_bytes; }
 
 size_t aecb200_encode_bound(const aecb200_params *p, size_t in_bytes)
 {
@@ -239,16 +279,15 @@ int aecb200_encode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
         snprintf(ctx->err, sizeof ctx->err, "input too large for one launch (%llu tiles)", (unsigned long long)g.ntiles);
         return AEC_CONF_ERROR;
     }
-    CK(ctx->desc.ensure(g.ntiles * 8), "cudaMalloc(desc)");
-    CK(ctx->pref.ensure(g.ntiles * 8), "cudaMalloc(pref)");
+    /* tile descriptors, prefixes and the ticket are zero between launches: the fix-up kernel, which
+     * runs last, clears what its launch used (no memsets in front of every launch) */
+    CK(ctx->desc.ensure_zeroed(g.ntiles * 8, ctx->stream), "cudaMalloc(desc)");
+    CK(ctx->pref.ensure_zeroed(g.ntiles * 8, ctx->stream), "cudaMalloc(pref)");
     CK(ctx->headc.ensure(g.ntiles * 4), "cudaMalloc(head)");
     CK(ctx->tailc.ensure(g.ntiles * 4), "cudaMalloc(tail)");
     CK(ctx->tile_end.ensure(g.ntiles * 8), "cudaMalloc(tile_end)");
     CK(ctx->tile_kagg.ensure(g.ntiles * 4), "cudaMalloc(tile_kagg)");
-    CK(ctx->misc.ensure(256), "cudaMalloc(misc)");
-    CK(cudaMemsetAsync(ctx->desc.p, 0, g.ntiles * 8, ctx->stream), "memset(desc)");
-    CK(cudaMemsetAsync(ctx->pref.p, 0, g.ntiles * 8, ctx->stream), "memset(pref)");
-    CK(cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream), "memset(misc)");
+    CK(ctx->misc.ensure_zeroed(256, ctx->stream), "cudaMalloc(misc)");
 
     AecEncArgs a;
     memset(&a, 0, sizeof a);
@@ -358,7 +397,7 @@ int aecb200_decode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
     ctx->dec_pending = true;
     ctx->dec_out_samples = out_samples;
     ctx->dec_B = c.B;
-    CK(ctx->misc.ensure(256), "cudaMalloc(misc)");
+    CK(ctx->misc.ensure_zeroed(256, ctx->stream), "cudaMalloc(misc)");
     uint64_t *res = (uint64_t *)((uint8_t *)ctx->misc.p + 128);
     /* delivered = min(out_samples, RSIs available * R) unless a lane reports less:
      * lanes that fall short atomicMax the complement of their position into
@@ -430,7 +469,7 @@ int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
     if (rc != AEC_OK) return rc;
     c.pad = (p->flags & AECF_PAD_RSI) ? 1u : 0u;      /* the decoder always honours it (decode.c:406-408) */
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    CK(ctx->misc.ensure(256), "cudaMalloc(misc)");
+    CK(ctx->misc.ensure_zeroed(256, ctx->stream), "cudaMalloc(misc)");
     uint64_t *res = (uint64_t *)((uint8_t *)ctx->misc.p + 192);
     if (found) *found = 0;
     if (max_rsi == 0) return AEC_OK;
@@ -469,6 +508,16 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
     uint64_t end_bits = phase;
     uint32_t end_k = carry->k;
     size_t bound = aecb200_encode_bound(p, use_bytes) + 8;
+    /* pieces of whole RSIs; a piece starts at the bit where the one before ended, so the pieces
+     * write one contiguous stream into out_stage (the same seeding as AEC_NO_FLUSH streaming) */
+    size_t piece = use_bytes;
+    if (ctx->pipe_piece && use_bytes >= 2 * ctx->pipe_piece) {
+        const size_t unit = rsi_bytes * 16;             /* pieces start 16-byte aligned (vector loads) */
+        piece = ((ctx->pipe_piece + unit - 1) / unit) * unit;
+        if ((use_bytes + piece - 1) / piece > 256) piece = (((use_bytes + 255) / 256 + unit - 1) / unit) * unit;
+    }
+    const size_t npieces = use_bytes ? (use_bytes + piece - 1) / piece : 0;
+    size_t copied = 0;                                   /* bytes of the stream already on their way to `out` */
     if (use_bytes) {
         CK(ctx->in_stage.ensure(use_bytes + 16), "cudaMalloc(in)");
         CK(ctx->out_stage.ensure(bound), "cudaMalloc(out)");
@@ -477,15 +526,57 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
             CK(ctx->offs.ensure(nrsi * 8), "cudaMalloc(offsets)");
             d_offs = (uint64_t *)ctx->offs.p;
         }
-        CK(cudaMemcpyAsync(ctx->in_stage.p, in, use_bytes, cudaMemcpyHostToDevice, ctx->stream), "H2D");
         aecb200_carry seed = {phase, carry->k, carry->word};
-        rc = aecb200_encode_device(ctx, p, ctx->in_stage.p, use_bytes, ctx->out_stage.p, ctx->out_stage.cap & ~(size_t)3,
-                                   &seed, d_offs);
-        if (rc != AEC_OK) return rc;
-        aecb200_carry e;
-        rc = aecb200_encode_finish(ctx, &e);
-        if (rc != AEC_OK) return rc;
-        end_bits = e.bits; end_k = e.k;
+        if (npieces == 1) {
+            CK(cudaMemcpyAsync(ctx->in_stage.p, in, use_bytes, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+            rc = aecb200_encode_device(ctx, p, ctx->in_stage.p, use_bytes, ctx->out_stage.p, ctx->out_stage.cap & ~(size_t)3,
+                                       &seed, d_offs);
+            if (rc != AEC_OK) return rc;
+            aecb200_carry e;
+            rc = aecb200_encode_finish(ctx, &e);
+            if (rc != AEC_OK) return rc;
+            end_bits = e.bits; end_k = e.k;
+        } else {
+            rc = pipe_prepare(ctx, npieces);
+            if (rc != AEC_OK) return rc;
+            for (size_t i = 0; i < npieces; i++) {       /* all uploads are queued now and run back to back */
+                const size_t o = i * piece, nb = (o + piece <= use_bytes) ? piece : use_bytes - o;
+                CK(cudaMemcpyAsync((uint8_t *)ctx->in_stage.p + o, (const uint8_t *)in + o, nb, cudaMemcpyHostToDevice, ctx->s_in), "H2D");
+                CK(cudaEventRecord(ctx->ev[i], ctx->s_in), "cudaEventRecord");
+            }
+            for (size_t i = 0; i < npieces; i++) {
+                const size_t o = i * piece, nb = (o + piece <= use_bytes) ? piece : use_bytes - o;
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[i], 0), "cudaStreamWaitEvent");
+                rc = aecb200_encode_device(ctx, p, (uint8_t *)ctx->in_stage.p + o, nb, ctx->out_stage.p,
+                                           ctx->out_stage.cap & ~(size_t)3, &seed,
+                                           d_offs ? d_offs + (o / rsi_bytes) : nullptr);
+                aecb200_carry e = {0, 0, 0};
+                if (rc == AEC_OK) rc = aecb200_encode_finish(ctx, &e);
+                if (rc != AEC_OK) return pipe_abort(ctx, rc);
+                end_bits = e.bits; end_k = e.k;
+                seed.bits = e.bits; seed.k = e.k; seed.word = 0;
+                if (i + 1 < npieces) {
+                    /* words in front of the stream's last, unfinished one are final: send them out
+                     * while the next piece is coded */
+                    size_t fin = (size_t)(end_bits >> 5) << 2;
+                    if (fin > out_cap) fin = out_cap;
+                    if (fin > copied) {
+                        CK(cudaMemcpyAsync((uint8_t *)out + copied, (uint8_t *)ctx->out_stage.p + copied, fin - copied,
+                                           cudaMemcpyDeviceToHost, ctx->s_out), "D2H");
+                        copied = fin;
+                    }
+                    if (end_bits & 31u) {
+                        /* the next piece completes that word: hand it the bits it already holds */
+                        uint8_t *hb = (uint8_t *)&ctx->h_res[11];
+                        CK(cudaMemcpyAsync(hb, (uint8_t *)ctx->out_stage.p + ((size_t)(end_bits >> 5) << 2), 4,
+                                           cudaMemcpyDeviceToHost, ctx->stream), "D2H word");
+                        CK(cudaStreamSynchronize(ctx->stream), "sync");
+                        const uint32_t w = ((uint32_t)hb[0] << 24) | ((uint32_t)hb[1] << 16) | ((uint32_t)hb[2] << 8) | hb[3];
+                        seed.word = w & ~(0xFFFFFFFFu >> (end_bits & 31u));
+                    }
+                }
+            }
+        }
         if (d_offs) {
             size_t ncopy = nrsi < offsets_cap ? (size_t)nrsi : offsets_cap;
             CK(cudaMemcpyAsync(rsi_offsets, d_offs, ncopy * 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H offsets");
@@ -501,12 +592,15 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
     size_t ncopy = nbytes < out_cap ? nbytes : out_cap;
     uint32_t tailword = 0;
     if (use_bytes) {
-        if (ncopy) CK(cudaMemcpyAsync(out, ctx->out_stage.p, ncopy, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+        if (ncopy > copied)
+            CK(cudaMemcpyAsync((uint8_t *)out + copied, (uint8_t *)ctx->out_stage.p + copied, ncopy - copied,
+                               cudaMemcpyDeviceToHost, ctx->stream), "D2H");
         if (!final && (end_bits & 7u)) {
             CK(cudaMemcpyAsync(&ctx->h_res[10], (uint8_t *)ctx->out_stage.p + (end_bits / 8), 1,
                                cudaMemcpyDeviceToHost, ctx->stream), "D2H tail");
         }
         CK(cudaStreamSynchronize(ctx->stream), "sync");
+        if (npieces > 1) CK(cudaStreamSynchronize(ctx->s_out), "sync(out)");
         if (!final && (end_bits & 7u)) tailword = (uint32_t)(*(uint8_t *)&ctx->h_res[10]) << 24;
     } else {
         /* no whole sample: the stream so far is just the carried partial byte */
@@ -629,6 +723,74 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
     return AEC_OK;
 }
 
+#define AECB200_NOT_PIPELINED 1000
+/* Whole-buffer decode of a large stream with a caller-supplied RSI offset index, as a pipeline of
+ * RSI ranges: a range is decoded as soon as the bytes up to its last bit have arrived, and its
+ * samples travel back while the next range is decoded.  Anything but a clean decode of every range
+ * (short index, truncated or damaged stream) returns AECB200_NOT_PIPELINED and the caller repeats
+ * the call on the one-piece path, which reproduces the reference's partial results. */
+static int decode_host_pipelined(aecb200_ctx *ctx, const aecb200_params *p, const AecCfg &c,
+                                 const void *in, size_t in_bytes,
+                                 const uint64_t *rsi_offsets, size_t n_offsets,
+                                 void *out, size_t out_cap, size_t *out_len)
+{
+    const size_t rsi_bytes = (size_t)c.R * c.B;
+    const uint64_t out_samples = out_cap / c.B;
+    const uint64_t need_rsi = (out_samples + c.R - 1) / c.R;
+    if (!ctx->pipe_piece || !rsi_offsets || need_rsi > n_offsets || need_rsi < 2 ||
+        out_samples * c.B < 2 * ctx->pipe_piece || in_bytes < 8)
+        return AECB200_NOT_PIPELINED;
+    for (uint64_t r = 0; r < need_rsi; r++)                     /* a usable index ascends inside the stream */
+        if (rsi_offsets[r] >= (uint64_t)in_bytes * 8ull || (r && rsi_offsets[r] <= rsi_offsets[r - 1]))
+            return AECB200_NOT_PIPELINED;
+    uint64_t per = (ctx->pipe_piece + rsi_bytes - 1) / rsi_bytes;            /* RSIs per piece */
+    if ((need_rsi + per - 1) / per > 256) per = (need_rsi + 255) / 256;
+    const size_t npieces = (size_t)((need_rsi + per - 1) / per);
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    int rc = pipe_prepare(ctx, npieces);
+    if (rc != AEC_OK) return rc;
+    const size_t in_pad = (in_bytes + 3) & ~(size_t)3;
+    CK(ctx->in_stage.ensure(in_pad + 16), "cudaMalloc(in)");
+    CK(ctx->out_stage.ensure((size_t)(out_samples * c.B) + 16), "cudaMalloc(out)");
+    CK(ctx->offs.ensure((need_rsi + 1) * 8), "cudaMalloc(offsets)");
+    CK(cudaMemsetAsync((uint8_t *)ctx->in_stage.p + (in_pad - 4), 0, 4, ctx->s_in), "memset(in tail)");
+    CK(cudaMemcpyAsync(ctx->offs.p, rsi_offsets, need_rsi * 8, cudaMemcpyHostToDevice, ctx->s_in), "H2D offsets");
+    size_t up = 0;                                              /* bytes of the stream queued for upload */
+    for (size_t i = 0; i < npieces; i++) {
+        const uint64_t r1 = (i + 1) * per < need_rsi ? (i + 1) * per : need_rsi;
+        /* through the last bit of the range, plus what the readers prefetch beyond it */
+        size_t upto = r1 < need_rsi ? (size_t)(rsi_offsets[r1] / 8) + 256 : in_bytes;
+        if (upto > in_bytes || i + 1 == npieces) upto = in_bytes;
+        if (upto > up) {
+            CK(cudaMemcpyAsync((uint8_t *)ctx->in_stage.p + up, (const uint8_t *)in + up, upto - up,
+                               cudaMemcpyHostToDevice, ctx->s_in), "H2D");
+            up = upto;
+        }
+        CK(cudaEventRecord(ctx->ev[i], ctx->s_in), "cudaEventRecord");
+    }
+    size_t total = 0;
+    for (size_t i = 0; i < npieces; i++) {
+        const uint64_t r0 = i * per, r1 = (i + 1) * per < need_rsi ? (i + 1) * per : need_rsi;
+        const size_t o = (size_t)r0 * rsi_bytes;
+        size_t nb = (size_t)(r1 - r0) * rsi_bytes;
+        if (o + nb > (size_t)(out_samples * c.B)) nb = (size_t)(out_samples * c.B) - o;
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[i], 0), "cudaStreamWaitEvent");
+        size_t got = 0;
+        rc = aecb200_decode_device(ctx, p, ctx->in_stage.p, in_bytes, (const uint64_t *)ctx->offs.p + r0, (size_t)(r1 - r0),
+                                   (uint8_t *)ctx->out_stage.p + o, nb);
+        if (rc == AEC_OK) rc = aecb200_decode_finish(ctx, &got);
+        if (rc != AEC_OK || got != nb) {
+            pipe_abort(ctx, rc);
+            return (rc == AEC_OK || rc == AEC_DATA_ERROR) ? AECB200_NOT_PIPELINED : rc;
+        }
+        CK(cudaMemcpyAsync((uint8_t *)out + o, (uint8_t *)ctx->out_stage.p + o, nb, cudaMemcpyDeviceToHost, ctx->s_out), "D2H");
+        total += nb;
+    }
+    CK(cudaStreamSynchronize(ctx->s_out), "sync(out)");
+    if (out_len) *out_len = total;
+    return AEC_OK;
+}
+
 int aecb200_decode_host(aecb200_ctx *ctx, const aecb200_params *p,
                         const void *in, size_t in_bytes,
                         const uint64_t *rsi_offsets, size_t n_offsets,
@@ -640,8 +802,10 @@ int aecb200_decode_host(aecb200_ctx *ctx, const aecb200_params *p,
     if (out_len) *out_len = 0;
     if (rc != AEC_OK) return rc;
     size_t written = 0;
-    rc = aecb200_decode_host_resume(ctx, p, in, in_bytes, rsi_offsets, n_offsets, 0, 0,
-                                    out, out_cap, &written, nullptr, nullptr);
+    rc = decode_host_pipelined(ctx, p, c, in, in_bytes, rsi_offsets, n_offsets, out, out_cap, &written);
+    if (rc == AECB200_NOT_PIPELINED)
+        rc = aecb200_decode_host_resume(ctx, p, in, in_bytes, rsi_offsets, n_offsets, 0, 0,
+                                        out, out_cap, &written, nullptr, nullptr);
     if (rc != AEC_OK) return rc;
     if (out_len) *out_len = written;
     size_t left = out_cap - written;

@@ -80,6 +80,53 @@ def test_pad_rsi_encode_matches_padding_build():
     codec.close()
 
 
+def test_host_pipeline_pieces_match_oracle():
+    """Host-pointer calls on buffers of several pieces (uploads, kernels and downloads overlapped on
+    three streams, every piece seeded with the bit position, k and partial word the one before left):
+    same bytes as the one-piece call and the oracle, for every layout; decode through the offset
+    index likewise."""
+    from cases import random_params, synth_values, pack_samples
+    from oracle.pyoracle import AEC_DATA_SIGNED
+    done = 0
+    for seed in range(400):
+        rng = np.random.default_rng(10_000 + seed)
+        p = random_params(rng, allow_pad=bool(seed & 1))
+        R = p.rsi * p.block_size
+        if 40 * R > 300_000:
+            continue
+        pad_build = bool(p.flags & L.AEC_PAD_RSI)
+        count = int(rng.integers(33, 40)) * R + int(rng.integers(0, R))
+        vals = synth_values(rng, p.bits_per_sample, count, int(rng.integers(0, 6)), bool(p.flags & AEC_DATA_SIGNED))
+        raw = np.ascontiguousarray(pack_samples(vals, p))
+        want = po.orc_encode(p, raw, want_offsets=True, pad_rsi_build=pad_build)
+        codec = L.DeviceCodec(encode_padding=pad_build)
+        codec.set_pipeline_piece(1)                      # smallest piece: 16 RSIs
+        cap = L.encode_bound(P(p), raw.size) + 16
+        out = np.zeros(cap, np.uint8)
+        nrsi = (count + R - 1) // R
+        offs = np.zeros(nrsi, np.uint64)
+        st, n, noff = codec.encode_host(P(p), raw.ctypes.data, raw.size, out.ctypes.data, cap, offs.ctypes.data, nrsi)
+        assert st == want["status"] == 0, (seed, p)
+        assert np.array_equal(out[:n], want["out"]), (seed, p)
+        assert noff == nrsi and np.array_equal(offs, want["offsets"]), (seed, p)
+        back = np.zeros(raw.size, np.uint8)
+        comp = np.ascontiguousarray(out[:n])
+        st, m = codec.decode_host(P(p), comp.ctypes.data, n, back.ctypes.data, raw.size, offs.ctypes.data, nrsi)
+        ref = po.orc_decode(p, want["out"], raw.size)      # signed samples come back sign-extended
+        assert ref["status"] == 0
+        assert st == 0 and m == raw.size and np.array_equal(back, ref["out"]), (seed, p)
+        # fewer samples than coded: the last piece ends inside an RSI
+        part = (count - R // 2 - 1) * p.bytes_per_sample
+        back[:] = 0
+        st, m = codec.decode_host(P(p), comp.ctypes.data, n, back.ctypes.data, part, offs.ctypes.data, nrsi)
+        assert st == 0 and m == part and np.array_equal(back[:part], ref["out"][:part]), (seed, p)
+        codec.close()
+        done += 1
+        if done >= 120:
+            break
+    assert done >= 60
+
+
 def test_golden_typical_rz_both_directions():
     rz = np.fromfile(os.path.join(ROOT, "tests", "golden", "typical.rz"), dtype=np.uint8)
     p = L.Params(16, 64, 256, L.AEC_DATA_MSB | L.AEC_DATA_PREPROCESS)
