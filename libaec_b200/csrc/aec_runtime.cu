@@ -71,6 +71,7 @@ struct aecb200_ctx {
     /* host-pointer calls on large buffers run as a pipeline of pieces: uploads on s_in, kernels on
      * `stream`, downloads on s_out (PCIe carries both directions at once) */
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_idx[4] = {nullptr, nullptr, nullptr, nullptr};   /* group-index builds of the decode pipeline */
     std::vector<cudaEvent_t> ev;
     size_t pipe_piece = (size_t)16 << 20; /* bytes of raw samples per piece; 0 = never pipeline */
 
@@ -132,6 +133,8 @@ int pipe_prepare(aecb200_ctx *ctx, size_t nevents)
 {
     if (!ctx->s_in) CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking), "cudaStreamCreate(in)");
     if (!ctx->s_out) CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking), "cudaStreamCreate(out)");
+    for (cudaStream_t &st : ctx->s_idx)
+        if (!st) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate(index)");
     while (ctx->ev.size() < nevents) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
@@ -144,6 +147,7 @@ int pipe_prepare(aecb200_ctx *ctx, size_t nevents)
 int pipe_abort(aecb200_ctx *ctx, int rc)
 {
     cudaStreamSynchronize(ctx->s_in);
+    for (cudaStream_t st : ctx->s_idx) if (st) cudaStreamSynchronize(st);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->s_out);
     return rc;
@@ -200,6 +204,7 @@ void aecb200_ctx_destroy(aecb200_ctx *ctx)
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    for (cudaStream_t st : ctx->s_idx) if (st) cudaStreamDestroy(st);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -744,10 +749,15 @@ static int decode_host_pipelined(aecb200_ctx *ctx, const aecb200_params *p, cons
         if (rsi_offsets[r] >= (uint64_t)in_bytes * 8ull || (r && rsi_offsets[r] <= rsi_offsets[r - 1]))
             return AECB200_NOT_PIPELINED;
     uint64_t per = (ctx->pipe_piece + rsi_bytes - 1) / rsi_bytes;            /* RSIs per piece */
-    if ((need_rsi + per - 1) / per > 256) per = (need_rsi + 255) / 256;
-    const size_t npieces = (size_t)((need_rsi + per - 1) / per);
+    if ((need_rsi + per - 1) / per > 240) per = (need_rsi + 239) / 240;
+    /* piece i covers RSIs [first[i], first[i+1]) (short leading pieces were tried and lost to the
+     * fixed cost of a piece: gpurun e2e_sweep3, profiles/r1_f_summary.md) */
+    std::vector<uint64_t> first;
+    for (uint64_t r = 0; r < need_rsi; r += per) first.push_back(r);
+    first.push_back(need_rsi);
+    const size_t npieces = first.size() - 1;
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    int rc = pipe_prepare(ctx, npieces);
+    int rc = pipe_prepare(ctx, 2 * npieces);
     if (rc != AEC_OK) return rc;
     const size_t in_pad = (in_bytes + 3) & ~(size_t)3;
     CK(ctx->in_stage.ensure(in_pad + 16), "cudaMalloc(in)");
@@ -757,7 +767,7 @@ static int decode_host_pipelined(aecb200_ctx *ctx, const aecb200_params *p, cons
     CK(cudaMemcpyAsync(ctx->offs.p, rsi_offsets, need_rsi * 8, cudaMemcpyHostToDevice, ctx->s_in), "H2D offsets");
     size_t up = 0;                                              /* bytes of the stream queued for upload */
     for (size_t i = 0; i < npieces; i++) {
-        const uint64_t r1 = (i + 1) * per < need_rsi ? (i + 1) * per : need_rsi;
+        const uint64_t r1 = first[i + 1] < need_rsi ? first[i + 1] : need_rsi;
         /* through the last bit of the range, plus what the readers prefetch beyond it */
         size_t upto = r1 < need_rsi ? (size_t)(rsi_offsets[r1] / 8) + 256 : in_bytes;
         if (upto > in_bytes || i + 1 == npieces) upto = in_bytes;
@@ -768,15 +778,39 @@ static int decode_host_pipelined(aecb200_ctx *ctx, const aecb200_params *p, cons
         }
         CK(cudaEventRecord(ctx->ev[i], ctx->s_in), "cudaEventRecord");
     }
+    /* The warp-per-RSI decoder wants the group index of its RSIs.  Building it (one lane skims one
+     * RSI) is latency bound and takes about as long for one piece as for the whole stream, so the
+     * builds run ahead of the decoder on side streams of their own, several at a time. */
+    const bool fast = aec_decode_warp_warps(c) != 0 && !ctx->careful_only;
+    if (fast) {
+        CK(ctx->grp.ensure(need_rsi * 32 * 8), "cudaMalloc(group index)");
+        for (size_t i = 0; i < npieces; i++) {
+            const uint64_t r0 = first[i], r1 = first[i + 1] < need_rsi ? first[i + 1] : need_rsi;
+            cudaStream_t si = ctx->s_idx[i & 3];
+            AecDecArgs a;
+            memset(&a, 0, sizeof a);
+            a.cfg = c;
+            a.in_words = (const uint32_t *)ctx->in_stage.p;
+            a.in_bytes = in_bytes;
+            a.rsi_offsets = (const uint64_t *)ctx->offs.p + r0;
+            a.nrsi = r1 - r0;
+            a.grp_G = aec_decode_group_blocks(c);
+            CK(cudaStreamWaitEvent(si, ctx->ev[i], 0), "cudaStreamWaitEvent");
+            CK(aec_build_group_index_launch(a, (uint64_t *)ctx->grp.p + r0 * 32, si), "group index launch");
+            ctx->launches += 1;
+            CK(cudaEventRecord(ctx->ev[npieces + i], si), "cudaEventRecord");
+        }
+    }
     size_t total = 0;
     for (size_t i = 0; i < npieces; i++) {
-        const uint64_t r0 = i * per, r1 = (i + 1) * per < need_rsi ? (i + 1) * per : need_rsi;
+        const uint64_t r0 = first[i], r1 = first[i + 1] < need_rsi ? first[i + 1] : need_rsi;
         const size_t o = (size_t)r0 * rsi_bytes;
         size_t nb = (size_t)(r1 - r0) * rsi_bytes;
         if (o + nb > (size_t)(out_samples * c.B)) nb = (size_t)(out_samples * c.B) - o;
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[i], 0), "cudaStreamWaitEvent");
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[fast ? npieces + i : i], 0), "cudaStreamWaitEvent");
         size_t got = 0;
-        rc = aecb200_decode_device(ctx, p, ctx->in_stage.p, in_bytes, (const uint64_t *)ctx->offs.p + r0, (size_t)(r1 - r0),
+        rc = aecb200_decode_device_indexed(ctx, p, ctx->in_stage.p, in_bytes, (const uint64_t *)ctx->offs.p + r0, (size_t)(r1 - r0),
+                                   fast ? (const uint64_t *)ctx->grp.p + r0 * 32 : nullptr,
                                    (uint8_t *)ctx->out_stage.p + o, nb);
         if (rc == AEC_OK) rc = aecb200_decode_finish(ctx, &got);
         if (rc != AEC_OK || got != nb) {
