@@ -320,6 +320,10 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
     __shared__ uint32_t s_side[TB];          /* one word per thread: the first completed word of its CDS (BitPack) */
     __shared__ uint32_t s_tend[2], s_ta[2], s_trest[2];   /* position map of the packed tile, per staging area */
     __shared__ unsigned long long s_base;    /* absolute bit offset of the tile being streamed out */
+    /* copy-out plan of that tile, worked out once by thread 0: first output word; then sh, nsl, i_lo, i_al,
+     * nvec, i_hi, nwhole, flags (1 head word shared, 2 tail word shared, 4 tile not empty) */
+    __shared__ unsigned long long s_cp_w0;
+    __shared__ uint32_t s_cp[8];
     __shared__ unsigned long long s_base_cur;/* late mode: absolute bit offset of the tile being packed */
 
     if (blockIdx.x == 0) {                  /* CTA 0 is the scanner */
@@ -595,7 +599,35 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                 uint32_t spins = 0;
                 if (!have) pv0 = ld_volatile_u64(&a.pref[s_ticket[gp]]);
                 while ((pv0 & 3) == 0) { pv0 = ld_volatile_u64(&a.pref[s_ticket[gp]]); spin_guard(spins); }
-                s_base = pv0 >> 12;
+                const uint64_t base = pv0 >> 12;
+                s_base = base;
+                /* output word w0+i = staging bits [32 i - sh, 32 i - sh + 32); words [i_lo, i_hi) belong to this
+                 * tile alone, the partial ones at either end go to the side arrays for the fix-up kernel */
+                PosFn pt; pt.has_end = s_tend[slot ^ 1u]; pt.a = s_ta[slot ^ 1u]; pt.rest = s_trest[slot ^ 1u];
+                const uint64_t end = aec_papply(pt, late ? base : 0ull) + (late ? 0ull : base);
+                const uint64_t w0 = base >> 5, we = end >> 5;
+                const bool head_partial = (base & 31u) != 0;
+                const bool tail_partial = (end & 31u) != 0 && (we > w0 || !head_partial);
+                const uint32_t nwhole = (uint32_t)(we - w0);
+                uint32_t i_hi = nwhole;
+                const uint64_t capw = a.out_cap_words > w0 ? a.out_cap_words - w0 : 0ull;
+                if ((uint64_t)i_hi > capw) i_hi = (uint32_t)capw;
+                /* 16-byte stores between the first and the last 16-byte boundary of the destination,
+                 * single words (at most six) for the rest */
+                const uint32_t i_lo = head_partial ? 1u : 0u;
+                const uint32_t mis = ((uint32_t)(uintptr_t)(a.out_words + w0) >> 2) & 3u;
+                uint32_t i_al = i_lo + ((0u - (mis + i_lo)) & 3u);
+                if (i_al > i_hi) i_al = i_hi;
+                if (i_hi < i_lo) i_al = i_lo;
+                s_cp_w0 = w0;
+                s_cp[0] = late ? 0u : (uint32_t)(base & 31u);             /* staging is at phase 0 unless late */
+                s_cp[1] = ((late ? (uint32_t)(base & 31u) : 0u) + (uint32_t)(end - base) + 31u) >> 5;
+                s_cp[2] = i_lo;
+                s_cp[3] = i_al;
+                s_cp[4] = i_hi > i_al ? (i_hi - i_al) >> 2 : 0u;
+                s_cp[5] = i_hi;
+                s_cp[6] = nwhole;
+                s_cp[7] = (head_partial ? 1u : 0u) | (tail_partial ? 2u : 0u) | (end > base ? 4u : 0u);
             }
             /* with a tile to stream out, the next tile is claimed after that (below): the later the
              * claim, the sooner after it the tile's aggregate is published, and every later tile's prefix
@@ -631,31 +663,9 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                     }
                 }
             }
-            PosFn prev_ptile; prev_ptile.has_end = s_tend[slot ^ 1u]; prev_ptile.a = s_ta[slot ^ 1u]; prev_ptile.rest = s_trest[slot ^ 1u];
-            const uint64_t end = aec_papply(prev_ptile, late ? base : 0ull) + (late ? 0ull : base);
-            const uint64_t w0 = base >> 5, we = end >> 5;
-            const uint32_t sh = late ? 0u : (uint32_t)(base & 31u);      /* staging is at phase 0 unless late */
-            const uint32_t nsl = ((late ? (uint32_t)(base & 31u) : 0u) + (uint32_t)(end - base) + 31u) >> 5;
-            const bool head_partial = (base & 31u) != 0;
-            const bool tail_partial = (end & 31u) != 0 && (we > w0 || !head_partial);
-            /* output word w0+i = staging bits [32 i - sh, 32 i - sh + 32); words [i_lo, i_hi) belong to this
-             * tile alone, the partial ones at either end go to the side arrays for the fix-up kernel */
-            const uint32_t nwhole = (uint32_t)(we - w0);
-            uint32_t i_hi = nwhole;
+            const uint32_t sh = s_cp[0], nsl = s_cp[1], i_lo = s_cp[2], i_al = s_cp[3], nvec = s_cp[4], i_hi = s_cp[5];
+            uint32_t *dst = a.out_words + s_cp_w0;
             {
-                const uint64_t capw = a.out_cap_words > w0 ? a.out_cap_words - w0 : 0ull;
-                if ((uint64_t)i_hi > capw) i_hi = (uint32_t)capw;
-            }
-            uint32_t *dst = a.out_words + w0;
-            {
-                /* words [i_lo, i_hi): 16-byte stores for the part between the first and the last 16-byte
-                 * boundary of the destination, single words (at most six, threads 0..5) for the rest */
-                const uint32_t i_lo = head_partial ? 1u : 0u;
-                const uint32_t mis = ((uint32_t)(uintptr_t)dst >> 2) & 3u;
-                uint32_t i_al = i_lo + ((0u - (mis + i_lo)) & 3u);
-                if (i_al > i_hi) i_al = i_hi;
-                if (i_hi < i_lo) i_al = i_lo;
-                const uint32_t nvec = i_hi > i_al ? (i_hi - i_al) >> 2 : 0u;
                 const uint32_t i_tl = i_al + 4u * nvec;
 #pragma unroll 1
                 for (uint32_t q = tid; q < nvec; q += TB) {
@@ -671,15 +681,17 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                 }
                 const uint32_t nh = i_al - i_lo;
                 const uint32_t i = tid < nh ? i_lo + tid : i_tl + (tid - nh);
-                if (i < i_hi && (tid < nh || i >= i_tl)) {
+                if (i < i_hi) {
                     const uint32_t v = __funnelshift_r(pstage[i], pstage[(int)i - 1], sh);
                     dst[i] = __byte_perm(v, 0, 0x0123);
                 }
             }
             if (tid == 0)
-                a.head_c[prev_tile] = (head_partial && end > base) ? (pstage[0] >> sh) : 0u;
-            if (tid == 32)
-                a.tail_c[prev_tile] = tail_partial ? __funnelshift_r(pstage[nwhole], pstage[(int)nwhole - 1], sh) : 0u;
+                a.head_c[prev_tile] = ((s_cp[7] & 5u) == 5u) ? (pstage[0] >> sh) : 0u;
+            if (tid == 32) {
+                const uint32_t nwhole = s_cp[6];
+                a.tail_c[prev_tile] = (s_cp[7] & 2u) ? __funnelshift_r(pstage[nwhole], pstage[(int)nwhole - 1], sh) : 0u;
+            }
             if (tid == 0 && have) nxt = atomicAdd(a.ticket, 1u);       /* the answer travels while the area is cleared */
             __syncthreads();                                           /* S4: everyone has read the words */
             {
