@@ -350,6 +350,11 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
     __syncthreads();
 
     bool prev_have = false;                 /* the previous tile is packed and waits to be streamed out */
+    /* my block of that tile and of the current one: kept in registers where there is room (short blocks),
+     * worked out again from the tile's place otherwise */
+    constexpr bool CARRY = (JT == 8 || JT == 16);
+    uint64_t prev_rsi = 0, cur_rsi = 0;
+    uint32_t prev_b = 0, cur_b = 0;
     uint32_t g = 0;                         /* ring entry of the current tile */
 
     for (uint32_t it = 0;; it++) {
@@ -365,6 +370,7 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
             /* ---- which block is mine ---- */
             uint64_t rsi_idx; uint32_t b;
             my_block(g, rsi_idx, b);
+            if (CARRY) { cur_rsi = rsi_idx; cur_b = b; }
             uint32_t nblk = 0;
             if (rsi_idx + 1 < a.nrsi) nblk = c.rsi;
             else if (rsi_idx + 1 == a.nrsi) nblk = a.last_nblk;
@@ -645,8 +651,8 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
             const uint32_t prev_tile = s_ticket[gp];
             const uint2 pe = want_index ? pend_all[(slot ^ 1u) * TB + tid] : make_uint2(0u, 0u);
             if (pe.y & (1u << 20)) {
-                uint64_t p_rsi; uint32_t p_b;
-                my_block(gp, p_rsi, p_b);
+                uint64_t p_rsi = prev_rsi; uint32_t p_b = prev_b;
+                if (!CARRY) my_block(gp, p_rsi, p_b);
                 const uint32_t p_len = pe.y & 0xFFFu, p_zrun = (pe.y >> 12) & 0xFFu;
                 const uint64_t myabs = (late ? ((base >> 5) << 5) : base) + pe.x;
                 if (p_b == 0 && a.rsi_offsets) a.rsi_offsets[p_rsi] = myabs;
@@ -707,6 +713,7 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
         }
         if (!have) break;
         prev_have = true;
+        if (CARRY) { prev_rsi = cur_rsi; prev_b = cur_b; }
         g = gn;
     }
 }

@@ -128,6 +128,12 @@ class ShardedCodec:
         self._mine = torch.zeros(4, dtype=torch.int64, device="cuda")
         self._all = torch.zeros(4 * world, dtype=torch.int64, device="cuda")
         self._mine_h = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self._all_h = torch.zeros(4 * world, dtype=torch.int64).pin_memory()
+        # the exchange runs on a stream of its own, next to whatever the caller enqueues on the
+        # codec's stream after encode_local (the decode of the local shard needs no exchange)
+        self._xstream = torch.cuda.Stream()
+        self._xdone = torch.cuda.Event()
+        self._xpending = False
 
     def close(self):
         self.codec.close()
@@ -157,22 +163,38 @@ class ShardedCodec:
         self._info = self.codec.shard_info()
         return bits
 
-    def stitch(self):
-        """Steps 2-4: the 32-byte exchange, k repair, placement at the global bit phase.
-        Independent of decoding the local shard, so callers may enqueue that first."""
+    def exchange_begin(self):
+        """Step 2, first half: start the only exchange (32 bytes per rank) on the side stream.  The
+        host does not wait here; work enqueued on the codec's stream meanwhile overlaps it."""
         import torch.distributed as dist
+        if self.world <= 1:
+            return
+        torch = self.torch
+        klo, khi, first_const, tail64 = self._info
+        h = self._mine_h
+        h[0], h[1], h[2] = self.bits, klo, khi
+        h[3] = tail64 - (1 << 64) if tail64 >= (1 << 63) else tail64
+        with torch.cuda.stream(self._xstream):
+            self._mine.copy_(h, non_blocking=True)
+            dist.all_gather_into_tensor(self._all, self._mine, group=self.group)
+            self._all_h.copy_(self._all, non_blocking=True)
+            self._xdone.record(self._xstream)
+        self._xpending = True
+
+    def stitch(self):
+        """Steps 2-4: the 32-byte exchange (finished here), k repair, placement at the global bit
+        phase.  Independent of decoding the local shard: callers call exchange_begin, enqueue the
+        decode, then stitch, so that the exchange and the host's part of it hide behind the decode."""
         from .api import Carry
         p = self.p
         bits = self.bits
         klo, khi, first_const, tail64 = self._info
-        # 2. the only exchange: 32 bytes per rank
         if self.world > 1:
-            h = self._mine_h
-            h[0], h[1], h[2] = bits, klo, khi
-            h[3] = tail64 - (1 << 64) if tail64 >= (1 << 63) else tail64
-            self._mine.copy_(h, non_blocking=True)
-            dist.all_gather_into_tensor(self._all, self._mine, group=self.group)
-            allv = self._all.cpu().view(self.world, 4).tolist()
+            if not self._xpending:
+                self.exchange_begin()
+            self._xdone.synchronize()                  # the side stream only, not the codec's stream
+            self._xpending = False
+            allv = self._all_h.view(self.world, 4).tolist()
             infos = [(v[0], v[1], v[2], v[3] & 0xFFFFFFFFFFFFFFFF) for v in allv]
         else:
             infos = [(bits, klo, khi, tail64)]
