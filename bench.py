@@ -263,9 +263,9 @@ def run_ours(args):
         a.record()
         if sharded is not None:
             sharded.encode_local(d_raw, raw.size)       # independent shard encode
-            sharded.exchange_begin()                    # 32-byte all_gather on a side stream
             b.record()
             sharded.decode_enqueue(d_back, raw.size)    # decode needs no exchange
+            sharded.exchange_begin()                    # 32-byte all_gather on a side stream, next to the decode
             sharded.stitch()                            # gathered offsets -> k repair, placement
         else:
             codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs, d_grp=d_grp)
