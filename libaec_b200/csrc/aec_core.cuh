@@ -207,8 +207,10 @@ AEC_HD uint32_t aec_sum_shift(const uint32_t *d, uint32_t J, uint32_t k)
  * logic); then klo/khi are the identity.
  */
 /*   small   the caller knows every d[i] < 2^24 (then the 32-bit sum stands in for the OR of the values) */
+/*   lut     device only, may be null: 256 words in shared memory, nibble j of lut[v] = bit j of v */
 template <int JT>
-AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t ref, bool small = false)
+AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t ref, bool small = false,
+                                   const uint32_t *lut = nullptr)
 {
     const uint32_t J = JT ? (uint32_t)JT : c.J;
     BlockInfo bi;
@@ -271,11 +273,37 @@ AEC_HD BlockInfo aec_analyze_block(const AecCfg &c, const uint32_t *d, uint32_t 
          * when kb = kg-2, and d >> (kmax-2) <= 31 when the guess was clamped */
         uint32_t S1 = 0, S2 = 0, S3 = 0, S4 = 0, S5 = 0;
 #if defined(__CUDA_ARCH__)
+        if ((JT == 8 || JT == 16) && lut != nullptr && (orv >> 25) == 0 && (s32 >> kb) <= 255u) {
+            /* Every d >> kb fits a byte (their sum does).  Count, per bit position j, the samples whose
+             * shifted value has bit j set: C_j, one nibble each, accumulated from a table look-up per
+             * sample (eight samples per accumulator, so a nibble holds its count).  Then
+             * S(kb + m) = sum_{j >= m} 2^(j-m) C_j: ten byte dot products.  One shift per sample on the
+             * ALU pipe, which bounds the kernel, instead of five shifts and five adds. */
+            const uint32_t lb = (uint32_t)__cvta_generic_to_shared(lut);
+            uint32_t acc[JT == 16 ? 2 : 1] = {0u};
+#pragma unroll
+            for (uint32_t i = 0; i < J; i++) {
+                uint32_t w;
+                asm("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"((d[i] >> kb) * 4u + lb));
+                acc[i >> 3] += w;
+            }
+            uint32_t E = acc[0] & 0x0F0F0F0Fu, O = (acc[0] >> 4) & 0x0F0F0F0Fu;     /* bytes C0 C2 C4 C6 / C1 C3 C5 C7 */
+            if (JT == 16) { E += acc[JT == 16 ? 1 : 0] & 0x0F0F0F0Fu; O += (acc[JT == 16 ? 1 : 0] >> 4) & 0x0F0F0F0Fu; }
+            S1 = __dp4a(E, 0x40100401u, __dp4a(O, 0x80200802u, 0u));
+            S2 = __dp4a(E, 0x20080200u, __dp4a(O, 0x40100401u, 0u));
+            S3 = __dp4a(E, 0x10040100u, __dp4a(O, 0x20080200u, 0u));
+            S4 = __dp4a(E, 0x08020000u, __dp4a(O, 0x10040100u, 0u));
+            S5 = __dp4a(E, 0x04010000u, __dp4a(O, 0x08020000u, 0u));
+        } else
+#endif
+        {
+#if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (uint32_t i = 0; i < J; i++) {
-            uint32_t v = d[i] >> kb;
-            S1 += v; S2 += v >> 1; S3 += v >> 2; S4 += v >> 3; S5 += v >> 4;
+            for (uint32_t i = 0; i < J; i++) {
+                uint32_t v = d[i] >> kb;
+                S1 += v; S2 += v >> 1; S3 += v >> 2; S4 += v >> 3; S5 += v >> 4;
+            }
         }
         const uint32_t T0 = S1 - S2, T1 = S2 - S3, T2 = S3 - S4, T3 = S4 - S5;
         uint32_t lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu, slo = 0;

@@ -346,6 +346,14 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
         else { rsi_idx += tid >> a.rp_shift; b = tid & (a.RP - 1u); }
     };
     for (uint32_t i = tid; i < 2u * SW; i += TB) staging_all[i] = 0;
+    /* bit-spreading table of the k-window sums (aec_analyze_block): nibble j of entry v = bit j of v */
+    __shared__ uint32_t s_lut[256];
+    for (uint32_t v = tid; v < 256u; v += TB) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) w |= ((v >> j) & 1u) << (4 * j);
+        s_lut[v] = w;
+    }
     if (tid == 0) place(0, atomicAdd(a.ticket, 1u));
     __syncthreads();
 
@@ -441,7 +449,7 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                     }
                     if (b == 0) d[0] = 0;
                 }
-                if (valid) bi = aec_analyze_block<JT>(c, d, ref, small);
+                if (valid) bi = aec_analyze_block<JT>(c, d, ref, small, s_lut);
             }
             const bool is_zero = valid && bi.opt == OPT_ZERO;
 
