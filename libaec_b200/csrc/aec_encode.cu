@@ -643,11 +643,11 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                 s_cp[6] = nwhole;
                 s_cp[7] = (head_partial ? 1u : 0u) | (tail_partial ? 2u : 0u) | (end > base ? 4u : 0u);
             }
-            /* with a tile to stream out, the next tile is claimed after that (below): the later the
-             * claim, the sooner after it the tile's aggregate is published, and every later tile's prefix
-             * waits for that aggregate (profiles/r1_e: the time from claim to publication plus the scanner's
-             * latency had grown as long as a whole tile time, so every tile waited at S3) */
-            if (have && !prev_have) nxt = atomicAdd(a.ticket, 1u);
+            /* claim the next tile now that the previous tile's prefix is here; the ticket's round trip
+             * overlaps the copy-out.  (Claiming after the copy-out instead was tried: it needs one more
+             * barrier per tile and the prefix is hardly ever late -- 766 polls for 16384 tiles,
+             * profiles/r1_f_summary.md.) */
+            if (have) nxt = atomicAdd(a.ticket, 1u);
             if (!prev_have || !have) { if (have) place(gn, nxt); else s_ticket[gn] = 0xFFFFFFFFu; }
         }
         __syncthreads();                                               /* S3 */
@@ -706,17 +706,13 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
                 const uint32_t nwhole = s_cp[6];
                 a.tail_c[prev_tile] = (s_cp[7] & 2u) ? __funnelshift_r(pstage[nwhole], pstage[(int)nwhole - 1], sh) : 0u;
             }
-            if (tid == 0 && have) nxt = atomicAdd(a.ticket, 1u);       /* the answer travels while the area is cleared */
+            if (tid == 0 && have) place(gn, nxt);                      /* the ticket claimed before S3 has arrived by now */
             __syncthreads();                                           /* S4: everyone has read the words */
             {
                 uint4 *z = reinterpret_cast<uint4 *>(staging_all + (slot ^ 1u) * SW);
                 const uint32_t n4 = (nsl + 5u) >> 2;                   /* pad word + nsl words + one spare */
 #pragma unroll 1
                 for (uint32_t i = tid; i < n4; i += TB) z[i] = make_uint4(0u, 0u, 0u, 0u);
-            }
-            if (have) {
-                if (tid == 0) place(gn, nxt);
-                __syncthreads();                                       /* S5: the next tile's place is known */
             }
         }
         if (!have) break;
