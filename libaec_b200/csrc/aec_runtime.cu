@@ -153,6 +153,15 @@ int pipe_abort(aecb200_ctx *ctx, int rc)
     return rc;
 }
 
+/* Leaves no copy or kernel of a pipeline in flight when a host call returns early (CUDA failure, bad
+ * piece): the caller's buffers must not be touched after the call has returned. */
+struct PipeGuard {
+    aecb200_ctx *ctx;
+    bool armed;
+    explicit PipeGuard(aecb200_ctx *c) : ctx(c), armed(true) {}
+    ~PipeGuard() { if (armed) pipe_abort(ctx, 0); }
+};
+
 } // namespace
 
 extern "C" {
@@ -544,6 +553,7 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
         } else {
             rc = pipe_prepare(ctx, npieces);
             if (rc != AEC_OK) return rc;
+            PipeGuard guard(ctx);
             for (size_t i = 0; i < npieces; i++) {       /* all uploads are queued now and run back to back */
                 const size_t o = i * piece, nb = (o + piece <= use_bytes) ? piece : use_bytes - o;
                 CK(cudaMemcpyAsync((uint8_t *)ctx->in_stage.p + o, (const uint8_t *)in + o, nb, cudaMemcpyHostToDevice, ctx->s_in), "H2D");
@@ -557,7 +567,7 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
                                            d_offs ? d_offs + (o / rsi_bytes) : nullptr);
                 aecb200_carry e = {0, 0, 0};
                 if (rc == AEC_OK) rc = aecb200_encode_finish(ctx, &e);
-                if (rc != AEC_OK) return pipe_abort(ctx, rc);
+                if (rc != AEC_OK) return rc;
                 end_bits = e.bits; end_k = e.k;
                 seed.bits = e.bits; seed.k = e.k; seed.word = 0;
                 if (i + 1 < npieces) {
@@ -581,6 +591,7 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
                     }
                 }
             }
+            guard.armed = false;                         /* s_in is drained, s_out is waited for below */
         }
         if (d_offs) {
             size_t ncopy = nrsi < offsets_cap ? (size_t)nrsi : offsets_cap;
@@ -759,6 +770,7 @@ static int decode_host_pipelined(aecb200_ctx *ctx, const aecb200_params *p, cons
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     int rc = pipe_prepare(ctx, 2 * npieces);
     if (rc != AEC_OK) return rc;
+    PipeGuard guard(ctx);
     const size_t in_pad = (in_bytes + 3) & ~(size_t)3;
     CK(ctx->in_stage.ensure(in_pad + 16), "cudaMalloc(in)");
     CK(ctx->out_stage.ensure((size_t)(out_samples * c.B) + 16), "cudaMalloc(out)");
@@ -813,14 +825,13 @@ static int decode_host_pipelined(aecb200_ctx *ctx, const aecb200_params *p, cons
                                    fast ? (const uint64_t *)ctx->grp.p + r0 * 32 : nullptr,
                                    (uint8_t *)ctx->out_stage.p + o, nb);
         if (rc == AEC_OK) rc = aecb200_decode_finish(ctx, &got);
-        if (rc != AEC_OK || got != nb) {
-            pipe_abort(ctx, rc);
+        if (rc != AEC_OK || got != nb)
             return (rc == AEC_OK || rc == AEC_DATA_ERROR) ? AECB200_NOT_PIPELINED : rc;
-        }
         CK(cudaMemcpyAsync((uint8_t *)out + o, (uint8_t *)ctx->out_stage.p + o, nb, cudaMemcpyDeviceToHost, ctx->s_out), "D2H");
         total += nb;
     }
     CK(cudaStreamSynchronize(ctx->s_out), "sync(out)");
+    guard.armed = false;
     if (out_len) *out_len = total;
     return AEC_OK;
 }
