@@ -55,6 +55,10 @@ typedef struct {
 } aecb200_carry;
 
 int  aecb200_device_count(void);
+/* The calling thread's current CUDA device (-1: none usable) and the device a context is bound to.
+ * Every aecb200_* call runs on its context's device and restores the caller's current device. */
+int  aecb200_current_device(void);
+int  aecb200_ctx_device(aecb200_ctx *ctx);
 /* device < 0: current device.  One context = one CUDA stream + workspace;
  * use one context per thread. */
 int  aecb200_ctx_create(aecb200_ctx **ctx, int device);
@@ -147,11 +151,20 @@ uint64_t aecb200_ctx_last_handover(aecb200_ctx *ctx);
 /* Wait for the last enqueued decode; *out_written = bytes of samples delivered. */
 int aecb200_decode_finish(aecb200_ctx *ctx, size_t *out_written);
 
-/* Sequentially discover the RSI start offsets of a stream without an index.
+/* Discover the RSI start offsets of a stream without an index (the only kind of stream a caller of
+ * libaec.h 0.3.4 can hand over; the reference finds them by decoding sequentially, decode.c:402-421).
+ * Streams of at least 2 KiB are skimmed in parallel: per-bit-position CDS tables, pointer doubling,
+ * one table look-up per RSI (aec_skim.cu); shorter ones by a single thread.
  * d_rsi_offsets must hold max_rsi entries.  Synchronous. */
 int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
                                 const void *d_in, size_t in_bytes, uint64_t start_bit,
                                 uint64_t *d_rsi_offsets, size_t max_rsi, size_t *found);
+
+/* mode 0: choose by stream size, 1: always the one-thread scan, 2: always the parallel tables;
+ * window_bits (0 = keep): stream bits whose tables are held at a time (default 2^25). */
+void aecb200_ctx_set_scan_mode(aecb200_ctx *ctx, int mode, uint64_t window_bits);
+/* RSIs of the last scan whose length came from the tables (the rest were skimmed serially). */
+uint64_t aecb200_ctx_last_scan_fast(aecb200_ctx *ctx);
 
 /* ---- host buffers (what the libaec.h entry points call) ------------------ */
 

@@ -86,7 +86,7 @@ LIBAEC_SYMBOLS = ["aec_encode_init", "aec_encode", "aec_encode_end", "aec_decode
                   "aec_decode_end", "aec_buffer_encode", "aec_buffer_decode",
                   "aec_encode_enable_offsets", "aec_encode_count_offsets", "aec_encode_get_offsets",
                   "aec_decode_set_offsets"]
-DEVICE_SYMBOLS = ["aecb200_device_count", "aecb200_ctx_create", "aecb200_ctx_destroy",
+DEVICE_SYMBOLS = ["aecb200_device_count", "aecb200_current_device", "aecb200_ctx_device", "aecb200_ctx_create", "aecb200_ctx_destroy",
                   "aecb200_ctx_set_stream", "aecb200_last_error", "aecb200_ctx_set_encode_padding",
                   "aecb200_ctx_launches", "aecb200_encode_bound", "aecb200_encode_device",
                   "aecb200_encode_finish", "aecb200_decode_device", "aecb200_decode_finish",
@@ -95,7 +95,7 @@ DEVICE_SYMBOLS = ["aecb200_device_count", "aecb200_ctx_create", "aecb200_ctx_des
                   "aecb200_encode_shard_info", "aecb200_ctx_set_tile_limit", "aecb200_place_bits_device",
                   "aecb200_encode_device_indexed", "aecb200_decode_device_indexed", "aecb200_group_index_entries",
                   "aecb200_ctx_set_careful_decode", "aecb200_ctx_last_handover",
-                  "aecb200_ctx_set_pipeline_piece"]
+                  "aecb200_ctx_set_pipeline_piece", "aecb200_ctx_set_scan_mode", "aecb200_ctx_last_scan_fast"]
 SZ_SYMBOLS = ["SZ_BufftoBuffCompress", "SZ_BufftoBuffDecompress", "SZ_encoder_enabled", "SZ_Compress"]
 
 
@@ -120,6 +120,8 @@ def load_library() -> C.CDLL:
         lib.aecb200_ctx_last_handover.restype = C.c_uint64
         lib.aecb200_ctx_set_tile_limit.restype = None
         lib.aecb200_ctx_set_pipeline_piece.restype = None
+        lib.aecb200_ctx_set_scan_mode.restype = None
+        lib.aecb200_ctx_last_scan_fast.restype = C.c_uint64
         _lib = lib
     return _lib
 
@@ -378,6 +380,14 @@ class DeviceCodec:
 
     def set_careful_decode(self, on: bool = True):
         self.lib.aecb200_ctx_set_careful_decode(self.ctx, C.c_int(int(on)))
+
+    def set_scan_mode(self, mode: int, window_bits: int = 0):
+        """RSI boundary discovery: 0 auto, 1 one-thread scan, 2 parallel tables; window in stream bits."""
+        self.lib.aecb200_ctx_set_scan_mode(self.ctx, C.c_int(mode), C.c_uint64(window_bits))
+
+    @property
+    def last_scan_fast(self) -> int:
+        return int(self.lib.aecb200_ctx_last_scan_fast(self.ctx))
 
     def set_pipeline_piece(self, raw_bytes: int):
         """Piece size of the host-pointer pipeline (0 = one piece)."""

@@ -27,8 +27,8 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVFLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--use_fast_math"]
 
-CU_SOURCES = ["aec_encode.cu", "aec_decode.cu", "aec_runtime.cu"]
-HEADERS = ["aec_core.cuh", "aec_decode_core.cuh", "aec_device.h",
+CU_SOURCES = ["aec_encode.cu", "aec_decode.cu", "aec_skim.cu", "aec_runtime.cu"]
+HEADERS = ["aec_core.cuh", "aec_decode_core.cuh", "aec_skim_core.cuh", "aec_device.h",
            os.path.join(ROOT, "include", "aec_b200.h"), os.path.join(ROOT, "include", "libaec.h"),
            os.path.join(ROOT, "include", "szlib.h")]
 

@@ -715,11 +715,10 @@ cudaError_t launch_dec(const AecDecArgs &a, cudaStream_t st)
     auto kern = aec_decode_kernel<JT, B>;
     uint32_t J = JT ? (uint32_t)JT : a.cfg.J;
     uint32_t smem = DEC_WARPS * 32u * (J + 1u) * 4u;
-    static uint32_t attr = 48 * 1024;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static AecSmemOptIn optin;
+    {
+        cudaError_t e = optin.ensure(kern, smem, 48 * 1024);
         if (e != cudaSuccess) return e;
-        attr = smem;
     }
     uint64_t nwarps = (a.nrsi + 31) / 32;
     uint64_t grid = (nwarps + DEC_WARPS - 1) / DEC_WARPS;
@@ -764,11 +763,10 @@ cudaError_t launch_decw(const AecDecArgs &a, cudaStream_t st)
     uint32_t J = JT ? (uint32_t)JT : a.cfg.J;
     uint32_t stride = (a.grp_G * J) | 1u;
     uint32_t smem = warps * 32u * stride * 4u;
-    static uint32_t attr = 48 * 1024;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static AecSmemOptIn optin;
+    {
+        cudaError_t e = optin.ensure(kern, smem, 48 * 1024);
         if (e != cudaSuccess) return e;
-        attr = smem;
     }
     uint64_t grid = (a.nrsi + warps - 1) / warps;
     if (grid == 0) return cudaSuccess;

@@ -8,7 +8,35 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "aec_core.cuh"
+
+/* Opt-in to more than the default dynamic shared memory of a kernel.  cudaFuncSetAttribute applies
+ * to the current device only, so the size already granted is remembered per device (one instance of
+ * this struct per kernel instantiation); raising it is serialised by a process-wide mutex because
+ * contexts of several host threads share the kernels. */
+struct AecSmemOptIn {
+    static constexpr int MAXDEV = 64;
+    std::atomic<uint32_t> have[MAXDEV];            /* zero-initialised (static storage): nothing granted yet */
+    template <class K>
+    cudaError_t ensure(K kern, uint32_t bytes, uint32_t dflt)
+    {
+        if (bytes <= dflt) return cudaSuccess;
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const bool tracked = dev >= 0 && dev < MAXDEV;
+        if (tracked && bytes <= have[dev].load(std::memory_order_acquire)) return cudaSuccess;
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lock(mu);
+        if (tracked && bytes <= have[dev].load(std::memory_order_relaxed)) return cudaSuccess;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess && tracked) have[dev].store(bytes, std::memory_order_release);
+        return e;
+    }
+};
 
 /* Arguments of one encode launch (passed by value). */
 struct AecEncArgs {
@@ -68,6 +96,28 @@ struct AecDecArgs {
     uint32_t *rsi_list;         /* [nrsi] */
     uint32_t *rsi_list_count;
 };
+
+/* Arguments of the parallel RSI-boundary discovery over one window of the stream (aec_skim.cu). */
+struct AecSkimArgs {
+    AecCfg cfg;                 /* cfg.pad: RSIs start on byte boundaries (the decoder always honours AEC_PAD_RSI) */
+    const uint32_t *in_words;   /* compressed stream, 4-byte aligned, device */
+    uint64_t nbits;             /* stream bits (in_bytes * 8) */
+    uint64_t wb;                /* first bit of the window (multiple of 32) */
+    uint32_t np;                /* bit positions of the window that get table entries */
+    uint32_t nh_eff;            /* RSIs that start before wb + nh_eff are walked in this window */
+    uint32_t last;              /* last window of the stream */
+    uint32_t LV;                /* levels of the CDS chain tables (level j = 2^j CDSs) */
+    uint32_t la_words;          /* filled by the launcher: words staged beyond a tile */
+    uint32_t *T;                /* [LV][np] */
+    uint32_t *H;                /* [np] RSI lengths (first-CDS entries between the kernels) */
+    uint64_t *state;            /* [0] next RSI bit, [1] RSIs found, [2] flags (1 ended, 2 data error), [3] RSIs taken from the tables */
+    uint64_t *offsets;          /* [max_rsi] */
+    uint64_t max_rsi;
+};
+uint32_t aec_skim_levels(const AecCfg &c);
+uint64_t aec_skim_margin_bits(const AecCfg &c);
+/* level-0 tables, doubling, RSI lengths and the walk of one window */
+cudaError_t aec_skim_window_launch(const AecSkimArgs &a, cudaStream_t st);
 
 uint32_t aec_encode_tile_blocks(uint32_t J);
 uint32_t aec_encode_staging_words(const AecCfg &c);

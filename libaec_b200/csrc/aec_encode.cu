@@ -155,12 +155,19 @@ __device__ __forceinline__ void load_block(const AecCfg &c, const uint8_t *in, u
     }
 }
 
-/* A spin that has not been answered after this many polls means a broken protocol: abort the
- * launch (the host sees a launch failure) instead of hanging the device. */
-constexpr uint32_t SPIN_LIMIT = 1u << 26;
+/* Every spin is bounded.  The kernel is launched cooperatively, so the scanner CTA and all worker CTAs
+ * are resident together and a poll is normally answered within microseconds; a wait that is long
+ * anyway (debugger, sanitizer, a preempted context) backs off with nanosleep instead of burning issue
+ * slots, and only a wait of tens of seconds -- a broken protocol -- aborts the launch (the host sees a
+ * launch failure) instead of hanging the device. */
+constexpr uint32_t SPIN_FAST = 1u << 16;     /* polls before backing off */
+constexpr uint32_t SPIN_LIMIT = 1u << 26;    /* then this many sleeps of ~1 us */
 __device__ __forceinline__ void spin_guard(uint32_t &n)
 {
-    if (++n > SPIN_LIMIT) __trap();
+    if (++n > SPIN_FAST) {
+        __nanosleep(1000);
+        if (n > SPIN_FAST + SPIN_LIMIT) __trap();
+    }
 }
 
 /* ---- dedicated scanner ------------------------------------------------------
@@ -223,6 +230,7 @@ __device__ __noinline__ void aec_encode_scanner(const AecEncArgs &a, uint64_t *s
             uint32_t spins = 0;
             while (*s_done != (uint32_t)b) spin_guard(spins);
         }
+        __syncwarp();                 /* the lanes leave the spin together before the carry slot is read */
         const uint64_t P = *reinterpret_cast<volatile uint64_t *>(&s_carry_pos[b & 1]);
         const uint32_t kc = *reinterpret_cast<volatile uint32_t *>(&s_carry_k[b & 1]);
         const uint64_t pos = aec_papply(fe, P);
@@ -834,15 +842,11 @@ template <int JT, int B>
 cudaError_t launch_variant(const AecEncArgs &a, uint32_t smem_bytes, int num_sms, cudaStream_t st)
 {
     auto kern = aec_encode_kernel<JT, B>;
-    /* opt in to large dynamic shared memory once; the 48 KiB default limit counts the kernel's
-     * static shared variables as well, so leave room for them */
-    static uint32_t attr_smem = 40 * 1024;
-    cudaError_t e;
-    if (smem_bytes > attr_smem) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        if (e != cudaSuccess) return e;
-        attr_smem = smem_bytes;
-    }
+    /* opt in to large dynamic shared memory (per device); the 48 KiB default limit counts the
+     * kernel's static shared variables as well, so leave room for them */
+    static AecSmemOptIn optin;
+    cudaError_t e = optin.ensure(kern, smem_bytes, 40 * 1024);
+    if (e != cudaSuccess) return e;
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TileCfg<JT>::TB, smem_bytes);
     if (e != cudaSuccess) return e;
@@ -852,8 +856,11 @@ cudaError_t launch_variant(const AecEncArgs &a, uint32_t smem_bytes, int num_sms
     if (grid > a.ntiles + 1) grid = a.ntiles + 1;
     if (grid < 2) grid = 2;
     if (a.ntiles == 0) return cudaSuccess;
-    kern<<<(unsigned)grid, TileCfg<JT>::TB, smem_bytes, st>>>(a);
-    return cudaGetLastError();
+    /* cooperative launch: the runtime guarantees that the scanner and every worker are resident at
+     * the same time (or refuses the launch) whatever else shares the device */
+    void *kargs[] = {const_cast<AecEncArgs *>(&a)};
+    return cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(TileCfg<JT>::TB), kargs,
+                                       smem_bytes, st);
 }
 
 template <int JT>

@@ -75,6 +75,12 @@ struct aecb200_ctx {
     std::vector<cudaEvent_t> ev;
     size_t pipe_piece = (size_t)16 << 20; /* bytes of raw samples per piece; 0 = never pipeline */
 
+    /* RSI boundary discovery for streams without an index (aec_skim.cu) */
+    DevBuf skim_tab;
+    int scan_mode = 0;                   /* 0 auto, 1 always the one-thread scan, 2 always the parallel tables */
+    uint64_t scan_window_bits = 1ull << 25;
+    uint64_t scan_end = 0, scan_fast = 0;
+
     /* bookkeeping of the last enqueued operation */
     uint64_t enc_out_cap_bits = 0;
     bool enc_pending = false;
@@ -93,6 +99,22 @@ int fail_cuda(aecb200_ctx *c, cudaError_t e, const char *what)
     return AECB200_CUDA_ERROR;
 }
 #define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(ctx, e_, what); } while (0)
+
+/* Work runs on the context's device; the caller's current device is put back when the call returns
+ * (the reference library has no such side effect, and a multi-GPU host thread relies on it). */
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t enter(int dev)
+    {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        if (prev != dev) { e = cudaSetDevice(dev); switched = (e == cudaSuccess); }
+        return e;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define ENTER_DEVICE() DeviceGuard dg_; CK(dg_.enter(ctx->device), "cudaSetDevice")
 
 uint32_t next_pow2(uint32_t v)
 {
@@ -185,7 +207,8 @@ int aecb200_ctx_create(aecb200_ctx **out, int device)
         if (e != cudaSuccess) { delete ctx; return AECB200_CUDA_ERROR; }
     }
     ctx->device = device;
-    e = cudaSetDevice(device);
+    DeviceGuard dg;
+    e = dg.enter(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) { ctx->own_stream = true; e = cudaMallocHost(&ctx->h_res, 16 * sizeof(uint64_t)); }
@@ -196,6 +219,9 @@ int aecb200_ctx_create(aecb200_ctx **out, int device)
         delete ctx;
         return AECB200_CUDA_ERROR;
     }
+    /* test hooks: force one of the RSI boundary discovery paths / a small table window */
+    if (const char *m = getenv("AECB200_SCAN_MODE")) ctx->scan_mode = atoi(m);
+    if (const char *w = getenv("AECB200_SCAN_WINDOW_BITS")) { long long v = atoll(w); if (v > 0) ctx->scan_window_bits = (uint64_t)v; }
     *out = ctx;
     return AEC_OK;
 }
@@ -203,12 +229,13 @@ int aecb200_ctx_create(aecb200_ctx **out, int device)
 void aecb200_ctx_destroy(aecb200_ctx *ctx)
 {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard dg;
+    dg.enter(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->tile_kagg.release(); ctx->pref.release(); ctx->grp.release(); ctx->rsi_list.release();
     ctx->desc.release(); ctx->headc.release(); ctx->tailc.release(); ctx->tile_end.release();
     ctx->misc.release(); ctx->in_stage.release(); ctx->out_stage.release(); ctx->offs.release();
-    ctx->rsi_count.release();
+    ctx->rsi_count.release(); ctx->skim_tab.release();
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -218,9 +245,20 @@ void aecb200_ctx_destroy(aecb200_ctx *ctx)
     delete ctx;
 }
 
+int aecb200_current_device(void)
+{
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) return -1;
+    return d;
+}
+
+int aecb200_ctx_device(aecb200_ctx *ctx) { return ctx ? ctx->device : -1; }
+
 int aecb200_ctx_set_stream(aecb200_ctx *ctx, void *cuda_stream)
 {
     if (!ctx) return AEC_CONF_ERROR;
+    DeviceGuard dg;
+    dg.enter(ctx->device);
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
     ctx->stream = (cudaStream_t)cuda_stream;
     return AEC_OK;
@@ -276,7 +314,7 @@ int aecb200_encode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
         snprintf(ctx->err, sizeof ctx->err, "device output must be 4-byte aligned");
         return AEC_CONF_ERROR;
     }
-    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ENTER_DEVICE();
     EncGeom g = enc_geometry(c, in_bytes);
     aecb200_carry zero = {0, 0, 0};
     if (!carry) carry = &zero;
@@ -375,7 +413,7 @@ int aecb200_place_bits_device(aecb200_ctx *ctx, const void *d_src, uint64_t nbit
 {
     if (!ctx) return AEC_CONF_ERROR;
     if ((((uintptr_t)d_src) & 3u) || (((uintptr_t)d_dst) & 3u)) return AEC_CONF_ERROR;
-    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ENTER_DEVICE();
     CK(aec_place_bits_launch((const uint32_t *)d_src, nbits, (uint32_t *)d_dst, dst_bit, dst_cap / 4, head_or, ctx->stream),
        "place launch");
     ctx->launches += 1;
@@ -404,7 +442,7 @@ int aecb200_decode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
         snprintf(ctx->err, sizeof ctx->err, "device input must be 4-byte aligned");
         return AEC_CONF_ERROR;
     }
-    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ENTER_DEVICE();
     uint64_t out_samples = out_bytes / c.B;
     uint64_t need_rsi = (out_samples + c.R - 1) / c.R;
     if (need_rsi > nrsi) need_rsi = nrsi;
@@ -482,19 +520,79 @@ int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
     int rc = make_cfg(ctx, p, 0, &c);
     if (rc != AEC_OK) return rc;
     c.pad = (p->flags & AECF_PAD_RSI) ? 1u : 0u;      /* the decoder always honours it (decode.c:406-408) */
-    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ENTER_DEVICE();
     CK(ctx->misc.ensure_zeroed(256, ctx->stream), "cudaMalloc(misc)");
-    uint64_t *res = (uint64_t *)((uint8_t *)ctx->misc.p + 192);
+    uint64_t *state = (uint64_t *)((uint8_t *)ctx->misc.p + 192);
     if (found) *found = 0;
+    ctx->scan_end = start_bit;
+    ctx->scan_fast = 0;
     if (max_rsi == 0) return AEC_OK;
-    CK(aec_scan_offsets_launch(c, (const uint32_t *)d_in, in_bytes, start_bit, d_rsi_offsets, max_rsi, res, ctx->stream),
-       "scan launch");
-    ctx->launches += 1;
-    CK(cudaMemcpyAsync(&ctx->h_res[12], res, 24, cudaMemcpyDeviceToHost, ctx->stream), "memcpy(scan)");
+    const uint64_t nbits = (uint64_t)in_bytes * 8ull;
+    /* walk state: next RSI bit, RSIs found, flags, RSIs taken from the tables */
+    uint64_t *h_state = &ctx->h_res[8];
+    h_state[0] = start_bit; h_state[1] = 0; h_state[2] = 0; h_state[3] = 0;
+    CK(cudaMemcpyAsync(state, h_state, 32, cudaMemcpyHostToDevice, ctx->stream), "memcpy(scan state)");
+    const uint64_t base = start_bit & ~31ull;
+    const bool parallel = ctx->scan_mode == 2 || (ctx->scan_mode == 0 && in_bytes >= 2048);
+    if (!parallel || base >= nbits) {
+        /* short streams: one thread skims CDS after CDS (a dozen launches would cost more) */
+        uint64_t *res = state;
+        CK(aec_scan_offsets_launch(c, (const uint32_t *)d_in, in_bytes, start_bit, d_rsi_offsets, max_rsi, res, ctx->stream),
+           "scan launch");
+        ctx->launches += 1;
+        CK(cudaMemcpyAsync(&ctx->h_res[12], res, 24, cudaMemcpyDeviceToHost, ctx->stream), "memcpy(scan)");
+        CK(cudaStreamSynchronize(ctx->stream), "scan sync");
+        if (found) *found = (size_t)ctx->h_res[12];
+        ctx->scan_end = ctx->h_res[14];
+        return (ctx->h_res[13] & 1ull) ? AEC_DATA_ERROR : AEC_OK;
+    }
+    /* Windows of nh bit positions; the tables of a window reach one worst-case RSI further so that
+     * every RSI starting inside the window can be followed to its end. */
+    const uint32_t LV = aec_skim_levels(c);
+    const uint64_t margin = aec_skim_margin_bits(c);
+    uint64_t nh = (ctx->scan_window_bits + 31ull) & ~31ull;
+    if (nh < 1024) nh = 1024;
+    const uint64_t span = ((nbits - base) + 31ull) & ~31ull;
+    const uint64_t nwin = (span + nh - 1) / nh;
+    const uint64_t np_max = nh + margin < span ? nh + margin : span;
+    if (np_max >= 0x7FFFFFFFull) { snprintf(ctx->err, sizeof ctx->err, "scan window too large"); return AEC_CONF_ERROR; }
+    CK(ctx->skim_tab.ensure((size_t)(LV + 1u) * (size_t)np_max * 4u), "cudaMalloc(skim tables)");
+    AecSkimArgs a;
+    memset(&a, 0, sizeof a);
+    a.cfg = c;
+    a.in_words = (const uint32_t *)d_in;
+    a.nbits = nbits;
+    a.LV = LV;
+    a.T = (uint32_t *)ctx->skim_tab.p;
+    a.H = a.T + (size_t)LV * (size_t)np_max;
+    a.state = state;
+    a.offsets = d_rsi_offsets;
+    a.max_rsi = max_rsi;
+    for (uint64_t i = 0; i < nwin; i++) {
+        a.wb = base + i * nh;
+        const uint64_t rem = ((nbits - a.wb) + 31ull) & ~31ull;
+        a.np = (uint32_t)(nh + margin < rem ? nh + margin : rem);
+        a.last = (i + 1 == nwin) ? 1u : 0u;
+        a.nh_eff = a.last ? a.np : (uint32_t)nh;
+        CK(aec_skim_window_launch(a, ctx->stream), "skim launch");
+        ctx->launches += LV + 2u;
+    }
+    CK(cudaMemcpyAsync(&ctx->h_res[12], state, 32, cudaMemcpyDeviceToHost, ctx->stream), "memcpy(scan)");
     CK(cudaStreamSynchronize(ctx->stream), "scan sync");
-    if (found) *found = (size_t)ctx->h_res[12];
-    return (ctx->h_res[13] & 1ull) ? AEC_DATA_ERROR : AEC_OK;
+    if (found) *found = (size_t)ctx->h_res[13];
+    ctx->scan_end = ctx->h_res[12];
+    ctx->scan_fast = ctx->h_res[15];
+    return (ctx->h_res[14] & 2ull) ? AEC_DATA_ERROR : AEC_OK;
 }
+
+void aecb200_ctx_set_scan_mode(aecb200_ctx *ctx, int mode, uint64_t window_bits)
+{
+    if (!ctx) return;
+    ctx->scan_mode = mode;
+    if (window_bits) ctx->scan_window_bits = window_bits;
+}
+
+uint64_t aecb200_ctx_last_scan_fast(aecb200_ctx *ctx) { return ctx ? ctx->scan_fast : 0; }
 
 /* ------------------------------------------------------------------------ */
 /* host buffers                                                              */
@@ -512,7 +610,7 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
     if (in_consumed) *in_consumed = 0;
     if (n_offsets) *n_offsets = 0;
     if (rc != AEC_OK) return rc;
-    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ENTER_DEVICE();
 
     const size_t rsi_bytes = (size_t)c.R * c.B;
     size_t use_bytes = final ? (in_bytes / c.B) * c.B : (in_bytes / rsi_bytes) * rsi_bytes;
@@ -668,7 +766,7 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
     if (resume_bit) *resume_bit = start_bit;
     if (resume_delivered) *resume_delivered = skip_samples;
     if (rc != AEC_OK) return rc;
-    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ENTER_DEVICE();
     const uint64_t want_new = out_cap / c.B;                       /* samples the caller can take */
     const uint64_t out_samples = skip_samples + want_new;          /* counted from the RSI at start_bit */
     uint64_t need_rsi = (out_samples + c.R - 1) / c.R;
@@ -705,7 +803,7 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
         rc = aecb200_scan_offsets_device(ctx, p, ctx->in_stage.p, nbytes, start_bit - base_bit,
                                          (uint64_t *)ctx->offs.p, (size_t)need_rsi, &nrsi);
         if (rc != AEC_OK && rc != AEC_DATA_ERROR) return rc;
-        scan_end = ctx->h_res[14];
+        scan_end = ctx->scan_end;
         h_offs = (uint64_t *)malloc((nrsi + 1) * sizeof(uint64_t));
         if (!h_offs) return AEC_MEM_ERROR;
         if (nrsi) {
@@ -767,7 +865,7 @@ static int decode_host_pipelined(aecb200_ctx *ctx, const aecb200_params *p, cons
     for (uint64_t r = 0; r < need_rsi; r += per) first.push_back(r);
     first.push_back(need_rsi);
     const size_t npieces = first.size() - 1;
-    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ENTER_DEVICE();
     int rc = pipe_prepare(ctx, 2 * npieces);
     if (rc != AEC_OK) return rc;
     PipeGuard guard(ctx);

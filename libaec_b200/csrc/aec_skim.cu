@@ -1,0 +1,160 @@
+/*
+ * aec_skim.cu -- parallel discovery of RSI boundaries in a stream that comes without an index.
+ *
+ * The reference finds the start of RSI r+1 only by decoding RSI r (/root/reference/src/decode.c:402-421
+ * m_id, :288-340 direct_get_fs): every libaec 0.3.4 stream a caller can hand to aec_decode /
+ * aec_buffer_decode / SZ_BufftoBuffDecompress is of that kind.  A GPU cannot afford that chain
+ * (one thread: ~80 us per RSI), so the chain is cut into pieces that do not depend on where the
+ * stream is entered:
+ *
+ *   1. aec_skim_level0_kernel   for EVERY bit position p of a window: if a coded data set (CDS) started
+ *                               at p, how long would it be and how many blocks would it stand for
+ *                               (T0[p]; R[p] = the same for the first CDS of an RSI, which carries the
+ *                               reference sample).  One thread per position, the window's words and
+ *                               their running popcount staged in shared memory; a unary section is
+ *                               skipped by rank/select on that popcount instead of bit by bit.
+ *   2. aec_skim_double_kernel   T(j+1)[p] = T(j)[p] then T(j)[p + length]: the CDS chain from p after
+ *                               2^(j+1) steps (pointer doubling; bits and blocks add up).
+ *   3. aec_skim_rsi_kernel      H[p] = length of a whole RSI that starts at p: the first CDS from R[p],
+ *                               then a greedy descent through the levels until exactly `rsi` blocks
+ *                               are accounted for (run-of-zero-segment codes stand for "up to the end of
+ *                               the 64-block segment" and are resolved here, where the block number is known).
+ *   4. aec_skim_walk_kernel     the only serial part: one load of H per RSI from the stream's known
+ *                               first bit; RSIs whose H is not available (truncated or corrupt stream,
+ *                               a chain leaving the window) are skimmed CDS by CDS like the reference does.
+ *
+ * Everything up to the walk is independent of the entry point, so it runs on all SMs; windows bound
+ * the table memory (4 bytes x (levels + 1) per stream bit).
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "aec_skim_core.cuh"
+#include "aec_device.h"
+
+namespace {
+
+constexpr int SK_THREADS = 256;
+constexpr uint32_t SK_TILE = 8192;          /* bit positions per CTA of the level-0 kernel */
+
+__global__ void __launch_bounds__(SK_THREADS)
+aec_skim_level0_kernel(const AecSkimArgs a)
+{
+    if (a.state[2] & 1ull) return;                      /* the walk has already ended */
+    const AecCfg &c = a.cfg;
+    extern __shared__ uint32_t sk_smem[];
+    const uint32_t nwords = SK_TILE / 32u + a.la_words;
+    uint32_t *w = sk_smem;                              /* [nwords + 1] */
+    uint32_t *pre = sk_smem + nwords + 1u;              /* [nwords + 1] */
+    __shared__ uint32_t s_part[SK_THREADS / 32];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tile0 = blockIdx.x * SK_TILE;        /* window-relative */
+    const uint64_t word0 = (a.wb + tile0) >> 5;
+    const uint64_t total_words = (a.nbits + 31ull) >> 5;
+
+    /* stage the words (big endian) and their running popcount */
+    for (uint32_t i = tid; i <= nwords; i += SK_THREADS) {
+        const uint64_t wi = word0 + i;
+        w[i] = wi < total_words ? __byte_perm(__ldg(a.in_words + wi), 0, 0x0123) : 0u;
+    }
+    __syncthreads();
+    {
+        /* nwords <= 256 + 70: two rounds of a block-wide exclusive scan */
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < nwords + 1u; base += SK_THREADS) {
+            const uint32_t i = base + tid;
+            const uint32_t v = i < nwords ? (uint32_t)__popc(w[i]) : 0u;
+            uint32_t inc = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+                if ((tid & 31u) >= (uint32_t)off) inc += o;
+            }
+            if ((tid & 31u) == 31u) s_part[tid >> 5] = inc;
+            __syncthreads();
+            uint32_t before = carry;
+            for (uint32_t ww = 0; ww < (tid >> 5); ww++) before += s_part[ww];
+            if (i <= nwords) pre[i] = before + inc - v;
+            uint32_t tot = 0;
+            for (uint32_t ww = 0; ww < SK_THREADS / 32; ww++) tot += s_part[ww];
+            carry += tot;
+            __syncthreads();
+        }
+    }
+    /* bits of the stream that exist, relative to the tile */
+    const uint64_t tile_abs = a.wb + tile0;
+    const uint32_t limit = a.nbits > tile_abs ? (uint32_t)min((unsigned long long)(a.nbits - tile_abs), 0x7FFFFFFFull) : 0u;
+    for (uint32_t q = tid; q < SK_TILE; q += SK_THREADS) {
+        const uint32_t p = tile0 + q;
+        if (p >= a.np) break;
+        uint32_t t0 = 0u, r0 = 0u;
+        if (q < limit) {
+            t0 = sk_entry(c, w, pre, nwords, q, limit, 0u);
+            r0 = c.pp ? sk_entry(c, w, pre, nwords, q, limit, 1u) : t0;
+        }
+        a.T[p] = t0;
+        a.H[p] = r0;
+    }
+}
+
+__global__ void __launch_bounds__(SK_THREADS)
+aec_skim_double_kernel(const AecSkimArgs a, uint32_t level)
+{
+    if (a.state[2] & 1ull) return;
+    const uint32_t p = blockIdx.x * SK_THREADS + threadIdx.x;
+    if (p >= a.np) return;
+    const uint32_t *src = a.T + (size_t)level * a.np;
+    uint32_t *dst = a.T + (size_t)(level + 1u) * a.np;
+    const uint32_t r = sk_double(src, a.np, p);
+    dst[p] = r;
+}
+
+/* H[p] <- bits from p to the start of the next RSI when an RSI starts at p (0: not available) */
+__global__ void __launch_bounds__(SK_THREADS)
+aec_skim_rsi_kernel(const AecSkimArgs a)
+{
+    if (a.state[2] & 1ull) return;
+    const AecCfg &c = a.cfg;
+    uint32_t p = blockIdx.x * SK_THREADS + threadIdx.x;
+    if (c.pad) p <<= 3;                                 /* padded RSIs start on byte boundaries */
+    if (p >= a.nh_eff) return;
+    const uint32_t res = sk_rsi_len(c, a.T, a.LV, a.np, p, a.H[p]);   /* H[p] still holds the first-CDS entry */
+    a.H[p] = res;
+}
+
+/* state: [0] bit position of the next RSI, [1] RSIs found, [2] flags (1 ended, 2 data error),
+ * [3] RSIs taken from the tables (diagnostics) */
+__global__ void aec_skim_walk_kernel(const AecSkimArgs a)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (a.state[2] & 1ull) return;
+    const AecCfg &c = a.cfg;
+    SkWalk s; s.pos = a.state[0]; s.found = a.state[1]; s.flags = 0; s.fast = a.state[3];
+    BitRd br;
+    br.init(a.in_words, (a.nbits + 31ull) >> 5, a.nbits);
+    const uint32_t *H = a.H;
+    while (sk_walk_step(c, br, a.nbits, a.wb, a.nh_eff, a.last, a.offsets, a.max_rsi, s,
+                        [H](uint64_t rel) { return __ldcg(H + rel); })) { }
+    a.state[0] = s.pos; a.state[1] = s.found; a.state[2] = s.flags; a.state[3] = s.fast;
+}
+
+} // namespace
+
+uint32_t aec_skim_levels(const AecCfg &c) { return sk_levels(c); }
+uint64_t aec_skim_margin_bits(const AecCfg &c) { return sk_margin_bits(c); }
+
+cudaError_t aec_skim_window_launch(const AecSkimArgs &args, cudaStream_t st)
+{
+    AecSkimArgs a = args;
+    if (a.np == 0) return cudaSuccess;
+    a.la_words = sk_lookahead_words(a.cfg);
+    const uint32_t smem = 2u * (SK_TILE / 32u + a.la_words + 1u) * 4u;
+    aec_skim_level0_kernel<<<(a.np + SK_TILE - 1u) / SK_TILE, SK_THREADS, smem, st>>>(a);
+    const uint32_t grid = (a.np + SK_THREADS - 1u) / SK_THREADS;
+    for (uint32_t j = 0; j + 1u < a.LV; j++)
+        aec_skim_double_kernel<<<grid, SK_THREADS, 0, st>>>(a, j);
+    const uint32_t cand = a.cfg.pad ? (a.nh_eff + 7u) / 8u : a.nh_eff;
+    aec_skim_rsi_kernel<<<(cand + SK_THREADS - 1u) / SK_THREADS, SK_THREADS, 0, st>>>(a);
+    aec_skim_walk_kernel<<<1, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}

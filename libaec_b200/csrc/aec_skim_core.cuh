@@ -1,0 +1,196 @@
+/*
+ * aec_skim_core.cuh -- building blocks of the parallel RSI-boundary discovery (aec_skim.cu), host+device
+ * so that the CPU model harness (cpu_model.cpp) runs the very same code against the oracle.
+ *
+ * Table entry (32 bits): bits 31..12 = length in bits of a piece of the CDS chain (0 = nothing valid
+ * starts here), bits 11..0 = blocks it stands for; a length with 0 blocks is a run-of-zero-segment CDS,
+ * whose block count depends on the block number (decode.c:528-530).
+ */
+#ifndef AEC_SKIM_CORE_CUH
+#define AEC_SKIM_CORE_CUH
+
+#include "aec_decode_core.cuh"
+
+#define SK_FAIL 0xFFFFFFFFu
+#define SK_MAX_LEVELS 8
+
+AEC_HD uint32_t sk_len(uint32_t e) { return e >> 12; }
+AEC_HD uint32_t sk_blk(uint32_t e) { return e & 0xFFFu; }
+AEC_HD bool sk_jump(uint32_t e) { return e >= 0x1000u && (e & 0xFFFu) != 0u; }
+AEC_HD bool sk_ros(uint32_t e) { return e >= 0x1000u && (e & 0xFFFu) == 0u; }
+
+AEC_HD uint32_t sk_popc(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+
+/* position (0 = most significant bit) of the r-th set bit of x counted from the top, 1 <= r <= popc(x) */
+AEC_HD uint32_t sk_select_from_top(uint32_t x, uint32_t r)
+{
+    uint32_t pos = 0, c;
+    bool lo;
+    c = sk_popc(x >> 16); lo = r > c; r -= lo ? c : 0u; pos += lo ? 16u : 0u; x = lo ? (x << 16) : x;
+    c = sk_popc(x >> 24); lo = r > c; r -= lo ? c : 0u; pos += lo ? 8u : 0u;  x = lo ? (x << 8) : x;
+    c = sk_popc(x >> 28); lo = r > c; r -= lo ? c : 0u; pos += lo ? 4u : 0u;  x = lo ? (x << 4) : x;
+    c = sk_popc(x >> 30); lo = r > c; r -= lo ? c : 0u; pos += lo ? 2u : 0u;  x = lo ? (x << 2) : x;
+    c = x >> 31; pos += (r > c) ? 1u : 0u;
+    return pos;
+}
+
+/* tile-relative position of the m-th one at or after tile-relative bit q (m >= 1); SK_FAIL when it is not
+ * inside the staged words.  w[0..nwords]: big-endian words, pre[i] = ones in w[0..i), i <= nwords */
+AEC_HD uint32_t sk_find_one(const uint32_t *w, const uint32_t *pre, uint32_t nwords, uint32_t q, uint32_t m)
+{
+    uint32_t i = q >> 5;
+    if (i >= nwords) return SK_FAIL;
+    const uint32_t first = w[i] & (0xFFFFFFFFu >> (q & 31u));
+    const uint32_t c = sk_popc(first);
+    if (m <= c) return 32u * i + sk_select_from_top(first, m);
+    i++;
+    const uint32_t target = pre[i] + (m - c);
+    while (i < nwords && pre[i + 1] < target) i++;
+    if (i >= nwords) return SK_FAIL;
+    return 32u * i + sk_select_from_top(w[i], target - pre[i]);
+}
+
+/* The CDS that would start at tile-relative bit q0 (decode.c:402-677 restated as "how long, how many
+ * blocks"); ref != 0: it is the first CDS of an RSI and carries the reference sample.  limit = stream
+ * bits that exist, tile-relative.  q0 < 32 * (nwords - 1). */
+AEC_HD uint32_t sk_entry(const AecCfg &c, const uint32_t *w, const uint32_t *pre, uint32_t nwords,
+                         uint32_t q0, uint32_t limit, uint32_t ref)
+{
+    const uint32_t i = q0 >> 5;
+    const uint32_t win = aec_funnel(w[i], w[i + 1], q0 & 31u);
+    const uint32_t id = win >> (32u - c.idl);
+    const uint32_t refb = ref ? c.n : 0u;
+    uint32_t q, m, extra = 0;
+    bool zero = false;
+    if (id == 0u) {
+        const uint32_t sel = (win >> (31u - c.idl)) & 1u;
+        q = q0 + c.idl + 1u + refb;
+        m = sel ? (c.J >> 1) : 1u;                      /* second extension: J/2 codes; zero run: one */
+        zero = sel == 0u;
+    } else if (id == (1u << c.idl) - 1u) {
+        const uint32_t len = c.idl + c.J * c.n;         /* the reference sample takes the place of sample 0 */
+        return (q0 + len <= limit) ? ((len << 12) | 1u) : 0u;
+    } else {
+        const uint32_t k = id - 1u;
+        q = q0 + c.idl + refb;
+        m = c.J - (ref ? 1u : 0u);
+        extra = m * k;
+    }
+    const uint32_t e = sk_find_one(w, pre, nwords, q, m);
+    if (e == SK_FAIL) return 0u;
+    const uint32_t end = e + 1u + extra;
+    if (end > limit) return 0u;
+    uint32_t blocks = 1u;
+    if (zero) {
+        const uint32_t zb = e - q + 1u;                 /* decode.c:525-533 */
+        blocks = zb == 5u ? 0u : (zb > 5u ? zb - 1u : zb);
+        if (blocks > 0xFFFu) return 0u;
+    }
+    return ((end - q0) << 12) | blocks;
+}
+
+/* one pointer-doubling step: the chain from p after twice as many CDSs */
+AEC_HD uint32_t sk_double(const uint32_t *src, uint32_t np, uint32_t p)
+{
+    const uint32_t x = src[p];
+    if (!sk_jump(x)) return 0u;
+    const uint32_t q = p + sk_len(x);
+    if (q >= np) return 0u;
+    const uint32_t y = src[q];
+    if (!sk_jump(y)) return 0u;
+    const uint32_t blk = sk_blk(x) + sk_blk(y), len = sk_len(x) + sk_len(y);
+    return (blk <= 0xFFFu && len <= 0xFFFFFu) ? ((len << 12) | blk) : 0u;
+}
+
+/* Bits from window-relative p to the start of the next RSI when an RSI starts at p (0: the tables cannot
+ * tell).  first = entry of the RSI's first CDS; T[LV][np] = the chain tables. */
+AEC_HD uint32_t sk_rsi_len(const AecCfg &c, const uint32_t *T, uint32_t LV, uint32_t np, uint32_t p, uint32_t first)
+{
+    if (first < 0x1000u) return 0u;
+    uint32_t b = sk_blk(first);
+    if (b == 0u) b = c.rsi < 64u ? c.rsi : 64u;        /* run-of-zero-segment at block 0 */
+    uint32_t q = p + sk_len(first);
+    if (b > c.rsi) return 0u;
+    while (b < c.rsi) {
+        uint32_t rem = c.rsi - b;
+        for (int j = (int)LV - 1; j >= 0; j--) {
+            const uint32_t *Tj = T + (size_t)j * np;
+            for (;;) {
+                if (q >= np) break;
+                const uint32_t e = Tj[q];
+                if (!sk_jump(e) || sk_blk(e) > rem) break;
+                q += sk_len(e); rem -= sk_blk(e);
+                if (j != (int)LV - 1) break;            /* below the top level a step fits at most once */
+            }
+        }
+        b = c.rsi - rem;
+        if (rem == 0u) break;
+        /* the CDS at q is not a plain step: run-of-zero-segment, or the chain ends here */
+        if (q >= np) return 0u;
+        const uint32_t e = T[q];
+        if (sk_ros(e)) {
+            const uint32_t seg = 64u - (b & 63u);
+            b += rem < seg ? rem : seg;                 /* decode.c:528-530 */
+            q += sk_len(e);
+        } else if (sk_jump(e) && sk_blk(e) <= rem) {
+            q += sk_len(e); b += sk_blk(e);
+        } else return 0u;
+    }
+    if (c.pad) q = (q + 7u) & ~7u;                      /* windows start on byte boundaries */
+    return q - p;
+}
+
+/* levels of the chain tables: level j = 2^j CDSs; 2^LV - 1 >= rsi - 1 up to the cap */
+AEC_HD uint32_t sk_levels(const AecCfg &c)
+{
+    uint32_t lv = 1;
+    while (lv < SK_MAX_LEVELS && (1u << lv) < c.rsi) lv++;
+    return lv;
+}
+
+/* bits an RSI can take at most, in whole words, plus slack */
+AEC_HD uint64_t sk_margin_bits(const AecCfg &c)
+{
+    const uint64_t cds = c.idl + 1ull + (uint64_t)(c.J + 1u) * c.n;
+    return ((cds * c.rsi + 8ull + 31ull) & ~31ull) + 64ull;
+}
+
+/* words staged beyond a tile: the longest CDS plus the funnel shift's neighbour */
+AEC_HD uint32_t sk_lookahead_words(const AecCfg &c)
+{
+    return (uint32_t)((c.idl + 1ull + (uint64_t)(c.J + 1u) * c.n + 31ull) / 32ull) + 2u;
+}
+
+/* One RSI of the walk: the serial part of the discovery.  Returns false when the walk ends.
+ * state: pos, found, flags (1 ended, 2 data error), fast. */
+struct SkWalk { uint64_t pos, found, flags, fast; };
+
+template <class LoadH>
+AEC_HD bool sk_walk_step(const AecCfg &c, BitRd &br, uint64_t nbits, uint64_t wb, uint32_t nh_eff, uint32_t last,
+                         uint64_t *offsets, uint64_t max_rsi, SkWalk &s, LoadH load_h)
+{
+    if (s.found >= max_rsi) { s.flags = 1; return false; }
+    const uint64_t start = c.pad ? ((s.pos + 7ull) & ~7ull) : s.pos;
+    if (start >= nbits) { s.flags = 1; return false; }
+    if (start >= wb + nh_eff && !last) return false;    /* the next window takes over */
+    offsets[s.found++] = start;                         /* even a truncated RSI may still deliver leading samples */
+    const uint64_t rel = start - wb;
+    const uint32_t h = rel < nh_eff ? load_h(rel) : 0u;
+    if (h) { s.pos = start + h; s.fast++; return true; }
+    /* not in the tables: skim this RSI CDS by CDS (truncated or damaged stream, chain leaving the window) */
+    RsiDec st; st.pos = start; st.zero_left = 0; st.status = DEC_OK;
+    for (uint32_t b = 0; b < c.rsi; b++)
+        if (!aec_skim_block(c, br, st, b)) break;
+    s.pos = st.pos;
+    if (st.status != DEC_OK) { s.flags = 1ull | (st.status == DEC_ERROR ? 2ull : 0ull); return false; }
+    return true;
+}
+
+#endif /* AEC_SKIM_CORE_CUH */

@@ -228,3 +228,89 @@ extern "C" int model_decode(uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags
     *out_len = (size_t)(total * c.B);
     return err ? -3 : 0;
 }
+
+/* ------------------------------------------------------------------------ */
+/* RSI boundary discovery (aec_skim.cu) on the CPU: the same window loop, tile staging, level tables,
+ * RSI lengths and walk, with the kernels' grids replaced by loops.                                   */
+/* ------------------------------------------------------------------------ */
+#include "aec_skim_core.cuh"
+
+extern "C" int model_scan_offsets(uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags,
+                                  const uint8_t *in, size_t in_bytes, uint64_t start_bit,
+                                  uint64_t *offsets, uint64_t max_rsi, uint64_t window_bits, int serial,
+                                  uint64_t *found, uint64_t *out_flags, uint64_t *fast, uint64_t *end_pos)
+{
+    AecCfg c;
+    if (aec_cfg_init(&c, n, J, rsi, flags, 0, 0) != 0) return -1;
+    if (J == 0 || J > AEC_MAX_J || rsi == 0) return -1;
+    c.pad = (flags & AECF_PAD_RSI) ? 1u : 0u;
+    const uint64_t nbits = (uint64_t)in_bytes * 8ull;
+    const uint64_t total_words = (nbits + 31ull) >> 5;
+    std::vector<uint32_t> words(total_words + 4, 0);            /* raw byte order like the device buffer */
+    memcpy(words.data(), in, in_bytes);
+    BitRd br;
+    br.init(words.data(), total_words, nbits);
+    SkWalk s; s.pos = start_bit; s.found = 0; s.flags = 0; s.fast = 0;
+    *found = 0; *out_flags = 0; *fast = 0; *end_pos = start_bit;
+    if (max_rsi == 0) return 0;
+    const uint64_t base = start_bit & ~31ull;
+    if (serial || base >= nbits) {
+        /* the one-thread scan (aec_scan_offsets_kernel) */
+        RsiDec st; st.pos = start_bit; st.zero_left = 0; st.status = DEC_OK;
+        uint64_t f = 0;
+        for (uint64_t r = 0; r < max_rsi; r++) {
+            if (c.pad) st.pos = (st.pos + 7ull) & ~7ull;
+            st.zero_left = 0;
+            if (st.pos >= br.nbits) break;
+            offsets[f++] = st.pos;
+            for (uint32_t b = 0; b < c.rsi; b++)
+                if (!aec_skim_block(c, br, st, b)) break;
+            if (st.status != DEC_OK) break;
+        }
+        *found = f; *out_flags = (st.status == DEC_ERROR) ? 2 : 0; *end_pos = st.pos;
+        return 0;
+    }
+    const uint32_t LV = sk_levels(c);
+    const uint64_t margin = sk_margin_bits(c);
+    uint64_t nh = (window_bits + 31ull) & ~31ull;
+    if (nh < 1024) nh = 1024;
+    const uint64_t span = ((nbits - base) + 31ull) & ~31ull;
+    const uint64_t nwin = (span + nh - 1) / nh;
+    const uint32_t TILE = 8192, la = sk_lookahead_words(c), nwords = TILE / 32u + la;
+    std::vector<uint32_t> T, H, w(nwords + 1), pre(nwords + 2);
+    for (uint64_t wi = 0; wi < nwin && !(s.flags & 1ull); wi++) {
+        const uint64_t wb = base + wi * nh;
+        const uint64_t rem = ((nbits - wb) + 31ull) & ~31ull;
+        const uint32_t np = (uint32_t)(nh + margin < rem ? nh + margin : rem);
+        const uint32_t last = (wi + 1 == nwin) ? 1u : 0u;
+        const uint32_t nh_eff = last ? np : (uint32_t)nh;
+        T.assign((size_t)LV * np, 0u); H.assign(np, 0u);
+        for (uint32_t tile0 = 0; tile0 < np; tile0 += TILE) {           /* level-0 kernel, one CTA */
+            const uint64_t word0 = (wb + tile0) >> 5;
+            for (uint32_t i = 0; i <= nwords; i++) {
+                const uint64_t x = word0 + i;
+                w[i] = x < total_words ? aec_bswap32(words[x]) : 0u;
+            }
+            pre[0] = 0;
+            for (uint32_t i = 0; i <= nwords; i++) pre[i + 1] = pre[i] + (i < nwords ? sk_popc(w[i]) : 0u);
+            const uint64_t tile_abs = wb + tile0;
+            const uint32_t limit = nbits > tile_abs ? (uint32_t)((nbits - tile_abs) < 0x7FFFFFFFull ? (nbits - tile_abs) : 0x7FFFFFFFull) : 0u;
+            for (uint32_t q = 0; q < TILE && tile0 + q < np; q++) {
+                uint32_t t0 = 0, r0 = 0;
+                if (q < limit) {
+                    t0 = sk_entry(c, w.data(), pre.data(), nwords, q, limit, 0u);
+                    r0 = c.pp ? sk_entry(c, w.data(), pre.data(), nwords, q, limit, 1u) : t0;
+                }
+                T[tile0 + q] = t0; H[tile0 + q] = r0;
+            }
+        }
+        for (uint32_t j = 0; j + 1 < LV; j++)
+            for (uint32_t p = 0; p < np; p++) T[(size_t)(j + 1) * np + p] = sk_double(T.data() + (size_t)j * np, np, p);
+        for (uint32_t p = 0; p < nh_eff; p += c.pad ? 8u : 1u) H[p] = sk_rsi_len(c, T.data(), LV, np, p, H[p]);
+        const uint32_t *Hp = H.data();
+        while (sk_walk_step(c, br, nbits, wb, nh_eff, last, offsets, max_rsi, s,
+                            [Hp](uint64_t rel) { return Hp[rel]; })) { }
+    }
+    *found = s.found; *out_flags = s.flags; *fast = s.fast; *end_pos = s.pos;
+    return 0;
+}

@@ -69,13 +69,22 @@ static pthread_mutex_t pool_lock = PTHREAD_MUTEX_INITIALIZER;
 static aecb200_ctx *pool[16];
 static int pool_n;
 
+/* a stream runs on the device that is current when it is initialised: only contexts of that device
+ * are reused */
 static aecb200_ctx *ctx_get(void)
 {
     aecb200_ctx *c = NULL;
+    const int dev = aecb200_current_device();
     pthread_mutex_lock(&pool_lock);
-    if (pool_n > 0) c = pool[--pool_n];
+    for (int i = pool_n - 1; i >= 0; i--) {
+        if (aecb200_ctx_device(pool[i]) == dev) {
+            c = pool[i];
+            pool[i] = pool[--pool_n];
+            break;
+        }
+    }
     pthread_mutex_unlock(&pool_lock);
-    if (!c && aecb200_ctx_create(&c, -1) != 0) return NULL;
+    if (!c && aecb200_ctx_create(&c, dev) != 0) return NULL;
     return c;
 }
 

@@ -1,0 +1,113 @@
+"""RSI boundary discovery for streams without an index (aec_skim.cu): the parallel tables
+(per-bit-position CDS lengths, pointer doubling, one look-up per RSI) against the one-thread scan and
+against the offsets the oracle's encoder records, on whole, truncated and padded streams; then the
+un-indexed decode of the README workload through aec_buffer_decode."""
+import numpy as np
+import pytest
+
+import libaec_b200 as L
+from cases import pack_samples, random_case, random_params, synth_values
+from libaec_b200 import datagen
+from oracle import pyoracle as po
+from oracle.pyoracle import AEC_DATA_SIGNED
+
+pytestmark = pytest.mark.gpu
+
+
+def P(p):
+    return L.Params(p.bits_per_sample, p.block_size, p.rsi, p.flags)
+
+
+def _scan(codec, torch, p, comp, max_rsi, mode, window):
+    codec.set_scan_mode(mode, window)
+    pad = (-comp.size) % 4
+    d_in = torch.from_numpy(np.concatenate([comp, np.zeros(pad + 8, np.uint8)])).cuda()
+    d_off = torch.zeros(max(max_rsi, 1), dtype=torch.int64, device="cuda")
+    st, found = codec.scan_offsets(P(p), d_in, comp.size, d_off, max_rsi)
+    return st, d_off[:found].cpu().numpy().astype(np.uint64), codec.last_scan_fast
+
+
+def _multi_rsi_case(seed):
+    rng = np.random.default_rng(77_000 + seed)
+    p = random_params(rng, allow_pad=bool(seed & 1))
+    R = p.rsi * p.block_size
+    if 12 * R > 200_000:
+        return None
+    count = int(rng.integers(5, 12)) * R + int(rng.integers(0, R))
+    vals = synth_values(rng, p.bits_per_sample, count, int(rng.integers(0, 6)), bool(p.flags & AEC_DATA_SIGNED))
+    return p, np.ascontiguousarray(pack_samples(vals, p)), count
+
+
+def test_parallel_scan_matches_serial_scan_and_encoder_offsets():
+    import torch
+    codec = L.DeviceCodec()
+    done = 0
+    for seed in range(300):
+        case = _multi_rsi_case(seed)
+        if case is None:
+            continue
+        p, raw, count = case
+        pad_build = bool(p.flags & L.AEC_PAD_RSI)
+        enc = po.orc_encode(p, raw, want_offsets=True, pad_rsi_build=pad_build)
+        assert enc["status"] == 0
+        comp = enc["out"]
+        R = p.rsi * p.block_size
+        nrsi = (count + R - 1) // R
+        rng = np.random.default_rng(seed)
+        for cut in (comp.size, int(rng.integers(1, comp.size + 1))):
+            c = np.ascontiguousarray(comp[:cut])
+            st1, off1, _ = _scan(codec, torch, p, c, nrsi + 3, 1, 0)
+            for window in (1024, 1 << 25):
+                st2, off2, fast = _scan(codec, torch, p, c, nrsi + 3, 2, window)
+                assert st2 == st1, (seed, p, cut, window)
+                assert np.array_equal(off2, off1), (seed, p, cut, window)
+                if cut == comp.size and window == 1 << 25 and nrsi > 2:
+                    # whole RSIs come from the tables; only the last (short or padded) one may not
+                    assert fast >= nrsi - 2, (seed, p, fast, nrsi)
+            if cut == comp.size:
+                k = min(off1.size, enc["offsets"].size)
+                assert k >= nrsi - 1 and np.array_equal(off1[:k], enc["offsets"][:k]), (seed, p)
+            # fewer RSIs asked for than the stream holds
+            st3, off3, _ = _scan(codec, torch, p, c, 2, 2, 1024)
+            assert np.array_equal(off3, off1[:2]), (seed, p, cut)
+        done += 1
+    assert done > 150
+    codec.close()
+
+
+def test_parallel_scan_small_random_cases():
+    """every n, flag set and block size of the sweep, including streams of less than one RSI"""
+    import torch
+    codec = L.DeviceCodec()
+    for seed in range(400):
+        p, raw = random_case(seed, allow_pad=True)
+        pad_build = bool(p.flags & L.AEC_PAD_RSI)
+        enc = po.orc_encode(p, raw, pad_rsi_build=pad_build)
+        comp = np.ascontiguousarray(enc["out"])
+        if comp.size == 0:
+            continue
+        st1, off1, _ = _scan(codec, torch, p, comp, 8, 1, 0)
+        st2, off2, _ = _scan(codec, torch, p, comp, 8, 2, 2048)
+        assert st1 == st2 and np.array_equal(off1, off2), (seed, p)
+    codec.close()
+
+
+@pytest.mark.parametrize("name,mib", [("c1", 32), ("c2", 16), ("c3", 8), ("c4", 24), ("c5_noise", 8), ("c5_restricted", 4)])
+def test_unindexed_buffer_decode_of_the_configs(name, mib):
+    """aec_buffer_decode (no index: what every libaec.h caller does) == the input, and nearly every
+    RSI boundary comes from the tables."""
+    import torch
+    p, _ = datagen.CONFIGS[name]
+    B = p.bytes_per_sample
+    raw = datagen.generate(name, (mib << 20) // B)
+    enc = L.buffer_encode(p, raw)
+    assert enc["status"] == 0
+    dec = L.buffer_decode(p, enc["out"], raw.size)
+    assert dec["status"] == 0 and dec["out"].size == raw.size
+    assert np.array_equal(dec["out"], raw)
+    codec = L.DeviceCodec()
+    R = p.rsi * p.block_size
+    nrsi = (raw.size // B + R - 1) // R
+    st, off, fast = _scan(codec, torch, p, np.ascontiguousarray(enc["out"]), nrsi, 2, 0)
+    assert st == 0 and off.size == nrsi and fast >= nrsi - 2, (name, off.size, nrsi, fast)
+    codec.close()

@@ -1,0 +1,108 @@
+"""RSI boundary discovery without a GPU: the host+device code of csrc/aec_skim_core.cuh (per-position CDS
+entries by rank/select, pointer doubling, RSI lengths by greedy descent, the walk) run on the CPU by
+tests/_build/libaec_cpumodel.so, arranged in windows and tiles like aec_skim.cu arranges it, against the
+one-thread scan and the offsets the oracle's encoder records."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from cases import pack_samples, random_case, random_params, synth_values
+from oracle import pyoracle as po
+from oracle.pyoracle import AEC_DATA_SIGNED, AEC_PAD_RSI
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def model():
+    from libaec_b200.build import build
+    build()
+    return C.CDLL(os.path.join(ROOT, "tests", "_build", "libaec_cpumodel.so"))
+
+
+def scan(m, p, comp, max_rsi, window, serial, start_bit=0):
+    src = np.ascontiguousarray(comp)
+    offs = np.zeros(max(max_rsi, 1), np.uint64)
+    found, flags, fast, end = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    rc = m.model_scan_offsets(C.c_uint32(p.bits_per_sample), C.c_uint32(p.block_size), C.c_uint32(p.rsi),
+                              C.c_uint32(p.flags), src.ctypes.data_as(C.c_void_p), C.c_size_t(src.size),
+                              C.c_uint64(start_bit), offs.ctypes.data_as(C.c_void_p), C.c_uint64(max_rsi),
+                              C.c_uint64(window), C.c_int(serial), C.byref(found), C.byref(flags), C.byref(fast),
+                              C.byref(end))
+    assert rc == 0
+    return offs[:found.value].copy(), flags.value & 2, fast.value, end.value
+
+
+def multi_rsi_case(seed, max_total=24_000):
+    rng = np.random.default_rng(77_000 + seed)
+    p = random_params(rng, allow_pad=bool(seed & 1))
+    R = p.rsi * p.block_size
+    if 6 * R > max_total:
+        return None
+    count = int(rng.integers(3, 6)) * R + int(rng.integers(0, R))
+    vals = synth_values(rng, p.bits_per_sample, count, int(rng.integers(0, 6)), bool(p.flags & AEC_DATA_SIGNED))
+    return p, np.ascontiguousarray(pack_samples(vals, p)), count
+
+
+def test_tables_match_serial_scan_and_encoder_offsets(model):
+    done = 0
+    for seed in range(120):
+        case = multi_rsi_case(seed)
+        if case is None:
+            continue
+        p, raw, count = case
+        enc = po.orc_encode(p, raw, want_offsets=True, pad_rsi_build=bool(p.flags & AEC_PAD_RSI))
+        assert enc["status"] == 0
+        comp = enc["out"]
+        R = p.rsi * p.block_size
+        nrsi = (count + R - 1) // R
+        rng = np.random.default_rng(seed)
+        for cut in (comp.size, int(rng.integers(1, comp.size + 1))):
+            c = comp[:cut]
+            o1, e1, _, end1 = scan(model, p, c, nrsi + 3, 0, 1)
+            for window in (1024, 1 << 25):
+                o2, e2, fast, end2 = scan(model, p, c, nrsi + 3, window, 0)
+                assert e1 == e2 and np.array_equal(o1, o2), (seed, p, cut, window)
+                if cut == comp.size and window == 1 << 25 and nrsi > 2:
+                    assert fast >= nrsi - 2, (seed, p, fast, nrsi)
+            if cut == comp.size:
+                k = min(o1.size, enc["offsets"].size)
+                assert k >= nrsi - 1 and np.array_equal(o1[:k], enc["offsets"][:k]), (seed, p)
+            o3, _, _, end3 = scan(model, p, c, 2, 2048, 0)
+            assert np.array_equal(o3, o1[:2]), (seed, p, cut)
+            if o1.size > 2:
+                # stopping early leaves the position of the next RSI behind (what a streaming decode resumes from)
+                assert end3 == o1[2] or (p.flags & AEC_PAD_RSI and (end3 + 7) // 8 * 8 == o1[2]), (seed, p)
+        done += 1
+    assert done > 40
+
+
+def test_tables_small_random_cases(model):
+    """every n, flag set and block size of the sweep, streams of less than one RSI included"""
+    for seed in range(150):
+        p, raw = random_case(seed, allow_pad=True, max_samples=2000)
+        enc = po.orc_encode(p, raw, pad_rsi_build=bool(p.flags & AEC_PAD_RSI))
+        comp = enc["out"]
+        if comp.size == 0:
+            continue
+        o1, e1, _, _ = scan(model, p, comp, 8, 0, 1)
+        o2, e2, _, _ = scan(model, p, comp, 8, 2048, 0)
+        assert e1 == e2 and np.array_equal(o1, o2), (seed, p)
+
+
+def test_tables_resume_inside_the_stream(model):
+    """a scan may start at any RSI (streaming decode resumes at the RSI of the next undelivered sample)"""
+    for seed in range(40):
+        case = multi_rsi_case(seed)
+        if case is None:
+            continue
+        p, raw, count = case
+        enc = po.orc_encode(p, raw, want_offsets=True, pad_rsi_build=bool(p.flags & AEC_PAD_RSI))
+        offs = enc["offsets"]
+        if offs.size < 3:
+            continue
+        o1, _, _, _ = scan(model, p, enc["out"], 100, 0, 1, start_bit=int(offs[2]))
+        o2, _, _, _ = scan(model, p, enc["out"], 100, 1024, 0, start_bit=int(offs[2]))
+        assert np.array_equal(o1, o2) and o1[0] == offs[2], (seed, p)
