@@ -6,9 +6,13 @@
 
 A step = one pass of the hot path over one batch of synthetic input: encode the
 batch, decode it back (both directions of the metric).  `value` is raw
-(uncompressed) GB/s with buffers resident in HBM; `e2e` is the same work
-through the libaec-facing host-pointer C ABI (pinned host buffers, H2D/D2H
-inside the timed region).  One JSON line on stdout (rank 0).
+(uncompressed) GB/s with buffers resident in HBM; `e2e` is the same work through
+the reference's own entry points -- aec_buffer_encode then aec_buffer_decode of
+include/libaec.h on host buffers, the decode WITHOUT any index (a libaec 0.3.4
+caller has none to give: RSI boundaries are discovered on the device), H2D/D2H
+inside the timed region.  `e2e` uses pinned host buffers, `e2e_pageable` plain
+numpy memory, `e2e_indexed` the offsets extension (aec_encode_enable_offsets /
+aec_decode_set_offsets).  One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
@@ -146,19 +150,62 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    # a step of the reference arm = the same workload and bytes as one GPU's step, whatever N is
+    # (bounded sample: the CPU figure does not depend on how many GPUs the other arm uses)
     nbytes = min(args.mib, 256) << 20
-    r = cpu_reference_run(args.workload, nbytes, threads, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    r = cpu_reference_run(args.workload, nbytes, threads, max(1, args.steps), max(0, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": max(1, min(args.steps, 3)), "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+        "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "bytes_per_step": r["raw_bytes"]},
+        "config": bench_config(args),
         "encode_gbs": r["encode_gbs"], "decode_gbs": r["decode_gbs"],
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                          "sample": "%d MiB of the workload, one RSI-aligned shard per host thread, aec_buffer_encode + aec_buffer_decode" % (r["raw_bytes"] >> 20)},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def bench_config(args):
+    """The same dict in both arms (the driver compares them)."""
+    return {"workload": workload_name(args), "raw_bytes_per_gpu_step": args.mib << 20,
+            "l2": "inputs larger than L2 (%d MiB raw per step vs 126 MB L2), no explicit flush" % args.mib}
+
+
+def csrc_fingerprint():
+    """sha256 over the kernel sources: ties an ncu capture under profiles/ to the build being benchmarked."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "libaec_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h", ".c")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode()); h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def pin_to_gpu_numa(local: int):
+    """Run this rank on the CPUs next to its GPU (pinned buffers are then allocated on that node)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        base = "/sys/bus/pci/devices/" + bus
+        node = int(open(base + "/numa_node").read())
+        cpus = []
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:                      # no NUMA information: leave the affinity alone
+        return {"numa_node": None, "error": type(e).__name__}
 
 
 def workload_name(args):
@@ -183,6 +230,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa(local)                # before any pinned allocation
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -238,12 +286,28 @@ def run_ours(args):
         codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs, d_grp=d_grp)
         codec.decode_enqueue(p, d_comp, comp_bytes, d_offs, nrsi, d_back, raw.size, d_grp=d_grp)
 
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     for _ in range(args.warmup):
         step()
         if sharded is not None:
             sharded.encode(d_raw, raw.size)
     torch.cuda.synchronize()
+    stitch_checked = None
+    if sharded is not None:
+        # The bytes this rank owns of the ONE stream must be what a single coder writes there: code the
+        # shard again, seeded with the stream state the plan says precedes it (bit phase, k, the
+        # predecessor's bits of the shared word), and compare.
+        plan = sharded.encode(d_raw, raw.size)
+        owned = sharded.owned_bytes()
+        d_chk = torch.zeros(cap + 8, dtype=torch.uint8, device="cuda")
+        codec.encode_enqueue(p, d_raw, raw.size, d_chk, None,
+                             carry=L.Carry(plan.bit_offset & 31, plan.k_in, plan.head_or))
+        st, _, _ = codec.encode_finish()
+        ok = st == 0 and bool(torch.equal(d_chk[: owned.numel()], owned))
+        t = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        stitch_checked = bool(t.item())
+        assert stitch_checked, "a rank's bytes of the stitched stream differ from the single-coder stream"
+        del d_chk
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -302,41 +366,91 @@ def run_ours(args):
     ms_per_step = elapsed_ms / args.steps
     value = 2 * raw_total / (ms_per_step * 1e-3) / 1e9
 
-    # ---- e2e: libaec-facing host-pointer ABI, pinned host buffers ----
-    h_raw = torch.from_numpy(raw).pin_memory()
-    h_comp = torch.empty(cap, dtype=torch.uint8).pin_memory()
-    h_back = torch.empty(raw.size + 16, dtype=torch.uint8).pin_memory()
-    h_offs = torch.empty(nrsi, dtype=torch.int64).pin_memory()
-    e2e_steps = max(1, min(args.steps, 5))
+    # ---- e2e: the reference's own entry points (include/libaec.h) on host buffers ----
+    import ctypes as C
+    lib = L.load_library()
 
-    def e2e_step():
-        st, n, noff = codec.encode_host(p, h_raw.data_ptr(), raw.size, h_comp.data_ptr(), cap,
-                                        h_offs.data_ptr(), nrsi)
-        assert st == 0 and n == comp_bytes
-        st, m = codec.decode_host(p, h_comp.data_ptr(), n, h_back.data_ptr(), raw.size,
-                                  h_offs.data_ptr(), noff)
-        assert st == 0 and m == raw.size
+    def stream_for(src_ptr, src_len, dst_ptr, dst_len):
+        s = L.AecStream()
+        s.bits_per_sample, s.block_size, s.rsi, s.flags = p.bits_per_sample, p.block_size, p.rsi, p.flags
+        s.next_in, s.avail_in, s.next_out, s.avail_out = src_ptr, src_len, dst_ptr, dst_len
+        return s
 
-    if args.device_only:
-        e2e_steps = 0
-        e2e_s = float("inf")
-    else:
-        e2e_step()
+    def plugin_round_trip(raw_ptr, comp_ptr, back_ptr, offs=None):
+        """aec_buffer_encode + aec_buffer_decode (offs: the offsets extension instead)."""
+        s = stream_for(raw_ptr, raw.size, comp_ptr, cap)
+        if offs is None:
+            assert lib.aec_buffer_encode(C.byref(s)) == 0
+        else:
+            assert lib.aec_encode_init(C.byref(s)) == 0
+            lib.aec_encode_enable_offsets(C.byref(s))
+            assert lib.aec_encode(C.byref(s), C.c_int(L.AEC_FLUSH)) == 0
+            n = C.c_size_t(0)
+            lib.aec_encode_count_offsets(C.byref(s), C.byref(n))
+            assert n.value == nrsi
+            lib.aec_encode_get_offsets(C.byref(s), C.c_void_p(offs), C.c_size_t(nrsi))
+            assert lib.aec_encode_end(C.byref(s)) == 0
+        n_comp = s.total_out
+        assert n_comp == comp_bytes
+        d = stream_for(comp_ptr, n_comp, back_ptr, raw.size)
+        if offs is None:
+            assert lib.aec_buffer_decode(C.byref(d)) == 0
+        else:
+            assert lib.aec_decode_init(C.byref(d)) == 0
+            lib.aec_decode_set_offsets(C.byref(d), C.c_void_p(offs), C.c_size_t(nrsi))
+            assert lib.aec_decode(C.byref(d), C.c_int(L.AEC_FLUSH)) == 0
+            lib.aec_decode_end(C.byref(d))
+        assert d.total_out == raw.size
+
+    def time_e2e(fn, steps):
+        fn()                                     # untimed first call (allocations inside the library)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / steps
+        if dist is not None:
+            t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return 2 * raw_total / sec / 1e9, sec
+
+    e2e = e2e_pageable = e2e_indexed = pcie = None
+    if not args.device_only:
+        e2e_steps = max(1, min(args.steps, 5))
+        h_raw = torch.from_numpy(raw).pin_memory()
+        h_comp = torch.empty(cap, dtype=torch.uint8).pin_memory()
+        h_back = torch.empty(raw.size + 16, dtype=torch.uint8).pin_memory()
+        h_offs = torch.empty(nrsi, dtype=torch.int64).pin_memory()
+        v, sec = time_e2e(lambda: plugin_round_trip(h_raw.data_ptr(), h_comp.data_ptr(), h_back.data_ptr()), e2e_steps)
         assert np.array_equal(h_back[:raw.size].numpy(), raw), "e2e round trip differs"
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    if e2e_steps:
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = 2 * raw_total / e2e_s / 1e9
+        e2e = {"value": v, "unit": UNIT, "h2d_bytes_per_step": raw.size + comp_bytes,
+               "d2h_bytes_per_step": comp_bytes + raw.size, "ms_per_step": sec * 1e3,
+               "api": "aec_buffer_encode + aec_buffer_decode (include/libaec.h, ctypes), pinned host buffers, "
+                      "decode without an index (RSI boundaries discovered on the device)"}
+        h_back.zero_()
+        v, sec = time_e2e(lambda: plugin_round_trip(h_raw.data_ptr(), h_comp.data_ptr(), h_back.data_ptr(),
+                                                    offs=h_offs.data_ptr()), e2e_steps)
+        assert np.array_equal(h_back[:raw.size].numpy(), raw), "e2e (indexed) round trip differs"
+        e2e_indexed = {"value": v, "unit": UNIT, "ms_per_step": sec * 1e3,
+                       "api": "aec_encode + aec_encode_get_offsets, aec_decode_set_offsets + aec_decode (offsets extension), pinned"}
+        n_comp = np.zeros(cap, np.uint8)
+        n_back = np.zeros(raw.size + 16, np.uint8)
+        v, sec = time_e2e(lambda: plugin_round_trip(raw.ctypes.data, n_comp.ctypes.data, n_back.ctypes.data), e2e_steps)
+        assert np.array_equal(n_back[:raw.size], raw), "e2e (pageable) round trip differs"
+        e2e_pageable = {"value": v, "unit": UNIT, "ms_per_step": sec * 1e3,
+                        "api": "aec_buffer_encode + aec_buffer_decode, pageable numpy buffers, no index"}
+        # what the copies alone cost: the same bytes, same directions, pinned, nothing else
+        def copies():
+            d_raw.copy_(h_raw, non_blocking=True); h_comp[:comp_bytes].copy_(d_comp[:comp_bytes], non_blocking=True)
+            d_comp[:comp_bytes].copy_(h_comp[:comp_bytes], non_blocking=True); h_back[:raw.size].copy_(d_back[:raw.size], non_blocking=True)
+            torch.cuda.synchronize()
+        v, sec = time_e2e(copies, e2e_steps)
+        pcie = {"value": v, "unit": UNIT, "ms_per_step": sec * 1e3,
+                "what": "cudaMemcpyAsync of the same bytes and directions back to back (pinned), all ranks at once"}
 
     if rank != 0:
         if dist is not None:
@@ -348,18 +462,23 @@ def run_ours(args):
     dec_gbs = raw.size / (dec_mean * 1e-3) / 1e9
     algo_bytes = raw.size + comp_bytes            # per launch: raw in + compressed out (encode), reverse for decode
     dominant = "aec_encode_kernel" if enc_mean >= dec_mean else "aec_decode_warp_kernel"
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            tj = json.load(f)[dominant]
-        if args.workload == "c1" and args.mib == 256:
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from an `ncu --set full` capture of THIS
+    # build (profiles/r2_traffic.json records the fingerprint of the kernel sources it was taken from);
+    # null when the sources have changed since
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("csrc") == csrc_fingerprint() and args.workload == tj.get("workload") and args.mib == tj.get("mib"):
+            k = tj["kernels"][dominant]
+            traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
+            traffic_src = tj.get("capture")
     except Exception:
         traffic = None
     dom_ms = max(enc_mean, dec_mean)
     achieved = algo_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "encode": {"ms": enc_mean, "achieved": algo_bytes / (enc_mean * 1e-3) / 1e9,
                            "frac": algo_bytes / (enc_mean * 1e-3) / 1e9 / peak},
@@ -377,17 +496,15 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "raw_bytes_per_gpu": raw.size,
-                   "compressed_bytes_per_gpu": comp_bytes, "ratio": raw.size / comp_bytes,
-                   "l2": "inputs larger than L2 (%.0f MiB raw per step vs 126 MB L2), no explicit flush" % (raw.size / 2**20),
-                   "parallelism": "rsi-shards x%d" % world, "shard_bits": shard_bits,
-                   "decode_rsis_handed_to_careful_kernel": handover, "rsis_per_gpu": nrsi},
+        "config": bench_config(args),
+        "detail": {"raw_bytes_per_gpu": raw.size, "compressed_bytes_per_gpu": comp_bytes, "ratio": raw.size / comp_bytes,
+                   "parallelism": "rsi-shards x%d" % world, "shard_bits": shard_bits, "stitch_checked": stitch_checked,
+                   "decode_rsis_handed_to_careful_kernel": handover, "rsis_per_gpu": nrsi, "numa": numa,
+                   "csrc": csrc_fingerprint()},
+        "stitch_checked": stitch_checked,
         "encode_gbs": enc_gbs * world, "decode_gbs": dec_gbs * world,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT,
-                "h2d_bytes_per_step": raw.size + comp_bytes + 8 * nrsi,
-                "d2h_bytes_per_step": comp_bytes + raw.size + 8 * nrsi,
-                "api": "aecb200_encode_host + aecb200_decode_host (what aec_buffer_encode/decode call), pinned host buffers"},
+        "e2e": e2e, "e2e_indexed": e2e_indexed, "e2e_pageable": e2e_pageable, "pcie_copy_floor": pcie,
         "gpu_launches": int(launches),
     }
     print(json.dumps(line))

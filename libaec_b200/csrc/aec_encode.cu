@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "aec_core.cuh"
 #include "aec_device.h"
@@ -225,14 +226,20 @@ __device__ __noinline__ void aec_encode_scanner(const AecEncArgs &a, uint64_t *s
         PosFn fe = shfl_posfn(fi, (int)lane - 1);
         uint32_t ke = __shfl_up_sync(FULL, ki, 1);
         if (lane == 0) { fe.has_end = 0; fe.a = 0; fe.rest = 0; ke = kident; }
-        /* carry of everything before this batch */
-        {   /* hand-over spin: a sleep quantum here would serialise the chain */
+        /* carry of everything before this batch.  Only lane 31 touches the hand-over slots (it also
+         * writes the next ones below) and passes the values on by shuffle: the other lanes never read
+         * shared memory here, so nothing depends on the lanes of a warp staying converged between
+         * the poll, the read and the publication of the next carry. */
+        uint64_t P = 0;
+        uint32_t kc = 0;
+        if (lane == 31) {   /* hand-over spin: a sleep quantum here would serialise the chain */
             uint32_t spins = 0;
             while (*s_done != (uint32_t)b) spin_guard(spins);
+            P = *reinterpret_cast<volatile uint64_t *>(&s_carry_pos[b & 1]);
+            kc = *reinterpret_cast<volatile uint32_t *>(&s_carry_k[b & 1]);
         }
-        __syncwarp();                 /* the lanes leave the spin together before the carry slot is read */
-        const uint64_t P = *reinterpret_cast<volatile uint64_t *>(&s_carry_pos[b & 1]);
-        const uint32_t kc = *reinterpret_cast<volatile uint32_t *>(&s_carry_k[b & 1]);
+        P = __shfl_sync(FULL, (unsigned long long)P, 31);
+        kc = __shfl_sync(FULL, kc, 31);
         const uint64_t pos = aec_papply(fe, P);
         const uint32_t k = aec_kapply(kc, ke);
         const uint64_t end = aec_papply(f, pos);
@@ -858,6 +865,11 @@ cudaError_t launch_variant(const AecEncArgs &a, uint32_t smem_bytes, int num_sms
     if (a.ntiles == 0) return cudaSuccess;
     /* cooperative launch: the runtime guarantees that the scanner and every worker are resident at
      * the same time (or refuses the launch) whatever else shares the device */
+    static const bool coop = getenv("AECB200_NO_COOP") == nullptr;
+    if (!coop) {
+        kern<<<(unsigned)grid, TileCfg<JT>::TB, smem_bytes, st>>>(a);
+        return cudaGetLastError();
+    }
     void *kargs[] = {const_cast<AecEncArgs *>(&a)};
     return cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(TileCfg<JT>::TB), kargs,
                                        smem_bytes, st);
