@@ -230,7 +230,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
-    numa = pin_to_gpu_numa(local)                # before any pinned allocation
+    numa = pin_to_gpu_numa(local) if not os.environ.get("AECB200_BENCH_NO_PIN") else {"numa_node": None}   # before any pinned allocation
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -289,14 +289,17 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
         if sharded is not None:
-            sharded.encode(d_raw, raw.size)
+            sharded.step_enqueue(d_raw, raw.size)
+            sharded.decode_enqueue(d_back, raw.size)
+            sharded.step_finish()
     torch.cuda.synchronize()
     stitch_checked = None
     if sharded is not None:
         # The bytes this rank owns of the ONE stream must be what a single coder writes there: code the
         # shard again, seeded with the stream state the plan says precedes it (bit phase, k, the
         # predecessor's bits of the shared word), and compare.
-        plan = sharded.encode(d_raw, raw.size)
+        sharded.step_enqueue(d_raw, raw.size)
+        plan = sharded.step_finish()
         owned = sharded.owned_bytes()
         d_chk = torch.zeros(cap + 8, dtype=torch.uint8, device="cuda")
         codec.encode_enqueue(p, d_raw, raw.size, d_chk, None,
@@ -326,11 +329,12 @@ def run_ours(args):
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record()
         if sharded is not None:
-            sharded.encode_local(d_raw, raw.size)       # independent shard encode
+            # shard encode, 32-byte all_gather (NCCL, from device memory), plan kernel, k repair and the
+            # placement at the global bit phase: enqueues only, no host round trip inside the step
+            sharded.step_enqueue(d_raw, raw.size)
             b.record()
-            sharded.decode_enqueue(d_back, raw.size)    # decode needs no exchange
-            sharded.exchange_begin()                    # 32-byte all_gather on a side stream, next to the decode
-            sharded.stitch()                            # gathered offsets -> k repair, placement
+            sharded.decode_enqueue(d_back, raw.size)    # decode needs no exchange; runs next to the placement
+            sharded.join()
         else:
             codec.encode_enqueue(p, d_raw, raw.size, d_comp, d_offs, d_grp=d_grp)
             b.record()
@@ -339,6 +343,8 @@ def run_ours(args):
         marks.append((a, b, c))
     t_end.record()
     torch.cuda.synchronize()
+    if sharded is not None:
+        sharded.step_finish()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()

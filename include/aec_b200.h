@@ -131,6 +131,23 @@ void aecb200_ctx_set_tile_limit(aecb200_ctx *ctx, uint64_t ntiles);
 int  aecb200_place_bits_device(aecb200_ctx *ctx, const void *d_src, uint64_t nbits,
                                void *d_dst, size_t dst_cap, uint64_t dst_bit, uint32_t head_or);
 
+/* The same protocol without the host inside a step (every call below only enqueues):
+ *   aecb200_ctx_set_shard_out   every shard-mode encode also writes (bits, klo, khi, tail64) -- four uint64,
+ *                               what the ranks all_gather -- to this device address;
+ *   aecb200_shard_plan_device   from the gathered 4 x world uint64 a one-thread kernel works out this rank's
+ *                               bit offset in the global stream, incoming k, predecessor bits of the shared
+ *                               word and how many leading tiles depend on k (d_plan_out, optional: eight
+ *                               uint64 = k_in, tiles to code again, bit offset, head bits, total bits, own bits);
+ *   aecb200_encode_repair_device  codes those tiles again with the true k (nothing when k_in is 0);
+ *   aecb200_place_bits_planned  moves the shard to its bit phase; global != 0: d_dst is the base of the
+ *                               whole stream (e.g. a peer GPU's buffer mapped over NVLink) and only the words
+ *                               the shard owns are written, so that the placement is the stitch. */
+void aecb200_ctx_set_shard_out(aecb200_ctx *ctx, void *d_info);
+int  aecb200_shard_plan_device(aecb200_ctx *ctx, const void *d_all, int world, int rank, void *d_plan_out);
+int  aecb200_encode_repair_device(aecb200_ctx *ctx, const aecb200_params *p, const void *d_in, size_t in_bytes,
+                                  void *d_out, size_t out_cap);
+int  aecb200_place_bits_planned(aecb200_ctx *ctx, const void *d_src, void *d_dst, size_t dst_cap, int global, int last_rank);
+
 /* Enqueue the decode of out_bytes/bytes_per_sample samples from the stream at
  * d_in using the RSI start offsets d_rsi_offsets[0..nrsi).  Asynchronous. */
 int aecb200_decode_device(aecb200_ctx *ctx, const aecb200_params *p,
@@ -165,6 +182,9 @@ int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
 void aecb200_ctx_set_scan_mode(aecb200_ctx *ctx, int mode, uint64_t window_bits);
 /* RSIs of the last scan whose length came from the tables (the rest were skimmed serially). */
 uint64_t aecb200_ctx_last_scan_fast(aecb200_ctx *ctx);
+/* RSI start offsets the last aecb200_decode_host / _resume call without an index discovered (bits from
+ * in[0]); returns their number, copies at most cap of them. */
+size_t aecb200_ctx_found_offsets(aecb200_ctx *ctx, uint64_t *dst, size_t cap);
 
 /* ---- host buffers (what the libaec.h entry points call) ------------------ */
 

@@ -80,6 +80,20 @@ int aec_encode_get_offsets(struct aec_stream *strm, size_t *offsets, size_t offs
  * and before the first aec_decode): every RSI is then decoded in parallel
  * instead of discovering the boundaries sequentially. */
 int aec_decode_set_offsets(struct aec_stream *strm, const size_t *offsets, size_t offsets_count);
+/* Offsets a decoder found on its own while decoding a stream without an index:
+ * enable after aec_decode_init, read after the stream has been decoded and
+ * before aec_decode_end. */
+int aec_decode_enable_offsets(struct aec_stream *strm);
+int aec_decode_count_offsets(struct aec_stream *strm, size_t *count);
+int aec_decode_get_offsets(struct aec_stream *strm, size_t *offsets, size_t offsets_count);
+/* Random access: decode `size` bytes of samples starting at byte `pos` of the
+ * uncompressed data.  strm->next_in / avail_in describe the WHOLE compressed
+ * stream, next_out / avail_out the destination (avail_out >= size); pos and
+ * size are multiples of the sample size.  Only the RSIs that hold the range are
+ * read and decoded.  (Same signature as aec_decode_range of later libaec
+ * releases; not in the 0.3.4 reference) */
+int aec_decode_range(struct aec_stream *strm, const size_t *rsi_offsets, size_t rsi_offsets_count,
+                     size_t pos, size_t size);
 
 #ifdef __cplusplus
 }

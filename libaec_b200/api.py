@@ -85,7 +85,8 @@ _libsz = None
 LIBAEC_SYMBOLS = ["aec_encode_init", "aec_encode", "aec_encode_end", "aec_decode_init", "aec_decode",
                   "aec_decode_end", "aec_buffer_encode", "aec_buffer_decode",
                   "aec_encode_enable_offsets", "aec_encode_count_offsets", "aec_encode_get_offsets",
-                  "aec_decode_set_offsets"]
+                  "aec_decode_set_offsets", "aec_decode_enable_offsets", "aec_decode_count_offsets",
+                  "aec_decode_get_offsets", "aec_decode_range"]
 DEVICE_SYMBOLS = ["aecb200_device_count", "aecb200_current_device", "aecb200_ctx_device", "aecb200_ctx_create", "aecb200_ctx_destroy",
                   "aecb200_ctx_set_stream", "aecb200_last_error", "aecb200_ctx_set_encode_padding",
                   "aecb200_ctx_launches", "aecb200_encode_bound", "aecb200_encode_device",
@@ -95,7 +96,9 @@ DEVICE_SYMBOLS = ["aecb200_device_count", "aecb200_current_device", "aecb200_ctx
                   "aecb200_encode_shard_info", "aecb200_ctx_set_tile_limit", "aecb200_place_bits_device",
                   "aecb200_encode_device_indexed", "aecb200_decode_device_indexed", "aecb200_group_index_entries",
                   "aecb200_ctx_set_careful_decode", "aecb200_ctx_last_handover",
-                  "aecb200_ctx_set_pipeline_piece", "aecb200_ctx_set_scan_mode", "aecb200_ctx_last_scan_fast"]
+                  "aecb200_ctx_set_pipeline_piece", "aecb200_ctx_set_scan_mode", "aecb200_ctx_last_scan_fast",
+                  "aecb200_ctx_found_offsets", "aecb200_ctx_set_shard_out", "aecb200_shard_plan_device",
+                  "aecb200_encode_repair_device", "aecb200_place_bits_planned"]
 SZ_SYMBOLS = ["SZ_BufftoBuffCompress", "SZ_BufftoBuffDecompress", "SZ_encoder_enabled", "SZ_Compress"]
 
 
@@ -122,6 +125,8 @@ def load_library() -> C.CDLL:
         lib.aecb200_ctx_set_pipeline_piece.restype = None
         lib.aecb200_ctx_set_scan_mode.restype = None
         lib.aecb200_ctx_last_scan_fast.restype = C.c_uint64
+        lib.aecb200_ctx_found_offsets.restype = C.c_size_t
+        lib.aecb200_ctx_set_shard_out.restype = None
         _lib = lib
     return _lib
 
@@ -212,6 +217,49 @@ def buffer_decode(p: Params, comp, out_size: int, offsets=None):
             st = lib.aec_decode(C.byref(s), C.c_int(AEC_FLUSH))
             lib.aec_decode_end(C.byref(s))
     return {"status": st, "out": out[:s.total_out].copy(), "total_in": s.total_in}
+
+
+def decode_range(p: Params, comp, offsets, pos: int, size: int):
+    """aec_decode_range: `size` bytes of samples from byte `pos` of the uncompressed data."""
+    lib = load_library()
+    src = _u8(comp)
+    out = np.zeros(max(size, 1), dtype=np.uint8)
+    offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+    s = _stream(p)
+    s.next_in = src.ctypes.data
+    s.avail_in = src.size
+    s.next_out = out.ctypes.data
+    s.avail_out = size
+    st = lib.aec_decode_init(C.byref(s))
+    if st != AEC_OK:
+        return {"status": st, "out": out[:0]}
+    st = lib.aec_decode_range(C.byref(s), offs.ctypes.data_as(C.c_void_p), C.c_size_t(offs.size),
+                              C.c_size_t(pos), C.c_size_t(size))
+    lib.aec_decode_end(C.byref(s))
+    return {"status": st, "out": out[:s.total_out].copy()}
+
+
+def buffer_decode_discover(p: Params, comp, out_size: int):
+    """aec_decode on a stream without an index, returning the RSI offsets the decoder discovered."""
+    lib = load_library()
+    src = _u8(comp)
+    out = np.zeros(max(out_size, 1), dtype=np.uint8)
+    s = _stream(p)
+    s.next_in = src.ctypes.data
+    s.avail_in = src.size
+    s.next_out = out.ctypes.data
+    s.avail_out = out_size
+    st = lib.aec_decode_init(C.byref(s))
+    if st != AEC_OK:
+        return {"status": st, "out": out[:0], "offsets": np.zeros(0, np.uint64)}
+    lib.aec_decode_enable_offsets(C.byref(s))
+    st = lib.aec_decode(C.byref(s), C.c_int(AEC_FLUSH))
+    n = C.c_size_t(0)
+    lib.aec_decode_count_offsets(C.byref(s), C.byref(n))
+    offs = np.zeros(max(n.value, 1), dtype=np.uint64)
+    lib.aec_decode_get_offsets(C.byref(s), offs.ctypes.data_as(C.c_void_p), C.c_size_t(n.value))
+    lib.aec_decode_end(C.byref(s))
+    return {"status": st, "out": out[:s.total_out].copy(), "offsets": offs[:n.value]}
 
 
 # --------------------------------------------------------------------------
@@ -406,6 +454,29 @@ class DeviceCodec:
         lo, hi, fc, tail = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
         self.lib.aecb200_encode_shard_info(self.ctx, C.byref(lo), C.byref(hi), C.byref(fc), C.byref(tail))
         return int(lo.value), int(hi.value), int(fc.value), int(tail.value)
+
+    def set_shard_out(self, d_info):
+        """Device tensor (4 x int64) that receives (bits, klo, khi, tail64) of every shard-mode encode."""
+        self.lib.aecb200_ctx_set_shard_out(self.ctx, C.c_void_p(d_info.data_ptr()) if d_info is not None else None)
+
+    def shard_plan(self, d_all, world: int, rank: int, d_plan=None):
+        st = self.lib.aecb200_shard_plan_device(self.ctx, C.c_void_p(d_all.data_ptr()), C.c_int(world), C.c_int(rank),
+                                                C.c_void_p(d_plan.data_ptr()) if d_plan is not None else None)
+        return self._check(st, "aecb200_shard_plan_device")
+
+    def encode_repair(self, p: Params, d_in, in_bytes: int, d_out):
+        prm = _Params(p.bits_per_sample, p.block_size, p.rsi, p.flags)
+        st = self.lib.aecb200_encode_repair_device(self.ctx, C.byref(prm), C.c_void_p(d_in.data_ptr()), C.c_size_t(in_bytes),
+                                                   C.c_void_p(d_out.data_ptr()), C.c_size_t(d_out.numel() * d_out.element_size()))
+        return self._check(st, "aecb200_encode_repair_device")
+
+    def place_planned(self, d_src, d_dst, dst_ptr: int | None = None, dst_cap: int | None = None,
+                      global_stream: bool = False, last_rank: bool = False):
+        ptr = dst_ptr if dst_ptr is not None else d_dst.data_ptr()
+        cap = dst_cap if dst_cap is not None else d_dst.numel() * d_dst.element_size()
+        st = self.lib.aecb200_place_bits_planned(self.ctx, C.c_void_p(d_src.data_ptr()), C.c_void_p(ptr), C.c_size_t(cap),
+                                                 C.c_int(int(global_stream)), C.c_int(int(last_rank)))
+        return self._check(st, "aecb200_place_bits_planned")
 
     def set_tile_limit(self, ntiles: int):
         self.lib.aecb200_ctx_set_tile_limit(self.ctx, C.c_uint64(ntiles))

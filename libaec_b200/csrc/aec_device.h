@@ -72,7 +72,16 @@ struct AecEncArgs {
     uint32_t tile_rsi_shift;    /* log2(TB / RP) when RP < TB */
     uint32_t grp_magic;         /* floor(2^32 / grp_G) + 1: b / grp_G == umulhi(b, grp_magic) for b < 4096; 0 when grp_G == 1 */
     uint64_t *result;           /* [0] end bit, [1] k after the last block, [2..5] shard summary (lo, hi, first constant tile, last 64 bits) */
+    /* multi-GPU shards, everything decided on the device (no host round trip inside a step): */
+    uint64_t *shard_out;        /* optional [4]: (bits, klo, khi, last 64 bits) of this shard, what the ranks all_gather */
+    const uint64_t *dyn;        /* optional (k repair planned on the device): [0] incoming k, replaces seed_k; [1] leading tiles
+                                 * that have to be coded again: the launch does nothing unless dyn_lo < dyn[1] <= dyn_hi */
+    uint64_t dyn_lo, dyn_hi;
 };
+
+/* what aec_shard_plan_kernel leaves for the repair and placement launches of a shard */
+enum { PLAN_K_IN = 0, PLAN_REPAIR_TILES = 1, PLAN_BIT_OFFSET = 2, PLAN_HEAD_OR = 3, PLAN_TOTAL_BITS = 4, PLAN_MY_BITS = 5,
+       PLAN_WORDS = 8 };
 
 /* Arguments of one decode launch. */
 struct AecDecArgs {
@@ -116,8 +125,9 @@ struct AecSkimArgs {
 };
 uint32_t aec_skim_levels(const AecCfg &c);
 uint64_t aec_skim_margin_bits(const AecCfg &c);
-/* level-0 tables, doubling, RSI lengths and the walk of one window */
+/* level-0 tables, doubling and RSI lengths of one window; then the walk through it */
 cudaError_t aec_skim_window_launch(const AecSkimArgs &a, cudaStream_t st);
+cudaError_t aec_skim_walk_launch(const AecSkimArgs &a, cudaStream_t st);
 
 uint32_t aec_encode_tile_blocks(uint32_t J);
 uint32_t aec_encode_staging_words(const AecCfg &c);
@@ -126,6 +136,13 @@ cudaError_t aec_encode_launch(const AecEncArgs &a, int num_sms, cudaStream_t st)
 cudaError_t aec_encode_summary_launch(const AecEncArgs &a, cudaStream_t st);
 /* copy nbits bits from src (bit 0 = MSB of word 0) to dst starting at bit dst_bit; dst words are private to the caller */
 cudaError_t aec_place_bits_launch(const uint32_t *src, uint64_t nbits, uint32_t *dst, uint64_t dst_bit, uint64_t dst_cap_words, uint32_t head_or, cudaStream_t st);
+/* plan[PLAN_*] from the gathered (bits, klo, khi, tail64) of all shards; result[4] = this shard's first constant tile */
+cudaError_t aec_shard_plan_launch(const uint64_t *all, uint32_t world, uint32_t rank, const uint64_t *result, uint64_t *plan, cudaStream_t st);
+/* placement with bit offset, length and head bits read from the plan; global != 0: dst is the base of the whole
+ * stream (possibly a peer GPU's buffer) and only the words this shard owns are written, else dst[0] is the word
+ * that holds the shard's first bit */
+cudaError_t aec_place_bits_planned_launch(const uint32_t *src, const uint64_t *plan, uint32_t *dst, uint64_t dst_cap_words,
+                                          uint32_t global, uint32_t last_rank, int num_sms, cudaStream_t st);
 
 cudaError_t aec_decode_launch(const AecDecArgs &a, int num_sms, cudaStream_t st);
 uint32_t aec_decode_group_blocks(const AecCfg &c);     /* G = ceil(rsi / 32) */

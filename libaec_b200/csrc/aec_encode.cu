@@ -157,18 +157,24 @@ __device__ __forceinline__ void load_block(const AecCfg &c, const uint8_t *in, u
 }
 
 /* Every spin is bounded.  The kernel is launched cooperatively, so the scanner CTA and all worker CTAs
- * are resident together and a poll is normally answered within microseconds; a wait that is long
- * anyway (debugger, sanitizer, a preempted context) backs off with nanosleep instead of burning issue
- * slots, and only a wait of tens of seconds -- a broken protocol -- aborts the launch (the host sees a
+ * are resident together and a poll is normally answered within microseconds.  The scanner (its own
+ * function, off the workers' register budget) backs off with nanosleep when a wait gets long anyway
+ * (debugger, sanitizer, a preempted context); the workers, which sit exactly at 64 registers, only
+ * count.  A wait of the order of a minute -- a broken protocol -- aborts the launch (the host sees a
  * launch failure) instead of hanging the device. */
-constexpr uint32_t SPIN_FAST = 1u << 16;     /* polls before backing off */
-constexpr uint32_t SPIN_LIMIT = 1u << 26;    /* then this many sleeps of ~1 us */
-__device__ __forceinline__ void spin_guard(uint32_t &n)
+constexpr uint32_t SPIN_FAST = 1u << 16;     /* scanner: polls before backing off */
+constexpr uint32_t SPIN_LIMIT = 1u << 26;    /* scanner: then this many sleeps of ~1 us */
+constexpr uint32_t SPIN_WORKER = 1u << 28;   /* workers: polls of an L2 word, ~0.3 us each */
+__device__ __forceinline__ void spin_guard_scanner(uint32_t &n)
 {
     if (++n > SPIN_FAST) {
         __nanosleep(1000);
         if (n > SPIN_FAST + SPIN_LIMIT) __trap();
     }
+}
+__device__ __forceinline__ void spin_guard(uint32_t &n)
+{
+    if (++n > SPIN_WORKER) __trap();
 }
 
 /* ---- dedicated scanner ------------------------------------------------------
@@ -176,33 +182,49 @@ __device__ __forceinline__ void spin_guard(uint32_t &n)
  * offset + incoming k of every tile).  Worker CTAs never look back: they
  * publish their aggregate, pack their tile, and read their prefix when they
  * are ready to write.  Warp w of the scanner owns the batches w, w+NW, ... of
- * 32 consecutive tiles: it loads the 32 aggregates and scans them on its own,
- * then takes the running (position, k) carry from the previous batch through
- * shared memory, writes the 32 prefixes and passes the carry on.  The serial
- * part of the chain is that hand-over only (no memory round trip per tile). */
-template <int NW>
+ * 32 x TPL consecutive tiles: every lane loads TPL aggregates and composes them,
+ * the warp scans the lane totals, lane 31 takes the running (position, k) carry
+ * from the previous batch through shared memory and passes the carry behind this
+ * batch on at once (it only needs the batch totals for that); then the lanes
+ * write their tiles' prefixes.  The serial part of the chain is that hand-over
+ * only, once per 32 x TPL tiles: with one hand-over per 32 tiles it was what
+ * bounded the whole encoder (0.41 us per batch against 0.42 us in which the
+ * workers produce 32 tiles: profiles/r2_summary.md). */
+template <int NW, int TPL>
 __device__ __noinline__ void aec_encode_scanner(const AecEncArgs &a, uint64_t *s_carry_pos, uint32_t *s_carry_k,
                                                 volatile uint32_t *s_done)
 {
     const AecCfg &c = a.cfg;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t kident = aec_kpair(0, c.kmax);
-    const uint64_t nbatch = (a.ntiles + 31) / 32;
-    if (threadIdx.x == 0) { s_carry_pos[0] = a.seed_bits; s_carry_k[0] = a.seed_k; *s_done = 0; }
+    const uint64_t ntiles = a.ntiles;
+    constexpr uint64_t PER = 32ull * TPL;
+    const uint64_t nbatch = (ntiles + PER - 1) / PER;
+    if (threadIdx.x == 0) { s_carry_pos[0] = a.seed_bits; s_carry_k[0] = a.dyn ? (uint32_t)a.dyn[0] : a.seed_k; *s_done = 0; }
     __syncthreads();
     for (uint64_t b = warp; b < nbatch; b += NW) {
-        const uint64_t t = b * 32 + lane;
-        uint64_t dv = ST_AGG | ((uint64_t)c.kmax << 7);           /* identity beyond the last tile */
-        if (t < a.ntiles) {
-            dv = ld_volatile_u64(&a.desc[t]);
+        const uint64_t t0 = b * PER + (uint64_t)lane * TPL;
+        uint64_t dv[TPL];
+#pragma unroll
+        for (int i = 0; i < TPL; i++)                             /* all loads in flight together */
+            dv[i] = (t0 + i < ntiles) ? ld_volatile_u64(&a.desc[t0 + i])
+                                      : (ST_AGG | ((uint64_t)c.kmax << 7));   /* identity beyond the last tile */
+#pragma unroll
+        for (int i = 0; i < TPL; i++) {
             uint32_t spins = 0;
-            while ((dv & 3) == 0) { dv = ld_volatile_u64(&a.desc[t]); spin_guard(spins); }
+            while ((dv[i] & 3) == 0) { dv[i] = ld_volatile_u64(&a.desc[t0 + i]); spin_guard_scanner(spins); }
         }
         __syncwarp();
-        PosFn f; uint32_t kj;
-        desc_unpack(dv, f, kj);
-        /* inclusive scan over the batch (lower lane = earlier tile) */
-        PosFn fi = f; uint32_t ki = kj;
+        PosFn f[TPL]; uint32_t kj[TPL];
+#pragma unroll
+        for (int i = 0; i < TPL; i++) desc_unpack(dv[i], f[i], kj[i]);
+        /* the lane's own tiles composed, then the inclusive scan over the lanes (lower lane = earlier tiles) */
+        PosFn fi = f[0]; uint32_t ki = kj[0];
+#pragma unroll
+        for (int i = 1; i < TPL; i++) {
+            if (c.pad) fi = aec_pcompose(fi, f[i]); else fi.a += f[i].a;
+            ki = aec_kcompose(ki, kj[i]);
+        }
         if (c.pad) {
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
@@ -210,7 +232,7 @@ __device__ __noinline__ void aec_encode_scanner(const AecEncArgs &a, uint64_t *s
                 if (lane >= (uint32_t)off) fi = aec_pcompose(o, fi);
             }
         } else {
-            uint32_t li = (uint32_t)f.a;                          /* 32 tiles x < 2^21 bits fit 32 bits */
+            uint32_t li = (uint32_t)fi.a;                         /* 32 x TPL tiles of < 2^21 bits fit 32 bits */
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 uint32_t o = __shfl_up_sync(FULL, li, off);
@@ -226,41 +248,52 @@ __device__ __noinline__ void aec_encode_scanner(const AecEncArgs &a, uint64_t *s
         PosFn fe = shfl_posfn(fi, (int)lane - 1);
         uint32_t ke = __shfl_up_sync(FULL, ki, 1);
         if (lane == 0) { fe.has_end = 0; fe.a = 0; fe.rest = 0; ke = kident; }
-        /* carry of everything before this batch.  Only lane 31 touches the hand-over slots (it also
-         * writes the next ones below) and passes the values on by shuffle: the other lanes never read
-         * shared memory here, so nothing depends on the lanes of a warp staying converged between
-         * the poll, the read and the publication of the next carry. */
+        /* carry of everything before this batch.  Only lane 31 touches the hand-over slots and passes
+         * the values on by shuffle: the other lanes never read shared memory here, so nothing depends
+         * on the lanes of a warp staying converged between the poll, the read and the publication of
+         * the next carry (an earlier version let every lane read the slot: the batch after next
+         * could overwrite it before a lane that ran late had read it).  Lane 31 holds the batch
+         * totals (its inclusive scan values), so the next carry leaves before anything else is done. */
         uint64_t P = 0;
         uint32_t kc = 0;
         if (lane == 31) {   /* hand-over spin: a sleep quantum here would serialise the chain */
             uint32_t spins = 0;
-            while (*s_done != (uint32_t)b) spin_guard(spins);
+            while (*s_done != (uint32_t)b) spin_guard_scanner(spins);
             P = *reinterpret_cast<volatile uint64_t *>(&s_carry_pos[b & 1]);
             kc = *reinterpret_cast<volatile uint32_t *>(&s_carry_k[b & 1]);
+            const uint64_t bend = aec_papply(fi, P);
+            const uint32_t bk = aec_kapply(kc, ki);
+            *reinterpret_cast<volatile uint64_t *>(&s_carry_pos[(b + 1) & 1]) = bend;
+            *reinterpret_cast<volatile uint32_t *>(&s_carry_k[(b + 1) & 1]) = bk;
+            __threadfence_block();
+            *s_done = (uint32_t)(b + 1);
+            if (b + 1 == nbatch && ntiles == a.ntiles_total && !a.dyn) {
+                /* the last batch: identity tiles beyond the end keep the totals */
+                a.result[0] = bend; a.result[1] = bk;
+            }
         }
         P = __shfl_sync(FULL, (unsigned long long)P, 31);
         kc = __shfl_sync(FULL, kc, 31);
-        const uint64_t pos = aec_papply(fe, P);
-        const uint32_t k = aec_kapply(kc, ke);
-        const uint64_t end = aec_papply(f, pos);
-        if (lane == 31) {
-            *reinterpret_cast<volatile uint64_t *>(&s_carry_pos[(b + 1) & 1]) = end;
-            *reinterpret_cast<volatile uint32_t *>(&s_carry_k[(b + 1) & 1]) = aec_kapply(k, kj);
-            __threadfence_block();
-            *s_done = (uint32_t)(b + 1);
-            if (b + 1 == nbatch && a.ntiles == a.ntiles_total) {
-                /* lane 31 of the last batch: identity tiles beyond the end keep the totals */
-                a.result[0] = end; a.result[1] = aec_kapply(k, kj);
+        uint64_t pos = aec_papply(fe, P);
+        uint32_t k = aec_kapply(kc, ke);
+#pragma unroll
+        for (int i = 0; i < TPL; i++) {
+            const uint64_t end = aec_papply(f[i], pos);
+            if (t0 + i < ntiles) {
+                st_volatile_u64(&a.pref[t0 + i], desc_pack_prefix(pos, k));
+                a.tile_end[t0 + i] = end;
             }
-        }
-        if (t < a.ntiles) {
-            st_volatile_u64(&a.pref[t], desc_pack_prefix(pos, k));
-            a.tile_end[t] = end;
+            pos = end;
+            k = aec_kapply(k, kj[i]);
         }
     }
 }
 
 /* ---- the kernel ----------------------------------------------------------- */
+
+#ifndef AEC_SCAN_TPL
+#define AEC_SCAN_TPL 1      /* tiles per scanner lane: one carry hand-over per 32 x AEC_SCAN_TPL tiles */
+#endif
 
 template <int JT>
 struct TileCfg {
@@ -341,11 +374,17 @@ aec_encode_kernel(const __grid_constant__ AecEncArgs a)
     __shared__ uint32_t s_cp[8];
     __shared__ unsigned long long s_base_cur;/* late mode: absolute bit offset of the tile being packed */
 
+    if (a.dyn) {
+        /* a repair launch runs only when the number of tiles the device-side plan wants coded again
+         * falls into this launch's window (nothing at all when the incoming k was 0) */
+        const uint64_t want = a.dyn[1];
+        if (want <= a.dyn_lo || want > a.dyn_hi) return;
+    }
     if (blockIdx.x == 0) {                  /* CTA 0 is the scanner */
         __shared__ unsigned long long s_cpos[2];
         __shared__ uint32_t s_ck[2];
         __shared__ uint32_t s_sdone;
-        aec_encode_scanner<NWARP>(a, reinterpret_cast<uint64_t *>(s_cpos), s_ck, &s_sdone);
+        aec_encode_scanner<NWARP, AEC_SCAN_TPL>(a, reinterpret_cast<uint64_t *>(s_cpos), s_ck, &s_sdone);
         return;
     }
     /* where a claimed tile sits (thread 0 only) */
@@ -821,6 +860,65 @@ __global__ void aec_encode_summary_kernel(const AecEncArgs a)
         uint64_t t64 = padb ? ((lo8 >> padb) | (hi1 << (64u - padb))) : lo8;
         if (total < 64) t64 &= (total ? ((1ull << total) - 1ull) : 0ull);
         a.result[5] = t64;
+        if (a.shard_out) {
+            a.shard_out[0] = a.result[0];               /* bits of the shard (coded from bit 0) */
+            a.shard_out[1] = aec_klo(acc); a.shard_out[2] = aec_khi(acc); a.shard_out[3] = t64;
+        }
+    }
+}
+
+/* One thread turns the gathered shard summaries into this rank's plan: exclusive scan of the bit lengths,
+ * clamp chain of k, the predecessor's bits of the shared word (libaec_b200/parallel.py
+ * plan_shards is the host model the gloo tests pin). */
+__global__ void aec_shard_plan_kernel(const uint64_t *all, uint32_t world, uint32_t rank, const uint64_t *result, uint64_t *plan)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint64_t off = 0, total = 0, prev_tail = 0;
+    uint32_t k = 0;
+    uint64_t my_off = 0, my_bits = 0, my_head = 0;
+    uint32_t my_k = 0;
+    for (uint32_t r = 0; r < world; r++) {
+        const uint64_t bits = all[4 * r];
+        if (r == rank) {
+            my_off = off; my_k = k; my_bits = bits;
+            const uint32_t n = (uint32_t)(off & 31u);
+            my_head = n ? ((prev_tail & ((1ull << n) - 1ull)) << (32u - n)) & 0xFFFFFFFFull : 0ull;
+        }
+        k = aec_clampu(k, (uint32_t)all[4 * r + 1], (uint32_t)all[4 * r + 2]);
+        off += bits;
+        if (bits) prev_tail = all[4 * r + 3];
+        total += bits;
+    }
+    plan[PLAN_K_IN] = my_k;
+    plan[PLAN_REPAIR_TILES] = (my_k != 0u && my_bits) ? result[4] + 1ull : 0ull;
+    plan[PLAN_BIT_OFFSET] = my_off;
+    plan[PLAN_HEAD_OR] = my_head;
+    plan[PLAN_TOTAL_BITS] = total;
+    plan[PLAN_MY_BITS] = my_bits;
+}
+
+/* aec_place_bits_kernel with everything read from the plan */
+__global__ void aec_place_bits_planned_kernel(const uint32_t *src, const uint64_t *plan, uint32_t *dst, uint64_t dst_cap_words,
+                                              uint32_t global, uint32_t last_rank)
+{
+    const uint64_t nbits = plan[PLAN_MY_BITS];
+    const uint64_t dst_bit = global ? plan[PLAN_BIT_OFFSET] : (plan[PLAN_BIT_OFFSET] & 31ull);
+    const uint32_t head_or = (uint32_t)plan[PLAN_HEAD_OR];
+    const uint64_t w0 = dst_bit >> 5;
+    const uint32_t sh = (uint32_t)(dst_bit & 31u);
+    const uint64_t endbit = dst_bit + nbits;
+    /* words written: every word the shard touches, or -- when the destination is the whole stream -- the
+     * words it owns: its partial last word belongs to the successor, who completes it */
+    const uint64_t we = (global && !last_rank) ? (endbit >> 5) : ((endbit + 31) >> 5);
+    const uint64_t nw = we > w0 ? we - w0 : 0;
+    const uint64_t src_words = (nbits + 31) >> 5;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t hi = (i >= 1 && i - 1 < src_words) ? __byte_perm(src[i - 1], 0, 0x0123) : 0u;
+        uint32_t lo = (i < src_words) ? __byte_perm(src[i], 0, 0x0123) : 0u;
+        uint32_t v = sh ? ((hi << (32u - sh)) | (lo >> sh)) : lo;
+        if (w0 + i == (endbit >> 5) && (endbit & 31u)) v &= ~(0xFFFFFFFFu >> (endbit & 31u));
+        if (i == 0 && sh) v = (v & (0xFFFFFFFFu >> sh)) | (head_or & ~(0xFFFFFFFFu >> sh));
+        if (w0 + i < dst_cap_words) dst[w0 + i] = __byte_perm(v, 0, 0x0123);
     }
 }
 
@@ -906,6 +1004,20 @@ uint32_t aec_encode_staging_words(const AecCfg &c)
 cudaError_t aec_encode_summary_launch(const AecEncArgs &a, cudaStream_t st)
 {
     aec_encode_summary_kernel<<<1, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t aec_shard_plan_launch(const uint64_t *all, uint32_t world, uint32_t rank, const uint64_t *result, uint64_t *plan,
+                                  cudaStream_t st)
+{
+    aec_shard_plan_kernel<<<1, 32, 0, st>>>(all, world, rank, result, plan);
+    return cudaGetLastError();
+}
+
+cudaError_t aec_place_bits_planned_launch(const uint32_t *src, const uint64_t *plan, uint32_t *dst, uint64_t dst_cap_words,
+                                          uint32_t global, uint32_t last_rank, int num_sms, cudaStream_t st)
+{
+    aec_place_bits_planned_kernel<<<(unsigned)(num_sms * 8), 256, 0, st>>>(src, plan, dst, dst_cap_words, global, last_rank);
     return cudaGetLastError();
 }
 

@@ -63,7 +63,8 @@ struct aecb200_ctx {
     uint64_t launches = 0;
     char err[256] = {0};
 
-    DevBuf grp, rsi_list, desc, pref, headc, tailc, tile_end, tile_kagg, misc, in_stage, out_stage, offs, rsi_count;
+    DevBuf grp, rsi_list, desc, pref, headc, tailc, tile_end, tile_kagg, misc, in_stage, out_stage, offs, rsi_count, plan;
+    void *shard_out = nullptr;           /* device: (bits, klo, khi, tail64) of every shard-mode encode */
     uint64_t tile_limit = 0;             /* next encode codes only this many leading tiles (k repair) */
     bool want_summary = false;
     bool careful_only = false;           /* decode with the lane-per-RSI kernel only (tests) */
@@ -72,6 +73,8 @@ struct aecb200_ctx {
      * `stream`, downloads on s_out (PCIe carries both directions at once) */
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaStream_t s_idx[4] = {nullptr, nullptr, nullptr, nullptr};   /* group-index builds of the decode pipeline */
+    cudaStream_t s_walk = nullptr;                                   /* RSI boundary walk (aec_skim.cu) */
+    cudaEvent_t ev_skim[4] = {nullptr, nullptr, nullptr, nullptr};   /* tables ready [0,1], walk done [2,3] per table set */
     std::vector<cudaEvent_t> ev;
     size_t pipe_piece = (size_t)16 << 20; /* bytes of raw samples per piece; 0 = never pipeline */
 
@@ -80,6 +83,7 @@ struct aecb200_ctx {
     int scan_mode = 0;                   /* 0 auto, 1 always the one-thread scan, 2 always the parallel tables */
     uint64_t scan_window_bits = 1ull << 25;
     uint64_t scan_end = 0, scan_fast = 0;
+    std::vector<uint64_t> found_offs;    /* RSI offsets the last host decode discovered itself (bits from in[0]) */
 
     /* bookkeeping of the last enqueued operation */
     uint64_t enc_out_cap_bits = 0;
@@ -235,12 +239,14 @@ void aecb200_ctx_destroy(aecb200_ctx *ctx)
     ctx->tile_kagg.release(); ctx->pref.release(); ctx->grp.release(); ctx->rsi_list.release();
     ctx->desc.release(); ctx->headc.release(); ctx->tailc.release(); ctx->tile_end.release();
     ctx->misc.release(); ctx->in_stage.release(); ctx->out_stage.release(); ctx->offs.release();
-    ctx->rsi_count.release(); ctx->skim_tab.release();
+    ctx->rsi_count.release(); ctx->skim_tab.release(); ctx->plan.release();
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     for (cudaStream_t st : ctx->s_idx) if (st) cudaStreamDestroy(st);
+    if (ctx->s_walk) cudaStreamDestroy(ctx->s_walk);
+    for (cudaEvent_t e : ctx->ev_skim) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -300,11 +306,30 @@ size_t aecb200_group_index_entries(const aecb200_params *p, size_t in_bytes)
     return ((ns + c.R - 1) / c.R) * 32;
 }
 
+static int encode_device_impl(aecb200_ctx *ctx, const aecb200_params *p, const void *d_in, size_t in_bytes,
+                              void *d_out, size_t out_cap, const aecb200_carry *carry, uint64_t *d_rsi_offsets,
+                              uint64_t *d_grp_index, bool planned_repair);
+
 int aecb200_encode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
                                   const void *d_in, size_t in_bytes,
                                   void *d_out, size_t out_cap,
                                   const aecb200_carry *carry, uint64_t *d_rsi_offsets,
                                   uint64_t *d_grp_index)
+{
+    return encode_device_impl(ctx, p, d_in, in_bytes, d_out, out_cap, carry, d_rsi_offsets, d_grp_index, false);
+}
+
+/* Shard protocol without the host (aec_b200.h): the k repair of a shard whose incoming k and number of
+ * tiles to code again were worked out on the device by aecb200_shard_plan_device. */
+int aecb200_encode_repair_device(aecb200_ctx *ctx, const aecb200_params *p, const void *d_in, size_t in_bytes,
+                                 void *d_out, size_t out_cap)
+{
+    return encode_device_impl(ctx, p, d_in, in_bytes, d_out, out_cap, nullptr, nullptr, nullptr, true);
+}
+
+static int encode_device_impl(aecb200_ctx *ctx, const aecb200_params *p, const void *d_in, size_t in_bytes,
+                              void *d_out, size_t out_cap, const aecb200_carry *carry, uint64_t *d_rsi_offsets,
+                              uint64_t *d_grp_index, bool planned_repair)
 {
     if (!ctx || !p) return AEC_CONF_ERROR;
     AecCfg c;
@@ -319,12 +344,23 @@ int aecb200_encode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
     aecb200_carry zero = {0, 0, 0};
     if (!carry) carry = &zero;
 
-    ctx->enc_out_cap_bits = (uint64_t)out_cap * 8ull;
-    ctx->enc_pending = true;
-    if (g.nsamples == 0) {
-        /* nothing to code: the result is the carry itself */
-        ctx->h_res[0] = carry->bits; ctx->h_res[1] = carry->k;
-        return AEC_OK;
+    if (planned_repair) {
+        if (g.nsamples == 0) return AEC_OK;
+        CK(ctx->plan.ensure_zeroed(PLAN_WORDS * 8, ctx->stream), "cudaMalloc(plan)");
+    } else {
+        ctx->enc_out_cap_bits = (uint64_t)out_cap * 8ull;
+        ctx->enc_pending = true;
+        if (g.nsamples == 0) {
+            /* nothing to code: the result is the carry itself */
+            ctx->h_res[0] = carry->bits; ctx->h_res[1] = carry->k;
+            if (ctx->want_summary && ctx->shard_out) {
+                /* an empty shard still has to answer the all_gather: zero bits, identity clamp pair */
+                const uint64_t ident[4] = {0, 0, c.kmax, 0};
+                memcpy(&ctx->h_res[8], ident, sizeof ident);
+                CK(cudaMemcpyAsync(ctx->shard_out, &ctx->h_res[8], 32, cudaMemcpyHostToDevice, ctx->stream), "memcpy(shard out)");
+            }
+            return AEC_OK;
+        }
     }
 
     if (g.ntiles >= 0xFFFFFFF0ull) {
@@ -370,7 +406,27 @@ int aecb200_encode_device_indexed(aecb200_ctx *ctx, const aecb200_params *p,
     a.rsi_offsets = d_rsi_offsets;
     a.grp_index = d_grp_index;
     a.grp_G = aec_decode_group_blocks(c);
-    const bool repair = a.ntiles < a.ntiles_total;
+    a.shard_out = (ctx->want_summary && !planned_repair) ? (uint64_t *)ctx->shard_out : nullptr;
+    a.dyn = planned_repair ? (const uint64_t *)ctx->plan.p : nullptr;
+    const bool repair = a.ntiles < a.ntiles_total || planned_repair;
+    if (planned_repair) {
+        /* How many leading tiles depend on the incoming k is known on the device only.  Nearly always
+         * it is one or two: a first launch covers up to 64 tiles and runs when the plan asks for 1..64,
+         * a second one over all tiles runs in the rare case that more are needed (both return at once
+         * otherwise; tiles coded again with the right k come out as they were). */
+        const uint64_t few = 64;
+        a.ntiles = g.ntiles < few ? g.ntiles : few;
+        a.dyn_lo = 0; a.dyn_hi = few;
+        CK(aec_encode_launch(a, ctx->num_sms, ctx->stream), "repair launch");
+        ctx->launches += 2;
+        if (g.ntiles > few) {
+            a.ntiles = g.ntiles;
+            a.dyn_lo = few; a.dyn_hi = ~0ull;
+            CK(aec_encode_launch(a, ctx->num_sms, ctx->stream), "repair launch (all tiles)");
+            ctx->launches += 2;
+        }
+        return AEC_OK;
+    }
     CK(aec_encode_launch(a, ctx->num_sms, ctx->stream), "encode launch");
     ctx->launches += 2;
     if (ctx->want_summary && !repair) {
@@ -394,6 +450,33 @@ int aecb200_encode_finish(aecb200_ctx *ctx, aecb200_carry *end)
 }
 
 void aecb200_ctx_set_shard_mode(aecb200_ctx *ctx, int on) { if (ctx) ctx->want_summary = on != 0; }
+void aecb200_ctx_set_shard_out(aecb200_ctx *ctx, void *d_info) { if (ctx) ctx->shard_out = d_info; }
+
+int aecb200_shard_plan_device(aecb200_ctx *ctx, const void *d_all, int world, int rank, void *d_plan_out)
+{
+    if (!ctx || !d_all || world < 1 || rank < 0 || rank >= world) return AEC_CONF_ERROR;
+    ENTER_DEVICE();
+    CK(ctx->plan.ensure_zeroed(PLAN_WORDS * 8, ctx->stream), "cudaMalloc(plan)");
+    CK(ctx->misc.ensure_zeroed(256, ctx->stream), "cudaMalloc(misc)");
+    const uint64_t *result = (const uint64_t *)((uint8_t *)ctx->misc.p + 64);
+    CK(aec_shard_plan_launch((const uint64_t *)d_all, (uint32_t)world, (uint32_t)rank, result, (uint64_t *)ctx->plan.p, ctx->stream),
+       "plan launch");
+    ctx->launches += 1;
+    if (d_plan_out)
+        CK(cudaMemcpyAsync(d_plan_out, ctx->plan.p, PLAN_WORDS * 8, cudaMemcpyDeviceToDevice, ctx->stream), "memcpy(plan)");
+    return AEC_OK;
+}
+
+int aecb200_place_bits_planned(aecb200_ctx *ctx, const void *d_src, void *d_dst, size_t dst_cap, int global, int last_rank)
+{
+    if (!ctx || !ctx->plan.p) return AEC_CONF_ERROR;
+    if ((((uintptr_t)d_src) & 3u) || (((uintptr_t)d_dst) & 3u)) return AEC_CONF_ERROR;
+    ENTER_DEVICE();
+    CK(aec_place_bits_planned_launch((const uint32_t *)d_src, (const uint64_t *)ctx->plan.p, (uint32_t *)d_dst, dst_cap / 4,
+                                     global ? 1u : 0u, last_rank ? 1u : 0u, ctx->num_sms, ctx->stream), "place launch");
+    ctx->launches += 1;
+    return AEC_OK;
+}
 
 int aecb200_encode_shard_info(aecb200_ctx *ctx, uint32_t *klo, uint32_t *khi, uint64_t *first_const_tile,
                               uint64_t *tail64)
@@ -556,27 +639,41 @@ int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
     const uint64_t nwin = (span + nh - 1) / nh;
     const uint64_t np_max = nh + margin < span ? nh + margin : span;
     if (np_max >= 0x7FFFFFFFull) { snprintf(ctx->err, sizeof ctx->err, "scan window too large"); return AEC_CONF_ERROR; }
-    CK(ctx->skim_tab.ensure((size_t)(LV + 1u) * (size_t)np_max * 4u), "cudaMalloc(skim tables)");
+    /* two table sets: the walk through window i (one thread, a dependent load per RSI) runs on a side
+     * stream next to the table kernels of window i+1 */
+    const size_t set_words = (size_t)(LV + 1u) * (size_t)np_max;
+    const int nsets = nwin > 1 ? 2 : 1;
+    CK(ctx->skim_tab.ensure(set_words * 4u * (size_t)nsets), "cudaMalloc(skim tables)");
+    if (!ctx->s_walk) CK(cudaStreamCreateWithFlags(&ctx->s_walk, cudaStreamNonBlocking), "cudaStreamCreate(walk)");
+    for (cudaEvent_t &e : ctx->ev_skim)
+        if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
     AecSkimArgs a;
     memset(&a, 0, sizeof a);
     a.cfg = c;
     a.in_words = (const uint32_t *)d_in;
     a.nbits = nbits;
     a.LV = LV;
-    a.T = (uint32_t *)ctx->skim_tab.p;
-    a.H = a.T + (size_t)LV * (size_t)np_max;
     a.state = state;
     a.offsets = d_rsi_offsets;
     a.max_rsi = max_rsi;
     for (uint64_t i = 0; i < nwin; i++) {
+        const int k = (int)(i & 1u) % nsets;
+        a.T = (uint32_t *)ctx->skim_tab.p + (size_t)k * set_words;
+        a.H = a.T + (size_t)LV * (size_t)np_max;
         a.wb = base + i * nh;
         const uint64_t rem = ((nbits - a.wb) + 31ull) & ~31ull;
         a.np = (uint32_t)(nh + margin < rem ? nh + margin : rem);
         a.last = (i + 1 == nwin) ? 1u : 0u;
         a.nh_eff = a.last ? a.np : (uint32_t)nh;
+        if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_skim[2 + k], 0), "cudaStreamWaitEvent");   /* set k is free again */
         CK(aec_skim_window_launch(a, ctx->stream), "skim launch");
+        CK(cudaEventRecord(ctx->ev_skim[k], ctx->stream), "cudaEventRecord");
+        CK(cudaStreamWaitEvent(ctx->s_walk, ctx->ev_skim[k], 0), "cudaStreamWaitEvent");
+        CK(aec_skim_walk_launch(a, ctx->s_walk), "walk launch");
+        CK(cudaEventRecord(ctx->ev_skim[2 + k], ctx->s_walk), "cudaEventRecord");
         ctx->launches += LV + 2u;
     }
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_skim[2 + (int)((nwin - 1) & 1u) % nsets], 0), "cudaStreamWaitEvent");
     CK(cudaMemcpyAsync(&ctx->h_res[12], state, 32, cudaMemcpyDeviceToHost, ctx->stream), "memcpy(scan)");
     CK(cudaStreamSynchronize(ctx->stream), "scan sync");
     if (found) *found = (size_t)ctx->h_res[13];
@@ -593,6 +690,14 @@ void aecb200_ctx_set_scan_mode(aecb200_ctx *ctx, int mode, uint64_t window_bits)
 }
 
 uint64_t aecb200_ctx_last_scan_fast(aecb200_ctx *ctx) { return ctx ? ctx->scan_fast : 0; }
+
+size_t aecb200_ctx_found_offsets(aecb200_ctx *ctx, uint64_t *dst, size_t cap)
+{
+    if (!ctx) return 0;
+    const size_t n = ctx->found_offs.size();
+    if (dst) for (size_t i = 0; i < n && i < cap; i++) dst[i] = ctx->found_offs[i];
+    return n;
+}
 
 /* ------------------------------------------------------------------------ */
 /* host buffers                                                              */
@@ -752,6 +857,12 @@ int aecb200_encode_host_piece(aecb200_ctx *ctx, const aecb200_params *p,
                             rsi_offsets, offsets_cap, n_offsets);
 }
 
+#define AECB200_NOT_PIPELINED 1000
+static int decode_host_pipelined(aecb200_ctx *ctx, const aecb200_params *p, const AecCfg &c,
+                                 const void *in, size_t in_bytes,
+                                 const uint64_t *rsi_offsets, size_t n_offsets,
+                                 void *out, size_t out_cap, size_t *out_len);
+
 int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
                                const void *in, size_t in_bytes,
                                const uint64_t *rsi_offsets, size_t n_offsets,
@@ -772,6 +883,28 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
     uint64_t need_rsi = (out_samples + c.R - 1) / c.R;
     if (want_new == 0 || in_bytes * 8ull <= start_bit)
         return AEC_OK;
+    if (rsi_offsets && skip_samples == 0) {
+        /* large indexed ranges from the start of an RSI: the three-stream pipeline */
+        size_t first = 0;
+        while (first < n_offsets && rsi_offsets[first] < start_bit) first++;
+        if (first < n_offsets && rsi_offsets[first] == start_bit) {
+            size_t written = 0;
+            rc = decode_host_pipelined(ctx, p, c, in, in_bytes, rsi_offsets + first, n_offsets - first, out,
+                                       (size_t)(want_new * c.B), &written);
+            if (rc == AEC_OK) {
+                const uint64_t W = written / c.B, full = W / c.R;
+                const size_t used = (n_offsets - first) < need_rsi ? (n_offsets - first) : (size_t)need_rsi;
+                uint64_t rb;
+                if (full < used) rb = rsi_offsets[first + full];
+                else rb = (first + used < n_offsets) ? rsi_offsets[first + used] : (uint64_t)in_bytes * 8ull;
+                if (out_len) *out_len = written;
+                if (resume_bit) *resume_bit = rb;
+                if (resume_delivered) *resume_delivered = (size_t)(W % c.R);
+                return AEC_OK;
+            }
+            if (rc != AECB200_NOT_PIPELINED) return rc;
+        }
+    }
     /* stage the stream from the 32-bit word that holds start_bit */
     const size_t base_byte = (size_t)((start_bit >> 5) << 2);
     const uint64_t base_bit = (uint64_t)base_byte * 8ull;
@@ -785,6 +918,7 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
     size_t nrsi = 0;
     uint64_t scan_end = 0;
     uint64_t *h_offs = nullptr;
+    ctx->found_offs.clear();
     if (rsi_offsets) {
         /* caller's index is relative to bit 0 of `in`: entries from the RSI that starts at start_bit */
         size_t first = 0;
@@ -811,6 +945,8 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) { free(h_offs); return fail_cuda(ctx, e, "D2H offsets"); }
         }
+        ctx->found_offs.resize(nrsi);
+        for (size_t i = 0; i < nrsi; i++) ctx->found_offs[i] = h_offs[i] + base_bit;
     }
     size_t written = 0;
     rc = aecb200_decode_device(ctx, p, ctx->in_stage.p, nbytes, (const uint64_t *)ctx->offs.p, nrsi,
@@ -818,6 +954,9 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
     if (rc == AEC_OK) rc = aecb200_decode_finish(ctx, &written);
     if (rc != AEC_OK) { free(h_offs); return rc; }
     uint64_t W = written / c.B;                                    /* samples decoded from start_bit */
+    /* only RSIs that delivered samples count as discovered (the scan also notes where the zero padding
+     * behind the last RSI begins) */
+    if (ctx->found_offs.size() > (size_t)((W + c.R - 1) / c.R)) ctx->found_offs.resize((size_t)((W + c.R - 1) / c.R));
     size_t newbytes = W > skip_samples ? (size_t)((W - skip_samples) * c.B) : 0;
     if (newbytes) {
         cudaError_t e = cudaMemcpyAsync(out, (uint8_t *)ctx->out_stage.p + skip_samples * c.B, newbytes,
@@ -837,7 +976,6 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
     return AEC_OK;
 }
 
-#define AECB200_NOT_PIPELINED 1000
 /* Whole-buffer decode of a large stream with a caller-supplied RSI offset index, as a pipeline of
  * RSI ranges: a range is decoded as soon as the bytes up to its last bit have arrived, and its
  * samples travel back while the next range is decoded.  Anything but a clean decode of every range
@@ -945,10 +1083,9 @@ int aecb200_decode_host(aecb200_ctx *ctx, const aecb200_params *p,
     if (out_len) *out_len = 0;
     if (rc != AEC_OK) return rc;
     size_t written = 0;
-    rc = decode_host_pipelined(ctx, p, c, in, in_bytes, rsi_offsets, n_offsets, out, out_cap, &written);
-    if (rc == AECB200_NOT_PIPELINED)
-        rc = aecb200_decode_host_resume(ctx, p, in, in_bytes, rsi_offsets, n_offsets, 0, 0,
-                                        out, out_cap, &written, nullptr, nullptr);
+    rc = aecb200_decode_host_resume(ctx, p, in, in_bytes, rsi_offsets, n_offsets,
+                                    (rsi_offsets && n_offsets) ? rsi_offsets[0] : 0, 0,
+                                    out, out_cap, &written, nullptr, nullptr);
     if (rc != AEC_OK) return rc;
     if (out_len) *out_len = written;
     size_t left = out_cap - written;

@@ -97,29 +97,103 @@ aec_skim_level0_kernel(const AecSkimArgs a)
     }
 }
 
+/* four consecutive positions per thread: one 16-byte load, four gathers in flight, one 16-byte store */
 __global__ void __launch_bounds__(SK_THREADS)
 aec_skim_double_kernel(const AecSkimArgs a, uint32_t level)
 {
     if (a.state[2] & 1ull) return;
-    const uint32_t p = blockIdx.x * SK_THREADS + threadIdx.x;
+    const uint32_t p = (blockIdx.x * SK_THREADS + threadIdx.x) * 4u;      /* np is a multiple of 32 */
     if (p >= a.np) return;
     const uint32_t *src = a.T + (size_t)level * a.np;
     uint32_t *dst = a.T + (size_t)(level + 1u) * a.np;
-    const uint32_t r = sk_double(src, a.np, p);
-    dst[p] = r;
+    const uint4 x = *reinterpret_cast<const uint4 *>(src + p);
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+    uint32_t y[4], r[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t q = p + i + sk_len(xs[i]);
+        y[i] = (sk_jump(xs[i]) && q < a.np) ? __ldg(src + q) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t blk = sk_blk(xs[i]) + sk_blk(y[i]), len = sk_len(xs[i]) + sk_len(y[i]);
+        r[i] = (sk_jump(y[i]) && blk <= 0xFFFu && len <= 0xFFFFFu) ? ((len << 12) | blk) : 0u;
+    }
+    *reinterpret_cast<uint4 *>(dst + p) = make_uint4(r[0], r[1], r[2], r[3]);
 }
 
-/* H[p] <- bits from p to the start of the next RSI when an RSI starts at p (0: not available) */
+/* H[p] <- bits from p to the start of the next RSI when an RSI starts at p (0: not available).
+ * Same walk as sk_rsi_len (aec_skim_core.cuh), NC candidates per thread in lock step so that their
+ * table look-ups -- each a dependent, mostly uncached load -- are in flight together. */
+constexpr int SK_NC = 4;
 __global__ void __launch_bounds__(SK_THREADS)
 aec_skim_rsi_kernel(const AecSkimArgs a)
 {
     if (a.state[2] & 1ull) return;
     const AecCfg &c = a.cfg;
-    uint32_t p = blockIdx.x * SK_THREADS + threadIdx.x;
-    if (c.pad) p <<= 3;                                 /* padded RSIs start on byte boundaries */
-    if (p >= a.nh_eff) return;
-    const uint32_t res = sk_rsi_len(c, a.T, a.LV, a.np, p, a.H[p]);   /* H[p] still holds the first-CDS entry */
-    a.H[p] = res;
+    const uint32_t step = c.pad ? 8u : 1u;              /* padded RSIs start on byte boundaries */
+    const uint32_t t = blockIdx.x * SK_THREADS + threadIdx.x;
+    /* candidate i of thread t: consecutive threads take consecutive positions (coalesced H accesses) */
+    const uint32_t grid_span = gridDim.x * SK_THREADS;
+    uint32_t p[SK_NC], q[SK_NC], rem[SK_NC];
+    bool live[SK_NC];
+    const uint32_t np = a.np, rsi = c.rsi;
+#pragma unroll
+    for (int i = 0; i < SK_NC; i++) {
+        p[i] = (t + (uint32_t)i * grid_span) * step;
+        live[i] = p[i] < a.nh_eff;
+        const uint32_t first = live[i] ? a.H[p[i]] : 0u;       /* still the first-CDS entry */
+        uint32_t b = sk_blk(first);
+        if (b == 0u) b = rsi < 64u ? rsi : 64u;                 /* run-of-zero-segment at block 0 */
+        live[i] = live[i] && first >= 0x1000u && b <= rsi;
+        q[i] = p[i] + sk_len(first);
+        rem[i] = live[i] ? rsi - b : 0u;
+    }
+    const int top = (int)a.LV - 1;
+    for (int guard = 0; guard < 4096; guard++) {
+        for (int j = top; j >= 0; j--) {
+            const uint32_t *Tj = a.T + (size_t)j * np;
+            bool again;
+            do {
+                uint32_t e[SK_NC];
+#pragma unroll
+                for (int i = 0; i < SK_NC; i++) e[i] = (rem[i] && q[i] < np) ? __ldg(Tj + q[i]) : 0u;
+                again = false;
+#pragma unroll
+                for (int i = 0; i < SK_NC; i++) {
+                    if (sk_jump(e[i]) && sk_blk(e[i]) <= rem[i]) {
+                        q[i] += sk_len(e[i]); rem[i] -= sk_blk(e[i]);
+                        again = again || rem[i] != 0u;
+                    }
+                }
+            } while (again && j == top);                        /* below the top level a step fits at most once */
+        }
+        /* whoever still has blocks left stands at a CDS that is not a plain step */
+        bool progress = false;
+#pragma unroll
+        for (int i = 0; i < SK_NC; i++) {
+            if (rem[i] == 0u) continue;
+            const uint32_t e = q[i] < np ? __ldg(a.T + q[i]) : 0u;
+            const uint32_t b = rsi - rem[i];
+            if (sk_ros(e)) {
+                const uint32_t seg = 64u - (b & 63u);
+                rem[i] -= rem[i] < seg ? rem[i] : seg;          /* decode.c:528-530 */
+                q[i] += sk_len(e);
+                progress = true;
+            } else if (sk_jump(e) && sk_blk(e) <= rem[i]) {
+                q[i] += sk_len(e); rem[i] -= sk_blk(e);
+                progress = true;
+            } else { live[i] = false; rem[i] = 0u; }
+        }
+        if (!progress) break;
+    }
+#pragma unroll
+    for (int i = 0; i < SK_NC; i++) {
+        if (p[i] >= a.nh_eff) continue;
+        uint32_t end = q[i];
+        if (c.pad) end = (end + 7u) & ~7u;                      /* windows start on byte boundaries */
+        a.H[p[i]] = (live[i] && rem[i] == 0u) ? end - p[i] : 0u;
+    }
 }
 
 /* state: [0] bit position of the next RSI, [1] RSIs found, [2] flags (1 ended, 2 data error),
@@ -150,11 +224,19 @@ cudaError_t aec_skim_window_launch(const AecSkimArgs &args, cudaStream_t st)
     a.la_words = sk_lookahead_words(a.cfg);
     const uint32_t smem = 2u * (SK_TILE / 32u + a.la_words + 1u) * 4u;
     aec_skim_level0_kernel<<<(a.np + SK_TILE - 1u) / SK_TILE, SK_THREADS, smem, st>>>(a);
-    const uint32_t grid = (a.np + SK_THREADS - 1u) / SK_THREADS;
+    const uint32_t grid = (a.np / 4u + SK_THREADS - 1u) / SK_THREADS;
     for (uint32_t j = 0; j + 1u < a.LV; j++)
         aec_skim_double_kernel<<<grid, SK_THREADS, 0, st>>>(a, j);
     const uint32_t cand = a.cfg.pad ? (a.nh_eff + 7u) / 8u : a.nh_eff;
-    aec_skim_rsi_kernel<<<(cand + SK_THREADS - 1u) / SK_THREADS, SK_THREADS, 0, st>>>(a);
+    const uint32_t per_cta = SK_THREADS * SK_NC;
+    aec_skim_rsi_kernel<<<(cand + per_cta - 1u) / per_cta, SK_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+/* the serial part, on its own stream so that it runs next to the tables of the following window */
+cudaError_t aec_skim_walk_launch(const AecSkimArgs &a, cudaStream_t st)
+{
+    if (a.np == 0) return cudaSuccess;
     aec_skim_walk_kernel<<<1, 32, 0, st>>>(a);
     return cudaGetLastError();
 }

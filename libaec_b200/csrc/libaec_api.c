@@ -28,6 +28,7 @@
 #include "../../include/libaec.h"
 
 #define DEC_AHEAD_BYTES ((size_t)8 << 20)   /* decode-ahead window of the streaming decoder */
+#define DEC_DIRECT_BYTES ((size_t)1 << 20)  /* input pieces of this size are decoded straight from the caller's buffer */
 
 struct internal_state {
     int decoder;
@@ -345,6 +346,58 @@ int aec_decode_set_offsets(struct aec_stream *strm, const size_t *offsets, size_
     return AEC_OK;
 }
 
+int aec_decode_enable_offsets(struct aec_stream *strm)
+{
+    if (!strm->state || !strm->state->decoder) return AEC_CONF_ERROR;
+    strm->state->want_offsets = 1;
+    return AEC_OK;
+}
+
+int aec_decode_count_offsets(struct aec_stream *strm, size_t *count)
+{
+    if (!strm->state || !strm->state->decoder || !strm->state->want_offsets || !count) return AEC_CONF_ERROR;
+    *count = strm->state->noffs;
+    return AEC_OK;
+}
+
+int aec_decode_get_offsets(struct aec_stream *strm, size_t *offsets, size_t offsets_count)
+{
+    struct internal_state *st = strm->state;
+    if (!st || !st->decoder || !st->want_offsets || !offsets) return AEC_CONF_ERROR;
+    if (offsets_count < st->noffs) return AEC_MEM_ERROR;
+    memcpy(offsets, st->offs, st->noffs * sizeof(size_t));
+    return AEC_OK;
+}
+
+int aec_decode_range(struct aec_stream *strm, const size_t *rsi_offsets, size_t rsi_offsets_count,
+                     size_t pos, size_t size)
+{
+    struct internal_state *st = strm->state;
+    if (!st || !st->decoder || !rsi_offsets) return AEC_CONF_ERROR;
+    if (pos % st->B || size % st->B) return AEC_CONF_ERROR;
+    if (strm->avail_out < size) return AEC_MEM_ERROR;
+    if (size == 0) return AEC_OK;
+    const size_t r0 = pos / st->rsi_bytes;             /* RSI that holds the first sample wanted */
+    if (r0 >= rsi_offsets_count) return AEC_DATA_ERROR;
+    /* the stream from the word that holds that RSI's first bit up to the first bit of the RSI after the
+     * last one wanted: nothing else is uploaded or decoded */
+    const size_t r1 = (pos + size + st->rsi_bytes - 1) / st->rsi_bytes;
+    size_t end_byte = strm->avail_in;
+    if (r1 < rsi_offsets_count) {
+        end_byte = (size_t)(rsi_offsets[r1] / 8) + 8;
+        if (end_byte > strm->avail_in) end_byte = strm->avail_in;
+    }
+    size_t got = 0, rdel = 0;
+    uint64_t rbit = 0;
+    int rc = aecb200_decode_host_resume(st->ctx, &st->prm, strm->next_in, end_byte,
+                                        (const uint64_t *)rsi_offsets, rsi_offsets_count,
+                                        (uint64_t)rsi_offsets[r0], (pos % st->rsi_bytes) / st->B,
+                                        strm->next_out, size, &got, &rbit, &rdel);
+    if (rc != AEC_OK) return rc == AECB200_CUDA_ERROR ? AEC_MEM_ERROR : rc;
+    strm->next_out += got; strm->avail_out -= got; strm->total_out += got;
+    return got == size ? AEC_OK : AEC_DATA_ERROR;       /* the stream ends before the range does */
+}
+
 static int cbuf_append(struct internal_state *st, const unsigned char *p, size_t n)
 {
     if (st->clen + n > st->ccap) {
@@ -373,15 +426,47 @@ static int decode_attempt(struct aec_stream *strm, struct internal_state *st,
     }
     size_t got = 0, rdel = st->rsi_delivered;
     uint64_t rbit = st->rsi_bit - base_bits;
-    /* the index, when given, is relative to stream bit 0 == in[0] (cbuf is not trimmed then) */
-    int rc = aecb200_decode_host_resume(st->ctx, &st->prm, in, in_len,
-                                        (const uint64_t *)st->doffs, st->ndoffs,
+    /* the caller's index counts from stream bit 0; the device layer wants it relative to in[0] */
+    const uint64_t *idx = (const uint64_t *)st->doffs;
+    size_t nidx = st->ndoffs;
+    uint64_t *rebased = NULL;
+    if (idx && base_bits) {
+        size_t first = 0;
+        while (first < nidx && idx[first] < st->rsi_bit) first++;
+        nidx -= first;
+        rebased = (uint64_t *)malloc((nidx ? nidx : 1) * sizeof(uint64_t));
+        if (!rebased) return AEC_MEM_ERROR;
+        for (size_t i = 0; i < nidx; i++) rebased[i] = idx[first + i] - base_bits;
+        idx = rebased;
+    }
+    int rc = aecb200_decode_host_resume(st->ctx, &st->prm, in, in_len, idx, nidx,
                                         st->rsi_bit - base_bits, st->rsi_delivered,
                                         dst, want, &got, &rbit, &rdel);
+    free(rebased);
     if (rc == AEC_DATA_ERROR) { st->data_error = 1; return AEC_DATA_ERROR; }
     if (rc != AEC_OK) return rc == AECB200_CUDA_ERROR ? AEC_MEM_ERROR : rc;
     st->rsi_bit = rbit + base_bits;
     st->rsi_delivered = rdel;
+    if (st->want_offsets && !st->doffs) {
+        /* remember the RSI boundaries the device discovered (an attempt may see some of them again) */
+        size_t n = aecb200_ctx_found_offsets(st->ctx, NULL, 0);
+        if (n) {
+            uint64_t *tmp = (uint64_t *)malloc(n * sizeof(uint64_t));
+            if (!tmp) return AEC_MEM_ERROR;
+            aecb200_ctx_found_offsets(st->ctx, tmp, n);
+            if (st->noffs + n > st->offcap) {
+                size_t ncap = (st->noffs + n) * 2;
+                size_t *no = (size_t *)realloc(st->offs, ncap * sizeof(size_t));
+                if (!no) { free(tmp); return AEC_MEM_ERROR; }
+                st->offs = no; st->offcap = ncap;
+            }
+            for (size_t i = 0; i < n; i++) {
+                size_t o = (size_t)(tmp[i] + base_bits);
+                if (st->noffs == 0 || o > st->offs[st->noffs - 1]) st->offs[st->noffs++] = o;
+            }
+            free(tmp);
+        }
+    }
     *filled = (got == want);
     if (direct) { strm->next_out += got; strm->avail_out -= got; strm->total_out += got; }
     else st->qtail += got;
@@ -406,6 +491,20 @@ int aec_decode(struct aec_stream *strm, int flush)
             strm->next_in += strm->avail_in; strm->avail_in = 0;
             break;
         }
+        if (st->clen == 0 && strm->avail_in >= DEC_DIRECT_BYTES && strm->avail_out >= st->B) {
+            /* nothing buffered and a large piece of the stream at hand: decode from the caller's
+             * buffer, then keep only the bytes from the RSI of the next undelivered sample on */
+            const size_t n = strm->avail_in;
+            rc = decode_attempt(strm, st, strm->next_in, n, st->cbase_bits, &filled);
+            if (rc != AEC_OK) return rc;
+            size_t keep_from = (size_t)(((st->rsi_bit - st->cbase_bits) >> 5) << 2);
+            if (keep_from > n) keep_from = n - n % 4;
+            if (cbuf_append(st, strm->next_in + keep_from, n - keep_from)) return AEC_MEM_ERROR;
+            st->cbase_bits += (uint64_t)keep_from * 8;
+            strm->total_in += n; strm->next_in += n; strm->avail_in = 0;
+            st->new_input = filled;
+            continue;
+        }
         if (strm->avail_in) {
             if (cbuf_append(st, strm->next_in, strm->avail_in)) return AEC_MEM_ERROR;
             strm->total_in += strm->avail_in;
@@ -417,7 +516,7 @@ int aec_decode(struct aec_stream *strm, int flush)
         if (rc != AEC_OK) return rc;
         st->new_input = filled;                         /* more may be decodable without new input */
         /* forget bytes in front of the current RSI (keep 32-bit alignment of the base) */
-        if (!st->doffs) {
+        {
             uint64_t keep_from = ((st->rsi_bit - st->cbase_bits) >> 5) << 2;
             if (keep_from > (1u << 20) || keep_from == st->clen) {
                 memmove(st->cbuf, st->cbuf + keep_from, st->clen - keep_from);

@@ -14,6 +14,12 @@ the previous block.  Protocol per encode:
      (aecb200_place_bits_device, a funnel-shift copy) and completes its
      first word with the predecessor's tail bits                     [CUDA]
 
+`ShardedCodec.step_enqueue` runs steps 1-4 without the host in between: the
+encoder's summary kernel writes the 32 bytes into device memory, NCCL gathers
+them on the codec's stream, a one-thread kernel works out the plan
+(aecb200_shard_plan_device), the repair launch reads its incoming k and tile
+count from that plan and the placement kernel its bit offset.
+
 After step 4 rank r holds exactly the bytes [4*word_lo, ...) of the single
 stream it owns; the concatenation over ranks is byte-identical to the stream a
 single GPU (or the CPU reference) produces for the whole input.  Decode needs
@@ -111,7 +117,9 @@ class ShardedCodec:
     """Device-side sharded encoder/decoder for one rank."""
 
     def __init__(self, params, rank: int, world: int, device: int, group=None, stream=None):
+        import ctypes
         import torch
+        self._C = ctypes
         from .api import DeviceCodec, encode_bound
         self.torch = torch
         self.p = params
@@ -134,6 +142,13 @@ class ShardedCodec:
         self._xstream = torch.cuda.Stream()
         self._xdone = torch.cuda.Event()
         self._xpending = False
+        # device-resident protocol: the summary kernel writes here, the plan kernel's result lands in _plan_d
+        self._info_d = torch.zeros(4, dtype=torch.int64, device="cuda")
+        self._plan_d = torch.zeros(8, dtype=torch.int64, device="cuda")
+        self._pstream = torch.cuda.Stream()
+        self._placed_ev = torch.cuda.Event()
+        self._async_pending = False
+        self.codec.set_shard_out(self._info_d)
 
     def close(self):
         self.codec.close()
@@ -218,6 +233,68 @@ class ShardedCodec:
         self.torch.cuda.current_stream().synchronize()
         return plan
 
+    # ---- the same protocol with nothing but enqueues (no host round trip inside a step) ----
+    def step_enqueue(self, d_raw, nbytes: int, gather_ptr: int | None = None, gather_cap: int = 0):
+        """Steps 1-4 for this rank's shard, all on the device: returns at once.  The placement runs on a
+        side stream (it only reads the shard, like the decode that may follow on the codec's stream).
+        gather_ptr: base address of a buffer for the WHOLE stream (this rank's own memory or a peer's
+        mapped over NVLink): the placement then writes the words this shard owns straight there."""
+        import torch.distributed as dist
+        torch = self.torch
+        p = self.p
+        R = p.rsi * p.block_size
+        nrsi = (nbytes // p.bytes_per_sample + R - 1) // R
+        self._ensure(nbytes, nrsi)
+        self._raw, self._nbytes = d_raw, nbytes
+        self.bits = None                                # known on the device only until step_finish
+        cur = torch.cuda.current_stream()
+        if self._async_pending:
+            cur.wait_event(self._placed_ev)            # the previous placement still reads self.local
+        self.codec.encode_enqueue(p, d_raw, nbytes, self.local, self.offsets, d_grp=self.grp)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._all, self._info_d, group=self.group)
+            src = self._all
+        else:
+            src = self._info_d
+        self.codec.shard_plan(src, self.world, self.rank, self._plan_d)
+        self.codec.encode_repair(p, d_raw, nbytes, self.local)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        # the placement reads the repaired shard; run it next to whatever follows on the codec's stream
+        self._pstream.wait_event(ev)
+        self.codec.lib.aecb200_ctx_set_stream(self.codec.ctx, self._C.c_void_p(self._pstream.cuda_stream))
+        try:
+            if gather_ptr is not None:
+                self.codec.place_planned(self.local, None, dst_ptr=gather_ptr, dst_cap=gather_cap,
+                                         global_stream=True, last_rank=self.rank == self.world - 1)
+            else:
+                self.codec.place_planned(self.local, self.placed)
+        finally:
+            self.codec.lib.aecb200_ctx_set_stream(self.codec.ctx, self._C.c_void_p(cur.cuda_stream))
+        self._placed_ev.record(self._pstream)
+        self._async_pending = True
+
+    def join(self):
+        """Make the codec's stream wait for the placement of the last step_enqueue (no host wait)."""
+        if self._async_pending:
+            self.torch.cuda.current_stream().wait_event(self._placed_ev)
+
+    def step_finish(self):
+        """Wait for the last step_enqueue and read the plan back (host)."""
+        self._placed_ev.synchronize()
+        self.torch.cuda.current_stream().synchronize()
+        v = self._plan_d.tolist()
+        bits = int(v[5])
+        off = int(v[2])
+        total = int(v[4])
+        end = off + bits
+        last = self.rank == self.world - 1
+        self.bits = bits
+        self.plan = ShardPlan(off, int(v[0]), end, off >> 5, ((end + 31) >> 5) if last else (end >> 5), total,
+                              int(v[3]) & 0xFFFFFFFF)
+        self._async_pending = False
+        return self.plan
+
     def owned_bytes(self):
         """This rank's bytes of the global stream (device tensor view)."""
         plan = self.plan
@@ -231,8 +308,9 @@ class ShardedCodec:
         p = self.p
         R = p.rsi * p.block_size
         nrsi = (nbytes // p.bytes_per_sample + R - 1) // R
-        return self.codec.decode_enqueue(p, self.local, (self.bits + 7) // 8, self.offsets, nrsi, d_out, nbytes,
-                                         d_grp=self.grp)
+        # the stream's length may still be known on the device only: the buffer's size bounds the reads then
+        nb = (self.bits + 7) // 8 if self.bits is not None else self.local.numel() - 8
+        return self.codec.decode_enqueue(p, self.local, nb, self.offsets, nrsi, d_out, nbytes, d_grp=self.grp)
 
     def decode(self, d_out, nbytes: int):
         self.decode_enqueue(d_out, nbytes)

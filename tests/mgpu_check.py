@@ -34,7 +34,14 @@ def main():
         d_raw = torch.from_numpy(raw).cuda()
         sc = ShardedCodec(p, rank, world, local, stream=torch.cuda.current_stream().cuda_stream)
         plan = sc.encode(d_raw, raw.size)
-        owned = sc.owned_bytes()
+        owned = sc.owned_bytes().clone()
+        # the same protocol with nothing but enqueues (summary, all_gather, plan, repair, placement on the device)
+        sc.placed.zero_()
+        sc.step_enqueue(d_raw, raw.size)
+        plan2 = sc.step_finish()
+        same_plan = (plan2.bit_offset, plan2.k_in, plan2.end_bit, plan2.total_bits, plan2.head_or) == \
+                    (plan.bit_offset, plan.k_in, plan.end_bit, plan.total_bits, plan.head_or)
+        async_ok = same_plan and torch.equal(sc.owned_bytes(), owned)
         # gather every rank's bytes on rank 0
         sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
         dist.all_gather(sizes, torch.tensor([owned.numel()], dtype=torch.int64, device="cuda"))
@@ -46,7 +53,9 @@ def main():
         # decode needs no exchange
         d_back = torch.empty(raw.size + 16, dtype=torch.uint8, device="cuda")
         st, written = sc.decode(d_back, raw.size)
-        good = st == 0 and written == raw.size and torch.equal(d_back[: raw.size], d_raw)
+        good = st == 0 and written == raw.size and torch.equal(d_back[: raw.size], d_raw) and async_ok
+        if not async_ok:
+            print("rank %d %s: device-side protocol differs from the host protocol (plan %s vs %s)" % (rank, name, plan2, plan), flush=True)
         if rank == 0:
             stitched = torch.cat([allb[r][: int(sizes[r])] for r in range(world)]).cpu().numpy()
             whole = datagen.generate(name, total, 0)

@@ -111,3 +111,47 @@ def test_unindexed_buffer_decode_of_the_configs(name, mib):
     st, off, fast = _scan(codec, torch, p, np.ascontiguousarray(enc["out"]), nrsi, 2, 0)
     assert st == 0 and off.size == nrsi and fast >= nrsi - 2, (name, off.size, nrsi, fast)
     codec.close()
+
+
+def test_decode_range_matches_slices_of_the_full_decode():
+    """aec_decode_range (random access through the RSI index) against slices of the oracle's decode."""
+    rng = np.random.default_rng(5)
+    done = 0
+    for seed in range(120):
+        case = _multi_rsi_case(seed)
+        if case is None:
+            continue
+        p, raw, count = case
+        pad_build = bool(p.flags & L.AEC_PAD_RSI)
+        enc = po.orc_encode(p, raw, want_offsets=True, pad_rsi_build=pad_build)
+        B = p.bytes_per_sample
+        full = po.orc_decode(p, enc["out"], count * B)
+        assert full["status"] == 0
+        for _ in range(4):
+            s0 = int(rng.integers(0, count))
+            s1 = int(rng.integers(s0, count + 1))
+            got = L.decode_range(P(p), enc["out"], enc["offsets"], s0 * B, (s1 - s0) * B)
+            assert got["status"] == 0, (seed, p, s0, s1)
+            assert np.array_equal(got["out"], full["out"][s0 * B: s1 * B]), (seed, p, s0, s1)
+        # a range that ends beyond the data
+        got = L.decode_range(P(p), enc["out"], enc["offsets"], (count - 1) * B, 2 * B * p.rsi * p.block_size)
+        assert got["status"] == L.AEC_DATA_ERROR or got["out"].size >= B, (seed, p)
+        assert L.decode_range(P(p), enc["out"], enc["offsets"], 1 if B > 1 else 0, B)["status"] == (L.AEC_CONF_ERROR if B > 1 else 0)
+        done += 1
+    assert done > 60
+
+
+def test_decoder_reports_the_offsets_it_discovered():
+    """aec_decode_enable_offsets / aec_decode_get_offsets: the index a decode without an index leaves
+    behind equals the encoder's, and decoding a range with it works."""
+    for name, mib in (("c1", 8), ("c2", 8), ("c4", 6)):
+        p, _ = datagen.CONFIGS[name]
+        B = p.bytes_per_sample
+        raw = datagen.generate(name, (mib << 20) // B - 7)
+        enc = L.buffer_encode(p, raw, want_offsets=True)
+        dec = L.buffer_decode_discover(p, enc["out"], raw.size)
+        assert dec["status"] == 0 and np.array_equal(dec["out"], raw)
+        assert np.array_equal(dec["offsets"], enc["offsets"]), name
+        R = p.rsi * p.block_size * B
+        got = L.decode_range(p, enc["out"], dec["offsets"], 3 * R + 5 * B, 2 * R)
+        assert got["status"] == 0 and np.array_equal(got["out"], raw[3 * R + 5 * B: 5 * R + 5 * B])
