@@ -142,6 +142,8 @@ int  aecb200_place_bits_device(aecb200_ctx *ctx, const void *d_src, uint64_t nbi
  *   aecb200_place_bits_planned  moves the shard to its bit phase; global != 0: d_dst is the base of the
  *                               whole stream (e.g. a peer GPU's buffer mapped over NVLink) and only the words
  *                               the shard owns are written, so that the placement is the stitch. */
+#define AECB200_REPAIR_TILES 64   /* tiles aecb200_encode_repair_device can code again; a plan that asks for more
+                                   * (plan word 1) is finished by the caller through the host-driven repair */
 void aecb200_ctx_set_shard_out(aecb200_ctx *ctx, void *d_info);
 int  aecb200_shard_plan_device(aecb200_ctx *ctx, const void *d_all, int world, int rank, void *d_plan_out);
 int  aecb200_encode_repair_device(aecb200_ctx *ctx, const aecb200_params *p, const void *d_in, size_t in_bytes,

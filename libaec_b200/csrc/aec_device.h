@@ -137,7 +137,8 @@ cudaError_t aec_encode_summary_launch(const AecEncArgs &a, cudaStream_t st);
 /* copy nbits bits from src (bit 0 = MSB of word 0) to dst starting at bit dst_bit; dst words are private to the caller */
 cudaError_t aec_place_bits_launch(const uint32_t *src, uint64_t nbits, uint32_t *dst, uint64_t dst_bit, uint64_t dst_cap_words, uint32_t head_or, cudaStream_t st);
 /* plan[PLAN_*] from the gathered (bits, klo, khi, tail64) of all shards; result[4] = this shard's first constant tile */
-cudaError_t aec_shard_plan_launch(const uint64_t *all, uint32_t world, uint32_t rank, const uint64_t *result, uint64_t *plan, cudaStream_t st);
+cudaError_t aec_shard_plan_launch(const uint64_t *all, uint32_t world, uint32_t rank, const uint64_t *result, uint64_t *plan,
+                                  uint64_t *plan_copy, cudaStream_t st);
 /* placement with bit offset, length and head bits read from the plan; global != 0: dst is the base of the whole
  * stream (possibly a peer GPU's buffer) and only the words this shard owns are written, else dst[0] is the word
  * that holds the shard's first bit */

@@ -817,23 +817,44 @@ __global__ void aec_encode_fixup_kernel(const AecEncArgs a)
 /* Clamp pair of the whole launch (ordered composition of the per-tile pairs)
  * and a tile index after which k no longer depends on the incoming k: what a
  * multi-GPU shard publishes so its successors can chain k. */
-__global__ void aec_encode_summary_kernel(const AecEncArgs a)
+__global__ void __launch_bounds__(1024) aec_encode_summary_kernel(const AecEncArgs a)
 {
-    const uint32_t lane = threadIdx.x;
+    /* 1024 threads, a contiguous run of tiles each; ordered composition inside the warps by shuffles,
+     * across the warps by warp 0 */
+    __shared__ uint32_t s_acc[32];
+    __shared__ unsigned long long s_first[32];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t n = a.ntiles_total;
-    const uint64_t per = (n + 31) / 32;
-    uint64_t b0 = lane * per, b1 = b0 + per;
+    const uint64_t per = (n + 1023) / 1024;
+    uint64_t b0 = threadIdx.x * per, b1 = b0 + per;
     if (b0 > n) b0 = n;
     if (b1 > n) b1 = n;
-    uint32_t acc = aec_kpair(0, a.cfg.kmax);
+    const uint32_t ident = aec_kpair(0, a.cfg.kmax);
+    uint32_t acc = ident;
     unsigned long long firstc = ~0ull;
     for (uint64_t t = b0; t < b1; t++) {
         acc = aec_kcompose(acc, a.tile_kagg[t]);
+        /* once a run of tiles maps every k to one value, so does everything up to there */
         if (firstc == ~0ull && aec_klo(acc) == aec_khi(acc)) firstc = t;
     }
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         uint32_t o = __shfl_up_sync(FULL, acc, off);       /* lower lane = earlier tiles */
+        if (lane >= (uint32_t)off) acc = aec_kcompose(o, acc);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        unsigned long long o = __shfl_xor_sync(FULL, firstc, off);
+        if (o < firstc) firstc = o;
+    }
+    if (lane == 31) { s_acc[warp] = acc; s_first[warp] = firstc; }
+    __syncthreads();
+    if (warp != 0) return;
+    acc = s_acc[lane];
+    firstc = s_first[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t o = __shfl_up_sync(FULL, acc, off);
         if (lane >= (uint32_t)off) acc = aec_kcompose(o, acc);
     }
 #pragma unroll
@@ -870,7 +891,8 @@ __global__ void aec_encode_summary_kernel(const AecEncArgs a)
 /* One thread turns the gathered shard summaries into this rank's plan: exclusive scan of the bit lengths,
  * clamp chain of k, the predecessor's bits of the shared word (libaec_b200/parallel.py
  * plan_shards is the host model the gloo tests pin). */
-__global__ void aec_shard_plan_kernel(const uint64_t *all, uint32_t world, uint32_t rank, const uint64_t *result, uint64_t *plan)
+__global__ void aec_shard_plan_kernel(const uint64_t *all, uint32_t world, uint32_t rank, const uint64_t *result, uint64_t *plan,
+                                      uint64_t *plan_copy)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     uint64_t off = 0, total = 0, prev_tail = 0;
@@ -895,6 +917,8 @@ __global__ void aec_shard_plan_kernel(const uint64_t *all, uint32_t world, uint3
     plan[PLAN_HEAD_OR] = my_head;
     plan[PLAN_TOTAL_BITS] = total;
     plan[PLAN_MY_BITS] = my_bits;
+    if (plan_copy)
+        for (int i = 0; i < PLAN_WORDS; i++) plan_copy[i] = plan[i];
 }
 
 /* aec_place_bits_kernel with everything read from the plan */
@@ -912,15 +936,42 @@ __global__ void aec_place_bits_planned_kernel(const uint32_t *src, const uint64_
     const uint64_t we = (global && !last_rank) ? (endbit >> 5) : ((endbit + 31) >> 5);
     const uint64_t nw = we > w0 ? we - w0 : 0;
     const uint64_t src_words = (nbits + 31) >> 5;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t hi = (i >= 1 && i - 1 < src_words) ? __byte_perm(src[i - 1], 0, 0x0123) : 0u;
-        uint32_t lo = (i < src_words) ? __byte_perm(src[i], 0, 0x0123) : 0u;
-        uint32_t v = sh ? ((hi << (32u - sh)) | (lo >> sh)) : lo;
-        if (w0 + i == (endbit >> 5) && (endbit & 31u)) v &= ~(0xFFFFFFFFu >> (endbit & 31u));
-        if (i == 0 && sh) v = (v & (0xFFFFFFFFu >> sh)) | (head_or & ~(0xFFFFFFFFu >> sh));
-        if (w0 + i < dst_cap_words) dst[w0 + i] = __byte_perm(v, 0, 0x0123);
+    /* four destination words per thread: five source words (one 16-byte load when aligned), one 16-byte
+     * store when the destination allows it */
+    const uint64_t nq = (nw + 3) >> 2;
+    const bool dst16 = ((reinterpret_cast<uintptr_t>(dst + w0)) & 15u) == 0;
+    const bool src16 = ((reinterpret_cast<uintptr_t>(src)) & 15u) == 0;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i0 = q << 2;
+        uint32_t sw[5];
+        sw[0] = (i0 >= 1 && i0 - 1 < src_words) ? __byte_perm(src[i0 - 1], 0, 0x0123) : 0u;
+        if (src16 && i0 + 4 <= src_words) {
+            const uint4 x = *reinterpret_cast<const uint4 *>(src + i0);
+            sw[1] = __byte_perm(x.x, 0, 0x0123); sw[2] = __byte_perm(x.y, 0, 0x0123);
+            sw[3] = __byte_perm(x.z, 0, 0x0123); sw[4] = __byte_perm(x.w, 0, 0x0123);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) sw[1 + j] = (i0 + j < src_words) ? __byte_perm(src[i0 + j], 0, 0x0123) : 0u;
+        }
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t i = i0 + j;
+            v[j] = sh ? ((sw[j] << (32u - sh)) | (sw[j + 1] >> sh)) : sw[j + 1];
+            if (w0 + i == (endbit >> 5) && (endbit & 31u)) v[j] &= ~(0xFFFFFFFFu >> (endbit & 31u));
+            if (i == 0 && sh) v[j] = (v[j] & (0xFFFFFFFFu >> sh)) | (head_or & ~(0xFFFFFFFFu >> sh));
+            v[j] = __byte_perm(v[j], 0, 0x0123);
+        }
+        if (dst16 && i0 + 4 <= nw && w0 + i0 + 4 <= dst_cap_words) {
+            *reinterpret_cast<uint4 *>(dst + w0 + i0) = make_uint4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (i0 + j < nw && w0 + i0 + j < dst_cap_words) dst[w0 + i0 + j] = v[j];
+        }
     }
 }
+
 
 /* dst[dst_bit ..) = src[0 .. nbits): one thread per destination word. */
 __global__ void aec_place_bits_kernel(const uint32_t *src, uint64_t nbits, uint32_t *dst, uint64_t dst_bit,
@@ -1003,14 +1054,14 @@ uint32_t aec_encode_staging_words(const AecCfg &c)
 
 cudaError_t aec_encode_summary_launch(const AecEncArgs &a, cudaStream_t st)
 {
-    aec_encode_summary_kernel<<<1, 32, 0, st>>>(a);
+    aec_encode_summary_kernel<<<1, 1024, 0, st>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t aec_shard_plan_launch(const uint64_t *all, uint32_t world, uint32_t rank, const uint64_t *result, uint64_t *plan,
-                                  cudaStream_t st)
+                                  uint64_t *plan_copy, cudaStream_t st)
 {
-    aec_shard_plan_kernel<<<1, 32, 0, st>>>(all, world, rank, result, plan);
+    aec_shard_plan_kernel<<<1, 32, 0, st>>>(all, world, rank, result, plan, plan_copy);
     return cudaGetLastError();
 }
 

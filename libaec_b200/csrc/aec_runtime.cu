@@ -411,20 +411,16 @@ static int encode_device_impl(aecb200_ctx *ctx, const aecb200_params *p, const v
     const bool repair = a.ntiles < a.ntiles_total || planned_repair;
     if (planned_repair) {
         /* How many leading tiles depend on the incoming k is known on the device only.  Nearly always
-         * it is one or two: a first launch covers up to 64 tiles and runs when the plan asks for 1..64,
-         * a second one over all tiles runs in the rare case that more are needed (both return at once
-         * otherwise; tiles coded again with the right k come out as they were). */
-        const uint64_t few = 64;
+         * it is one or two.  This launch covers up to AECB200_REPAIR_TILES tiles and runs when the plan
+         * asks for that many or fewer (it returns at once when the incoming k is 0; tiles coded again with
+         * the right k come out as they were).  The rare shard that needs more is repaired by the caller,
+         * who sees the number in the plan (plan word 1 > AECB200_REPAIR_TILES): aecb200_ctx_set_tile_limit
+         * + aecb200_encode_device with the true k, as in the host-driven protocol. */
+        const uint64_t few = AECB200_REPAIR_TILES;
         a.ntiles = g.ntiles < few ? g.ntiles : few;
         a.dyn_lo = 0; a.dyn_hi = few;
         CK(aec_encode_launch(a, ctx->num_sms, ctx->stream), "repair launch");
         ctx->launches += 2;
-        if (g.ntiles > few) {
-            a.ntiles = g.ntiles;
-            a.dyn_lo = few; a.dyn_hi = ~0ull;
-            CK(aec_encode_launch(a, ctx->num_sms, ctx->stream), "repair launch (all tiles)");
-            ctx->launches += 2;
-        }
         return AEC_OK;
     }
     CK(aec_encode_launch(a, ctx->num_sms, ctx->stream), "encode launch");
@@ -459,11 +455,9 @@ int aecb200_shard_plan_device(aecb200_ctx *ctx, const void *d_all, int world, in
     CK(ctx->plan.ensure_zeroed(PLAN_WORDS * 8, ctx->stream), "cudaMalloc(plan)");
     CK(ctx->misc.ensure_zeroed(256, ctx->stream), "cudaMalloc(misc)");
     const uint64_t *result = (const uint64_t *)((uint8_t *)ctx->misc.p + 64);
-    CK(aec_shard_plan_launch((const uint64_t *)d_all, (uint32_t)world, (uint32_t)rank, result, (uint64_t *)ctx->plan.p, ctx->stream),
-       "plan launch");
+    CK(aec_shard_plan_launch((const uint64_t *)d_all, (uint32_t)world, (uint32_t)rank, result, (uint64_t *)ctx->plan.p,
+                             (uint64_t *)d_plan_out, ctx->stream), "plan launch");
     ctx->launches += 1;
-    if (d_plan_out)
-        CK(cudaMemcpyAsync(d_plan_out, ctx->plan.p, PLAN_WORDS * 8, cudaMemcpyDeviceToDevice, ctx->stream), "memcpy(plan)");
     return AEC_OK;
 }
 

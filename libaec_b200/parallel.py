@@ -35,6 +35,9 @@ from dataclasses import dataclass
 import numpy as np
 
 
+REPAIR_TILES = 64        # AECB200_REPAIR_TILES of include/aec_b200.h
+
+
 def shard_range(total_samples: int, rsi_samples: int, rank: int, world: int):
     """Contiguous RSI-aligned shard [start, start + count) of `rank`."""
     nrsi = (total_samples + rsi_samples - 1) // rsi_samples
@@ -246,6 +249,7 @@ class ShardedCodec:
         nrsi = (nbytes // p.bytes_per_sample + R - 1) // R
         self._ensure(nbytes, nrsi)
         self._raw, self._nbytes = d_raw, nbytes
+        self._gather = (gather_ptr, gather_cap) if gather_ptr is not None else None
         self.bits = None                                # known on the device only until step_finish
         cur = torch.cuda.current_stream()
         if self._async_pending:
@@ -293,6 +297,18 @@ class ShardedCodec:
         self.plan = ShardPlan(off, int(v[0]), end, off >> 5, ((end + 31) >> 5) if last else (end >> 5), total,
                               int(v[3]) & 0xFFFFFFFF)
         self._async_pending = False
+        if int(v[1]) > REPAIR_TILES and self._nbytes:
+            # rare: k depends on the incoming k for more leading tiles than the device-side repair covers
+            # (long runs of all-zero and plateau blocks): finish with the host-driven repair and place again
+            from .api import Carry
+            self.codec.set_tile_limit(int(v[1]))
+            self.codec.encode_enqueue(self.p, self._raw, self._nbytes, self.local, None, Carry(0, self.plan.k_in, 0))
+            if self._gather is not None:
+                self.codec.place_planned(self.local, None, dst_ptr=self._gather[0], dst_cap=self._gather[1],
+                                         global_stream=True, last_rank=last)
+            else:
+                self.codec.place_planned(self.local, self.placed)
+            self.torch.cuda.current_stream().synchronize()
         return self.plan
 
     def owned_bytes(self):
