@@ -59,6 +59,7 @@ int  aecb200_device_count(void);
  * Every aecb200_* call runs on its context's device and restores the caller's current device. */
 int  aecb200_current_device(void);
 int  aecb200_ctx_device(aecb200_ctx *ctx);
+int  aecb200_set_device(int device);
 /* device < 0: current device.  One context = one CUDA stream + workspace;
  * use one context per thread. */
 int  aecb200_ctx_create(aecb200_ctx **ctx, int device);
@@ -228,6 +229,29 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
                                uint64_t start_bit, size_t skip_samples,
                                void *out, size_t out_cap, size_t *out_len,
                                uint64_t *resume_bit, size_t *resume_delivered);
+
+/* ---- SZIP shim on the device (what libsz's SZ_BufftoBuffCompress / SZ_BufftoBuffDecompress call;
+ * reference: sz_compat.c:110-268).  The byte-plane (de)interleave of 32/64-bit pixels and the scanline
+ * padding run as kernels between the copies and the coder instead of host loops.  Return values are
+ * the szlib.h codes (SZ_OK 0, SZ_OUTBUFF_FULL 2, SZ_PARAM_ERROR -1, SZ_MEM_ERROR -4) or an AEC_* /
+ * AECB200_CUDA_ERROR code from the coder.  *dest_len: in = capacity, out = bytes produced. */
+int aecb200_sz_compress_host(aecb200_ctx *ctx, int options_mask, int bits_per_pixel, int pixels_per_block,
+                             int pixels_per_scanline, const void *source, size_t source_len, void *dest, size_t *dest_len);
+int aecb200_sz_decompress_host(aecb200_ctx *ctx, int options_mask, int bits_per_pixel, int pixels_per_block,
+                               int pixels_per_scanline, const void *source, size_t source_len, void *dest, size_t *dest_len);
+/* Many chunks in flight (HDF5 chunk pipelines): chunk i goes through its own pooled context and CUDA
+ * stream on one of `threads` host threads (0 = a default), so uploads, kernels and downloads of different
+ * chunks overlap.  status[i] receives what the single call would have returned; the function returns the
+ * first non-zero status (0 when every chunk succeeded). */
+int aecb200_sz_compress_batch(int n, void *const *dest, size_t *dest_len, const void *const *source, const size_t *source_len,
+                              int options_mask, int bits_per_pixel, int pixels_per_block, int pixels_per_scanline,
+                              int *status, int threads);
+int aecb200_sz_decompress_batch(int n, void *const *dest, size_t *dest_len, const void *const *source, const size_t *source_len,
+                                int options_mask, int bits_per_pixel, int pixels_per_block, int pixels_per_scanline,
+                                int *status, int threads);
+/* contexts (stream + workspace) of the calling thread's current device, kept between calls */
+aecb200_ctx *aecb200_pool_get(void);
+void aecb200_pool_put(aecb200_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -9,4 +9,4 @@ from .api import (AEC_DATA_3BYTE, AEC_DATA_MSB, AEC_DATA_PREPROCESS, AEC_DATA_SI
                   AEC_NOT_ENFORCE, AEC_PAD_RSI, AEC_RESTRICTED, AEC_OK, AEC_CONF_ERROR,
                   AEC_STREAM_ERROR, AEC_DATA_ERROR, AEC_MEM_ERROR, AEC_FLUSH, AEC_NO_FLUSH,
                   Params, AecStream, Carry, DeviceCodec, Encoder, Decoder, buffer_encode, buffer_decode, decode_range, buffer_decode_discover,
-                  encode_bound, sz_compress, sz_decompress, load_library)
+                  encode_bound, sz_compress, sz_decompress, sz_compress_batch, sz_decompress_batch, load_library)

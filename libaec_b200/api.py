@@ -98,7 +98,9 @@ DEVICE_SYMBOLS = ["aecb200_device_count", "aecb200_current_device", "aecb200_ctx
                   "aecb200_ctx_set_careful_decode", "aecb200_ctx_last_handover",
                   "aecb200_ctx_set_pipeline_piece", "aecb200_ctx_set_scan_mode", "aecb200_ctx_last_scan_fast",
                   "aecb200_ctx_found_offsets", "aecb200_ctx_set_shard_out", "aecb200_shard_plan_device",
-                  "aecb200_encode_repair_device", "aecb200_place_bits_planned"]
+                  "aecb200_encode_repair_device", "aecb200_place_bits_planned", "aecb200_set_device",
+                  "aecb200_sz_compress_host", "aecb200_sz_decompress_host", "aecb200_sz_compress_batch",
+                  "aecb200_sz_decompress_batch", "aecb200_pool_get", "aecb200_pool_put"]
 SZ_SYMBOLS = ["SZ_BufftoBuffCompress", "SZ_BufftoBuffDecompress", "SZ_encoder_enabled", "SZ_Compress"]
 
 
@@ -127,6 +129,8 @@ def load_library() -> C.CDLL:
         lib.aecb200_ctx_last_scan_fast.restype = C.c_uint64
         lib.aecb200_ctx_found_offsets.restype = C.c_size_t
         lib.aecb200_ctx_set_shard_out.restype = None
+        lib.aecb200_pool_get.restype = C.c_void_p
+        lib.aecb200_pool_put.restype = None
         _lib = lib
     return _lib
 
@@ -363,6 +367,37 @@ def sz_compress(src, dest_cap, options_mask, bits_per_pixel, pixels_per_block, p
 def sz_decompress(src, dest_cap, options_mask, bits_per_pixel, pixels_per_block, pixels_per_scanline):
     return _sz(load_sz_library().SZ_BufftoBuffDecompress, src, dest_cap, options_mask, bits_per_pixel,
                pixels_per_block, pixels_per_scanline)
+
+
+def _sz_batch(decompress: bool, chunks, dest_caps, options_mask, bits_per_pixel, pixels_per_block,
+              pixels_per_scanline, threads: int = 0, dests=None):
+    """aecb200_sz_compress_batch / aecb200_sz_decompress_batch: many chunks in flight."""
+    lib = load_library()
+    n = len(chunks)
+    srcs = [_u8(c) for c in chunks]
+    if dests is None:
+        dests = [np.zeros(max(int(cap), 1), dtype=np.uint8) for cap in dest_caps]
+    src_p = (C.c_void_p * n)(*[s.ctypes.data for s in srcs])
+    src_l = (C.c_size_t * n)(*[s.size for s in srcs])
+    dst_p = (C.c_void_p * n)(*[d.ctypes.data for d in dests])
+    dst_l = (C.c_size_t * n)(*[int(cap) for cap in dest_caps])
+    status = (C.c_int * n)()
+    fn = lib.aecb200_sz_decompress_batch if decompress else lib.aecb200_sz_compress_batch
+    rc = fn(C.c_int(n), dst_p, dst_l, src_p, src_l, C.c_int(options_mask), C.c_int(bits_per_pixel),
+            C.c_int(pixels_per_block), C.c_int(pixels_per_scanline), status, C.c_int(threads))
+    return {"status": rc, "statuses": list(status), "out": [d[:dst_l[i]] for i, d in enumerate(dests)]}
+
+
+def sz_compress_batch(chunks, dest_caps, options_mask, bits_per_pixel, pixels_per_block, pixels_per_scanline,
+                      threads: int = 0, dests=None):
+    return _sz_batch(False, chunks, dest_caps, options_mask, bits_per_pixel, pixels_per_block, pixels_per_scanline,
+                     threads, dests)
+
+
+def sz_decompress_batch(chunks, dest_caps, options_mask, bits_per_pixel, pixels_per_block, pixels_per_scanline,
+                        threads: int = 0, dests=None):
+    return _sz_batch(True, chunks, dest_caps, options_mask, bits_per_pixel, pixels_per_block, pixels_per_scanline,
+                     threads, dests)
 
 
 # --------------------------------------------------------------------------

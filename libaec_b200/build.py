@@ -27,7 +27,7 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVFLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--use_fast_math"]
 
-CU_SOURCES = ["aec_encode.cu", "aec_decode.cu", "aec_skim.cu", "aec_runtime.cu"]
+CU_SOURCES = ["aec_encode.cu", "aec_decode.cu", "aec_skim.cu", "aec_sz.cu", "aec_runtime.cu"]
 HEADERS = ["aec_core.cuh", "aec_decode_core.cuh", "aec_skim_core.cuh", "aec_device.h",
            os.path.join(ROOT, "include", "aec_b200.h"), os.path.join(ROOT, "include", "libaec.h"),
            os.path.join(ROOT, "include", "szlib.h")]
@@ -64,11 +64,12 @@ def build(force: bool = False, verbose: bool = False) -> dict:
         objs.append(o)
         if force or _newer([s] + hdrs, o):
             jobs.append([NVCC] + ARCH + NVFLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
-    api_o = os.path.join(OBJ, "libaec_api.o")
-    api_c = os.path.join(CSRC, "libaec_api.c")
-    objs.append(api_o)
-    if force or _newer([api_c] + hdrs, api_o):
-        jobs.append(["gcc", "-O2", "-fPIC", "-std=c99", "-Wall", "-D_POSIX_C_SOURCE=200809L", "-c", api_c, "-o", api_o])
+    for cname in ("libaec_api", "sz_batch"):
+        c_o = os.path.join(OBJ, cname + ".o")
+        c_c = os.path.join(CSRC, cname + ".c")
+        objs.append(c_o)
+        if force or _newer([c_c] + hdrs, c_o):
+            jobs.append(["gcc", "-O2", "-fPIC", "-std=c99", "-Wall", "-D_POSIX_C_SOURCE=200809L", "-c", c_c, "-o", c_o])
     with ThreadPoolExecutor(max_workers=4) as ex:
         outs = list(ex.map(_run, jobs))
     if verbose:

@@ -129,6 +129,12 @@ uint64_t aec_skim_margin_bits(const AecCfg &c);
 cudaError_t aec_skim_window_launch(const AecSkimArgs &a, cudaStream_t st);
 cudaError_t aec_skim_walk_launch(const AecSkimArgs &a, cudaStream_t st);
 
+/* SZIP shim on the device (aec_sz.cu): caller's bytes -> byte planes + padded scanlines, and back */
+cudaError_t aec_sz_pack_launch(const uint8_t *src, uint64_t src_len, uint8_t *dst, uint64_t padded_len, uint32_t ws,
+                               uint64_t line, uint64_t full_line, uint32_t px, uint32_t nn, cudaStream_t st);
+cudaError_t aec_sz_unpack_launch(const uint8_t *src, uint8_t *dst, uint64_t n, uint32_t ws, uint64_t line, uint64_t full_line,
+                                 cudaStream_t st);
+
 uint32_t aec_encode_tile_blocks(uint32_t J);
 uint32_t aec_encode_staging_words(const AecCfg &c);
 cudaError_t aec_encode_launch(const AecEncArgs &a, int num_sms, cudaStream_t st);

@@ -65,6 +65,8 @@ struct aecb200_ctx {
 
     DevBuf grp, rsi_list, desc, pref, headc, tailc, tile_end, tile_kagg, misc, in_stage, out_stage, offs, rsi_count, plan;
     void *shard_out = nullptr;           /* device: (bits, klo, khi, tail64) of every shard-mode encode */
+    DevBuf raw_stage, out2_stage;        /* SZIP shim: the caller's bytes before / after the byte shuffles */
+    bool in_stage_ready = false;         /* the next host encode finds its input in in_stage already */
     uint64_t tile_limit = 0;             /* next encode codes only this many leading tiles (k repair) */
     bool want_summary = false;
     bool careful_only = false;           /* decode with the lane-per-RSI kernel only (tests) */
@@ -240,6 +242,7 @@ void aecb200_ctx_destroy(aecb200_ctx *ctx)
     ctx->desc.release(); ctx->headc.release(); ctx->tailc.release(); ctx->tile_end.release();
     ctx->misc.release(); ctx->in_stage.release(); ctx->out_stage.release(); ctx->offs.release();
     ctx->rsi_count.release(); ctx->skim_tab.release(); ctx->plan.release();
+    ctx->raw_stage.release(); ctx->out2_stage.release();
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -259,6 +262,9 @@ int aecb200_current_device(void)
 }
 
 int aecb200_ctx_device(aecb200_ctx *ctx) { return ctx ? ctx->device : -1; }
+
+/* make `device` the calling thread's current device (worker threads of the batch calls) */
+int aecb200_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? AEC_OK : AECB200_CUDA_ERROR; }
 
 int aecb200_ctx_set_stream(aecb200_ctx *ctx, void *cuda_stream)
 {
@@ -711,6 +717,8 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
     if (rc != AEC_OK) return rc;
     ENTER_DEVICE();
 
+    const bool staged = ctx->in_stage_ready;             /* input already sits in in_stage (SZIP shim) */
+    ctx->in_stage_ready = false;
     const size_t rsi_bytes = (size_t)c.R * c.B;
     size_t use_bytes = final ? (in_bytes / c.B) * c.B : (in_bytes / rsi_bytes) * rsi_bytes;
     const uint64_t nrsi = (use_bytes / c.B + c.R - 1) / c.R;
@@ -722,7 +730,7 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
     /* pieces of whole RSIs; a piece starts at the bit where the one before ended, so the pieces
      * write one contiguous stream into out_stage (the same seeding as AEC_NO_FLUSH streaming) */
     size_t piece = use_bytes;
-    if (ctx->pipe_piece && use_bytes >= 2 * ctx->pipe_piece) {
+    if (!staged && ctx->pipe_piece && use_bytes >= 2 * ctx->pipe_piece) {
         const size_t unit = rsi_bytes * 16;             /* pieces start 16-byte aligned (vector loads) */
         piece = ((ctx->pipe_piece + unit - 1) / unit) * unit;
         if ((use_bytes + piece - 1) / piece > 256) piece = (((use_bytes + 255) / 256 + unit - 1) / unit) * unit;
@@ -739,7 +747,7 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
         }
         aecb200_carry seed = {phase, carry->k, carry->word};
         if (npieces == 1) {
-            CK(cudaMemcpyAsync(ctx->in_stage.p, in, use_bytes, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+            if (!staged) CK(cudaMemcpyAsync(ctx->in_stage.p, in, use_bytes, cudaMemcpyHostToDevice, ctx->stream), "H2D");
             rc = aecb200_encode_device(ctx, p, ctx->in_stage.p, use_bytes, ctx->out_stage.p, ctx->out_stage.cap & ~(size_t)3,
                                        &seed, d_offs);
             if (rc != AEC_OK) return rc;
@@ -1084,6 +1092,130 @@ int aecb200_decode_host(aecb200_ctx *ctx, const aecb200_params *p,
     if (out_len) *out_len = written;
     size_t left = out_cap - written;
     if (left > 0 && left < c.B) return AEC_MEM_ERROR;               /* decode.c:821-823 */
+    return AEC_OK;
+}
+
+/* ------------------------------------------------------------------------ */
+/* SZIP shim (szlib.h) with the byte shuffles on the device                  */
+/* ------------------------------------------------------------------------ */
+
+#define SZ_MSB_OPTION_MASK 16
+#define SZ_NN_OPTION_MASK 32
+#define SZ_OUTBUFF_FULL 2
+
+namespace {
+struct SzGeom {
+    aecb200_params prm;
+    int planes;
+    uint32_t ws, px;
+    size_t line, full_line;
+};
+
+void sz_geometry(int options_mask, int bits_per_pixel, int pixels_per_block, int pixels_per_scanline, int enc, SzGeom *g)
+{
+    /* sz_compat.c:12-37, :125-142 / :200-214: only MSB and NN reach the coder */
+    g->planes = bits_per_pixel == 32 || bits_per_pixel == 64;
+    g->prm.bits_per_sample = g->planes ? 8u : (uint32_t)bits_per_pixel;
+    g->prm.block_size = (uint32_t)pixels_per_block;
+    g->prm.rsi = pixels_per_block > 0 ? (uint32_t)((pixels_per_scanline + pixels_per_block - 1) / pixels_per_block) : 0u;
+    g->prm.flags = (enc ? AECF_NOT_ENFORCE : 0u) | ((options_mask & SZ_MSB_OPTION_MASK) ? AECF_MSB : 0u) |
+                   ((options_mask & SZ_NN_OPTION_MASK) ? AECF_PREPROCESS : 0u);
+    g->ws = g->planes ? (uint32_t)bits_per_pixel / 8u : 1u;
+    g->px = g->prm.bits_per_sample > 16 ? 4u : (g->prm.bits_per_sample > 8 ? 2u : 1u);
+    g->line = (size_t)pixels_per_scanline * g->px;
+    g->full_line = (size_t)g->prm.rsi * g->prm.block_size * g->px;
+}
+} // namespace
+
+int aecb200_sz_compress_host(aecb200_ctx *ctx, int options_mask, int bits_per_pixel, int pixels_per_block,
+                             int pixels_per_scanline, const void *source, size_t source_len, void *dest, size_t *dest_len)
+{
+    if (!ctx || !dest_len) return AEC_CONF_ERROR;
+    SzGeom g;
+    sz_geometry(options_mask, bits_per_pixel, pixels_per_block, pixels_per_scanline, 1, &g);
+    AecCfg c;
+    int rc = make_cfg(ctx, &g.prm, 1, &c);
+    if (rc != AEC_OK || pixels_per_scanline <= 0) return AEC_CONF_ERROR;
+    const size_t nlines = (source_len / g.px + (size_t)pixels_per_scanline - 1) / (size_t)pixels_per_scanline;
+    const size_t padded_len = g.full_line * nlines;
+    const bool shuffle = g.planes || g.full_line != g.line || source_len != padded_len;
+    size_t produced = 0, consumed = 0;
+    aecb200_carry carry = {0, 0, 0};
+    const void *in = source;
+    if (shuffle && padded_len) {
+        ENTER_DEVICE();
+        CK(ctx->raw_stage.ensure(source_len + 16), "cudaMalloc(sz source)");
+        CK(ctx->in_stage.ensure(padded_len + 16), "cudaMalloc(in)");
+        CK(cudaMemcpyAsync(ctx->raw_stage.p, source, source_len, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+        CK(aec_sz_pack_launch((const uint8_t *)ctx->raw_stage.p, source_len, (uint8_t *)ctx->in_stage.p, padded_len, g.ws, g.line,
+                              g.full_line, g.px, (g.prm.flags & AECF_PREPROCESS) ? 1u : 0u, ctx->stream), "sz pack launch");
+        ctx->launches += 1;
+        ctx->in_stage_ready = true;
+        in = nullptr;
+    }
+    rc = encode_host_impl(ctx, &g.prm, in, padded_len, 1, dest, *dest_len, &produced, &consumed, &carry, nullptr, 0, nullptr);
+    ctx->in_stage_ready = false;
+    *dest_len = produced;
+    return rc == AEC_STREAM_ERROR ? SZ_OUTBUFF_FULL : rc;
+}
+
+int aecb200_sz_decompress_host(aecb200_ctx *ctx, int options_mask, int bits_per_pixel, int pixels_per_block,
+                               int pixels_per_scanline, const void *source, size_t source_len, void *dest, size_t *dest_len)
+{
+    if (!ctx || !dest_len) return AEC_CONF_ERROR;
+    SzGeom g;
+    sz_geometry(options_mask, bits_per_pixel, pixels_per_block, pixels_per_scanline, 0, &g);
+    AecCfg c;
+    int rc = make_cfg(ctx, &g.prm, 0, &c);
+    if (rc != AEC_OK || pixels_per_scanline <= 0) return AEC_CONF_ERROR;
+    const bool ragged = (pixels_per_scanline % pixels_per_block) != 0;
+    size_t written = 0;
+    if (!ragged && !g.planes) {
+        rc = aecb200_decode_host(ctx, &g.prm, source, source_len, nullptr, 0, dest, *dest_len, &written);
+        if (rc != AEC_OK) return rc;
+        if (written < *dest_len) *dest_len = written;
+        return AEC_OK;
+    }
+    size_t nlines = 0, cap = *dest_len;
+    if (ragged) {
+        nlines = (*dest_len / g.px + (size_t)pixels_per_scanline - 1) / (size_t)pixels_per_scanline;
+        cap = g.full_line * nlines;
+    }
+    ENTER_DEVICE();
+    /* decode into out_stage (the padded, plane-ordered samples stay in HBM) */
+    const uint64_t out_samples = cap / c.B;
+    const uint64_t need_rsi = (out_samples + c.R - 1) / c.R;
+    if (out_samples && source_len) {
+        const size_t in_pad = (source_len + 3) & ~(size_t)3;
+        CK(ctx->in_stage.ensure(in_pad + 16), "cudaMalloc(in)");
+        CK(ctx->out_stage.ensure((size_t)(out_samples * c.B) + 16), "cudaMalloc(out)");
+        CK(ctx->offs.ensure((need_rsi + 1) * 8), "cudaMalloc(offsets)");
+        CK(cudaMemsetAsync((uint8_t *)ctx->in_stage.p + (in_pad - 4), 0, 4, ctx->stream), "memset(in tail)");
+        CK(cudaMemcpyAsync(ctx->in_stage.p, source, source_len, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+        size_t nrsi = 0;
+        rc = aecb200_scan_offsets_device(ctx, &g.prm, ctx->in_stage.p, source_len, 0, (uint64_t *)ctx->offs.p, (size_t)need_rsi, &nrsi);
+        if (rc != AEC_OK && rc != AEC_DATA_ERROR) return rc;
+        rc = aecb200_decode_device(ctx, &g.prm, ctx->in_stage.p, source_len, (const uint64_t *)ctx->offs.p, nrsi,
+                                   ctx->out_stage.p, (size_t)(out_samples * c.B));
+        if (rc == AEC_OK) rc = aecb200_decode_finish(ctx, &written);
+        if (rc != AEC_OK) return rc;
+    }
+    if (cap - written > 0 && cap - written < c.B) return AEC_MEM_ERROR;      /* decode.c:821-823 */
+    size_t total = written;
+    if (ragged) total = nlines * g.line;                                     /* sz_compat.c:243-250 */
+    if (total < *dest_len) *dest_len = total;
+    const size_t n = *dest_len;
+    if (n) {
+        CK(ctx->out2_stage.ensure(n + 16), "cudaMalloc(sz out)");
+        if (g.planes && n % g.ws)            /* bytes behind the last whole word are not written by the reference either */
+            CK(cudaMemsetAsync(ctx->out2_stage.p, 0, n, ctx->stream), "memset(sz out)");
+        CK(aec_sz_unpack_launch((const uint8_t *)ctx->out_stage.p, (uint8_t *)ctx->out2_stage.p, n, g.ws,
+                                ragged ? g.line : (size_t)1 << 62, ragged ? g.full_line : (size_t)1 << 62, ctx->stream),
+           "sz unpack launch");
+        ctx->launches += 1;
+        CK(cudaMemcpyAsync(dest, ctx->out2_stage.p, n, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+        CK(cudaStreamSynchronize(ctx->stream), "sync");
+    }
     return AEC_OK;
 }
 

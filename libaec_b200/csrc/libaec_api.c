@@ -98,6 +98,10 @@ static void ctx_put(aecb200_ctx *c)
     if (c) aecb200_ctx_destroy(c);
 }
 
+/* the same pool for callers outside this file (the SZIP shim, batch calls) */
+aecb200_ctx *aecb200_pool_get(void) { return ctx_get(); }
+void aecb200_pool_put(aecb200_ctx *c) { ctx_put(c); }
+
 static unsigned bytes_per_sample(const struct aec_stream *s)
 {
     unsigned n = s->bits_per_sample;

@@ -405,3 +405,24 @@ def test_encoder_repeated_large_runs_byte_exact(torch_cuda, name, mib, reps):
         enc = L.buffer_encode(p, raw)
         assert enc["status"] == 0 and hashlib.sha256(enc["out"].tobytes()).hexdigest() == h_want, (name, rep)
     codec.close()
+
+
+def test_sz_batch_many_chunks_in_flight():
+    """aecb200_sz_compress_batch / _decompress_batch: every chunk of a batch equals what the oracle's
+    SZ_BufftoBuffCompress gives for it (BASELINE config 3 geometry and a ragged 64-bit one)."""
+    rng = np.random.default_rng(3)
+    for bpp, ppb, pps, mask, nbytes in [(8, 32, 4096, 16 | 32 | 128 | 1, 1 << 20), (64, 8, 1000, 16 | 32 | 128, 200_000)]:
+        chunks = []
+        for i in range(12):
+            n = nbytes - (i % 3) * 4096 * (bpp // 8)
+            chunks.append(np.cumsum(rng.integers(-2, 3, size=n)).astype(np.uint8))
+        caps = [c.size * 2 + 1000 for c in chunks]
+        got = L.sz_compress_batch(chunks, caps, mask, bpp, ppb, pps, threads=4)
+        assert got["status"] == 0 and all(s == 0 for s in got["statuses"])
+        for c, out in zip(chunks, got["out"]):
+            want = po.orc_sz_compress(c, c.size * 2 + 1000, mask, bpp, ppb, pps)
+            assert want["status"] == 0 and np.array_equal(out, want["out"]), (bpp, ppb, pps)
+        back = L.sz_decompress_batch([o.copy() for o in got["out"]], [c.size for c in chunks], mask, bpp, ppb, pps, threads=4)
+        assert back["status"] == 0
+        for c, out in zip(chunks, back["out"]):
+            assert np.array_equal(out, c), (bpp, ppb, pps)
