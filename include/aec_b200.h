@@ -185,6 +185,12 @@ int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
 void aecb200_ctx_set_scan_mode(aecb200_ctx *ctx, int mode, uint64_t window_bits);
 /* RSIs of the last scan whose length came from the tables (the rest were skimmed serially). */
 uint64_t aecb200_ctx_last_scan_fast(aecb200_ctx *ctx);
+/* AEC_NO_FLUSH decoding accumulates the stream on the device: after aecb200_ctx_accumulate_next(ctx, b)
+ * the next aecb200_decode_host_resume call treats in[0] as byte b (a multiple of 4) of one stream whose
+ * earlier bytes, uploaded by earlier such calls, are still in HBM, and uploads only what is new.
+ * b < 0 starts a new stream.  aecb200_ctx_accumulated_uploads: bytes uploaded that way so far. */
+void aecb200_ctx_accumulate_next(aecb200_ctx *ctx, long long stream_byte0);
+uint64_t aecb200_ctx_accumulated_uploads(aecb200_ctx *ctx);
 /* RSI start offsets the last aecb200_decode_host / _resume call without an index discovered (bits from
  * in[0]); returns their number, copies at most cap of them. */
 size_t aecb200_ctx_found_offsets(aecb200_ctx *ctx, uint64_t *dst, size_t cap);

@@ -100,7 +100,8 @@ DEVICE_SYMBOLS = ["aecb200_device_count", "aecb200_current_device", "aecb200_ctx
                   "aecb200_ctx_found_offsets", "aecb200_ctx_set_shard_out", "aecb200_shard_plan_device",
                   "aecb200_encode_repair_device", "aecb200_place_bits_planned", "aecb200_set_device",
                   "aecb200_sz_compress_host", "aecb200_sz_decompress_host", "aecb200_sz_compress_batch",
-                  "aecb200_sz_decompress_batch", "aecb200_pool_get", "aecb200_pool_put"]
+                  "aecb200_sz_decompress_batch", "aecb200_pool_get", "aecb200_pool_put",
+                  "aecb200_ctx_accumulate_next", "aecb200_ctx_accumulated_uploads"]
 SZ_SYMBOLS = ["SZ_BufftoBuffCompress", "SZ_BufftoBuffDecompress", "SZ_encoder_enabled", "SZ_Compress"]
 
 
@@ -131,6 +132,8 @@ def load_library() -> C.CDLL:
         lib.aecb200_ctx_set_shard_out.restype = None
         lib.aecb200_pool_get.restype = C.c_void_p
         lib.aecb200_pool_put.restype = None
+        lib.aecb200_ctx_accumulate_next.restype = None
+        lib.aecb200_ctx_accumulated_uploads.restype = C.c_uint64
         _lib = lib
     return _lib
 

@@ -265,8 +265,34 @@ __device__ __forceinline__ void warp_decode_block(const AecCfg &c, Rd64 &rd, uin
         return;
     }
     if (id == (1u << c.idl) - 1u) {
-#pragma unroll 4
-        for (uint32_t i = 0; i < J; i++) { uint32_t v = rd.get(c.n); row[i] = (i >= ref) ? la.add(v) : v; }
+        /* J fields of n bits, one after the other: the words they occupy are known now, so they are
+         * fetched eight at a time with all loads in flight together.  (Through get() every sample waited
+         * for a load issued one refill earlier: with a word consumed per sample the lanes of
+         * incompressible data spent 57 % of their stall samples there, profiles/r2_summary.md.) */
+        uint32_t i = 0;
+        while (i < J) {
+            uint32_t wv[8];
+            wv[0] = rd.nextw;
+#pragma unroll
+            for (int j = 1; j < 8; j++) wv[j] = rd.ldraw(rd.widx + (uint32_t)j);
+            uint32_t used = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                while (rd.nb >= (int)c.n && i < J) {
+                    const uint32_t v = (uint32_t)(rd.acc >> 32) >> (32u - c.n);
+                    rd.acc <<= c.n; rd.nb -= (int)c.n;
+                    row[i] = (i >= ref) ? la.add(v) : v;
+                    i++;
+                }
+                if (i < J) {                              /* nb < n <= 32: room for the next word */
+                    rd.acc |= (uint64_t)__byte_perm(wv[j], 0, 0x0123) << (32 - rd.nb);
+                    rd.nb += 32;
+                    used = (uint32_t)j + 1u;
+                }
+            }
+            rd.widx += used;
+            rd.nextw = rd.ldraw(rd.widx);                 /* the word behind the ones taken (a cache hit) */
+        }
         return;
     }
     const uint32_t k = id - 1u;

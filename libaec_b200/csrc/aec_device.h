@@ -117,6 +117,7 @@ struct AecSkimArgs {
     uint32_t last;              /* last window of the stream */
     uint32_t LV;                /* levels of the CDS chain tables (level j = 2^j CDSs) */
     uint32_t la_words;          /* filled by the launcher: words staged beyond a tile */
+    uint32_t bulk;              /* filled by the launcher: tiles can be staged with cp.async.bulk (16-byte aligned) */
     uint32_t *T;                /* [LV][np] */
     uint32_t *H;                /* [np] RSI lengths (first-CDS entries between the kernels) */
     uint64_t *state;            /* [0] next RSI bit, [1] RSIs found, [2] flags (1 ended, 2 data error), [3] RSIs taken from the tables */

@@ -49,6 +49,20 @@ struct DevBuf {
         if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, cap, st);
         return e;
     }
+    /* same, keeping the first `keep` bytes */
+    cudaError_t ensure_preserve(size_t n, size_t keep, cudaStream_t st)
+    {
+        if (n <= cap) return cudaSuccess;
+        void *np = nullptr;
+        size_t want = n + n / 2 + 256;
+        cudaError_t e = cudaMalloc(&np, want);
+        if (e != cudaSuccess) return e;
+        if (p && keep) e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (p) cudaFree(p);
+        p = np; cap = want;
+        return e;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
@@ -66,6 +80,14 @@ struct aecb200_ctx {
     DevBuf grp, rsi_list, desc, pref, headc, tailc, tile_end, tile_kagg, misc, in_stage, out_stage, offs, rsi_count, plan;
     void *shard_out = nullptr;           /* device: (bits, klo, khi, tail64) of every shard-mode encode */
     DevBuf raw_stage, out2_stage;        /* SZIP shim: the caller's bytes before / after the byte shuffles */
+    /* streaming decode: the compressed bytes received so far stay in HBM (acc_stage holds stream bytes
+     * [acc_start, acc_start + acc_len)); a call only uploads what is new */
+    DevBuf acc_stage;
+    uint64_t acc_start = 0;
+    size_t acc_len = 0;
+    bool acc_valid = false;
+    long long acc_stream_byte0 = -1;     /* >= 0: the next aecb200_decode_host_resume call accumulates; in[0] is this stream byte */
+    uint64_t acc_uploaded = 0;           /* bytes sent to the device by accumulating calls (diagnostics) */
     bool in_stage_ready = false;         /* the next host encode finds its input in in_stage already */
     uint64_t tile_limit = 0;             /* next encode codes only this many leading tiles (k repair) */
     bool want_summary = false;
@@ -242,7 +264,7 @@ void aecb200_ctx_destroy(aecb200_ctx *ctx)
     ctx->desc.release(); ctx->headc.release(); ctx->tailc.release(); ctx->tile_end.release();
     ctx->misc.release(); ctx->in_stage.release(); ctx->out_stage.release(); ctx->offs.release();
     ctx->rsi_count.release(); ctx->skim_tab.release(); ctx->plan.release();
-    ctx->raw_stage.release(); ctx->out2_stage.release();
+    ctx->raw_stage.release(); ctx->out2_stage.release(); ctx->acc_stage.release();
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -615,7 +637,7 @@ int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
     uint64_t *h_state = &ctx->h_res[8];
     h_state[0] = start_bit; h_state[1] = 0; h_state[2] = 0; h_state[3] = 0;
     CK(cudaMemcpyAsync(state, h_state, 32, cudaMemcpyHostToDevice, ctx->stream), "memcpy(scan state)");
-    const uint64_t base = start_bit & ~31ull;
+    const uint64_t base = start_bit & ~127ull;          /* windows start 16-byte aligned (bulk copies of the tiles) */
     const bool parallel = ctx->scan_mode == 2 || (ctx->scan_mode == 0 && in_bytes >= 2048);
     if (!parallel || base >= nbits) {
         /* short streams: one thread skims CDS after CDS (a dozen launches would cost more) */
@@ -633,7 +655,7 @@ int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
      * every RSI starting inside the window can be followed to its end. */
     const uint32_t LV = aec_skim_levels(c);
     const uint64_t margin = aec_skim_margin_bits(c);
-    uint64_t nh = (ctx->scan_window_bits + 31ull) & ~31ull;
+    uint64_t nh = (ctx->scan_window_bits + 127ull) & ~127ull;
     if (nh < 1024) nh = 1024;
     const uint64_t span = ((nbits - base) + 31ull) & ~31ull;
     const uint64_t nwin = (span + nh - 1) / nh;
@@ -690,6 +712,17 @@ void aecb200_ctx_set_scan_mode(aecb200_ctx *ctx, int mode, uint64_t window_bits)
 }
 
 uint64_t aecb200_ctx_last_scan_fast(aecb200_ctx *ctx) { return ctx ? ctx->scan_fast : 0; }
+
+/* Streaming decode: the next aecb200_decode_host_resume call keeps the compressed bytes it uploads in
+ * HBM and sends only bytes it has not seen (in[0] is byte stream_byte0 of the stream, a multiple of 4).
+ * stream_byte0 < 0 forgets the accumulated stream. */
+void aecb200_ctx_accumulate_next(aecb200_ctx *ctx, long long stream_byte0)
+{
+    if (!ctx) return;
+    if (stream_byte0 < 0) { ctx->acc_valid = false; ctx->acc_len = 0; ctx->acc_stream_byte0 = -1; }
+    else ctx->acc_stream_byte0 = stream_byte0;
+}
+uint64_t aecb200_ctx_accumulated_uploads(aecb200_ctx *ctx) { return ctx ? ctx->acc_uploaded : 0; }
 
 size_t aecb200_ctx_found_offsets(aecb200_ctx *ctx, uint64_t *dst, size_t cap)
 {
@@ -912,11 +945,35 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
     const uint64_t base_bit = (uint64_t)base_byte * 8ull;
     const size_t nbytes = in_bytes - base_byte;
     const size_t in_pad = (nbytes + 3) & ~(size_t)3;
-    CK(ctx->in_stage.ensure(in_pad + 16), "cudaMalloc(in)");
     CK(ctx->out_stage.ensure((size_t)(out_samples * c.B) + 16), "cudaMalloc(out)");
     CK(ctx->offs.ensure((need_rsi + 1) * 8), "cudaMalloc(offsets)");
-    CK(cudaMemsetAsync((uint8_t *)ctx->in_stage.p + (in_pad - 4), 0, 4, ctx->stream), "memset(in tail)");
-    CK(cudaMemcpyAsync(ctx->in_stage.p, (const uint8_t *)in + base_byte, nbytes, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+    const uint8_t *d_stream;                                     /* device copy of in[base_byte .. in_bytes) */
+    const long long acc0 = ctx->acc_stream_byte0;
+    ctx->acc_stream_byte0 = -1;
+    if (acc0 >= 0) {
+        /* accumulate: bytes of this stream uploaded by earlier calls are still in acc_stage */
+        const uint64_t A = (uint64_t)acc0 + base_byte, E = (uint64_t)acc0 + in_bytes;
+        if (!ctx->acc_valid || A < ctx->acc_start || ctx->acc_start + ctx->acc_len > E || A > ctx->acc_start + ctx->acc_len ||
+            A - ctx->acc_start > ((uint64_t)64 << 20)) {
+            ctx->acc_start = A; ctx->acc_len = 0; ctx->acc_valid = true;
+        }
+        const size_t want_len = (size_t)(E - ctx->acc_start);
+        CK(ctx->acc_stage.ensure_preserve(want_len + 16, ctx->acc_len, ctx->stream), "cudaMalloc(stream)");
+        if (want_len > ctx->acc_len) {
+            CK(cudaMemcpyAsync((uint8_t *)ctx->acc_stage.p + ctx->acc_len,
+                               (const uint8_t *)in + (size_t)(ctx->acc_start + ctx->acc_len - (uint64_t)acc0), want_len - ctx->acc_len,
+                               cudaMemcpyHostToDevice, ctx->stream), "H2D");
+            ctx->acc_uploaded += want_len - ctx->acc_len;
+        }
+        ctx->acc_len = want_len;
+        CK(cudaMemsetAsync((uint8_t *)ctx->acc_stage.p + want_len, 0, 8, ctx->stream), "memset(stream tail)");
+        d_stream = (const uint8_t *)ctx->acc_stage.p + (size_t)(A - ctx->acc_start);
+    } else {
+        CK(ctx->in_stage.ensure(in_pad + 16), "cudaMalloc(in)");
+        CK(cudaMemsetAsync((uint8_t *)ctx->in_stage.p + (in_pad - 4), 0, 4, ctx->stream), "memset(in tail)");
+        CK(cudaMemcpyAsync(ctx->in_stage.p, (const uint8_t *)in + base_byte, nbytes, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+        d_stream = (const uint8_t *)ctx->in_stage.p;
+    }
     size_t nrsi = 0;
     uint64_t scan_end = 0;
     uint64_t *h_offs = nullptr;
@@ -936,7 +993,7 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
             if (e != cudaSuccess) { free(h_offs); return fail_cuda(ctx, e, "H2D offsets"); }
         }
     } else {
-        rc = aecb200_scan_offsets_device(ctx, p, ctx->in_stage.p, nbytes, start_bit - base_bit,
+        rc = aecb200_scan_offsets_device(ctx, p, d_stream, nbytes, start_bit - base_bit,
                                          (uint64_t *)ctx->offs.p, (size_t)need_rsi, &nrsi);
         if (rc != AEC_OK && rc != AEC_DATA_ERROR) return rc;
         scan_end = ctx->scan_end;
@@ -951,7 +1008,7 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
         for (size_t i = 0; i < nrsi; i++) ctx->found_offs[i] = h_offs[i] + base_bit;
     }
     size_t written = 0;
-    rc = aecb200_decode_device(ctx, p, ctx->in_stage.p, nbytes, (const uint64_t *)ctx->offs.p, nrsi,
+    rc = aecb200_decode_device(ctx, p, d_stream, nbytes, (const uint64_t *)ctx->offs.p, nrsi,
                                ctx->out_stage.p, (size_t)(out_samples * c.B));
     if (rc == AEC_OK) rc = aecb200_decode_finish(ctx, &written);
     if (rc != AEC_OK) { free(h_offs); return rc; }

@@ -42,20 +42,52 @@ aec_skim_level0_kernel(const AecSkimArgs a)
 {
     if (a.state[2] & 1ull) return;                      /* the walk has already ended */
     const AecCfg &c = a.cfg;
-    extern __shared__ uint32_t sk_smem[];
+    extern __shared__ __align__(16) uint32_t sk_smem[];
     const uint32_t nwords = SK_TILE / 32u + a.la_words;
-    uint32_t *w = sk_smem;                              /* [nwords + 1] */
-    uint32_t *pre = sk_smem + nwords + 1u;              /* [nwords + 1] */
+    uint32_t *w = sk_smem;                              /* [nwords + 1], padded to a multiple of 4 words */
+    uint32_t *pre = sk_smem + ((nwords + 1u + 3u) & ~3u);   /* [nwords + 1] */
     __shared__ uint32_t s_part[SK_THREADS / 32];
+    __shared__ __align__(8) unsigned long long s_mbar;
     const uint32_t tid = threadIdx.x;
     const uint32_t tile0 = blockIdx.x * SK_TILE;        /* window-relative */
     const uint64_t word0 = (a.wb + tile0) >> 5;
     const uint64_t total_words = (a.nbits + 31ull) >> 5;
 
-    /* stage the words (big endian) and their running popcount */
-    for (uint32_t i = tid; i <= nwords; i += SK_THREADS) {
+    /* Stage the tile's words: one bulk asynchronous copy (cp.async.bulk, the TMA engine's 1-D form)
+     * brings the 16-byte aligned part straight into shared memory and signals an mbarrier; what lies
+     * behind the last whole 16 bytes of the stream comes by ordinary loads (zeros past the end). */
+    uint32_t nbulk = 0;                                 /* words the bulk copy delivers */
+    if (a.bulk && word0 < total_words) {
+        const uint64_t avail = (total_words - word0) & ~3ull;
+        const uint32_t want = (nwords + 1u) & ~3u;
+        nbulk = avail < want ? (uint32_t)avail : want;
+    }
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    if (nbulk) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = nbulk * 4u;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(w);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst), "l"(a.in_words + word0), "r"(bytes), "r"(mbar) : "memory");
+        }
+    }
+    for (uint32_t i = nbulk + tid; i <= nwords; i += SK_THREADS) {
         const uint64_t wi = word0 + i;
         w[i] = wi < total_words ? __byte_perm(__ldg(a.in_words + wi), 0, 0x0123) : 0u;
+    }
+    if (nbulk) {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
+        for (uint32_t i = tid; i < nbulk; i += SK_THREADS) w[i] = __byte_perm(w[i], 0, 0x0123);   /* to big endian */
     }
     __syncthreads();
     {
@@ -222,7 +254,9 @@ cudaError_t aec_skim_window_launch(const AecSkimArgs &args, cudaStream_t st)
     AecSkimArgs a = args;
     if (a.np == 0) return cudaSuccess;
     a.la_words = sk_lookahead_words(a.cfg);
-    const uint32_t smem = 2u * (SK_TILE / 32u + a.la_words + 1u) * 4u;
+    /* the bulk copy wants 16-byte aligned addresses on both sides */
+    a.bulk = ((reinterpret_cast<uintptr_t>(a.in_words) & 15u) == 0 && (a.wb & 127ull) == 0) ? 1u : 0u;
+    const uint32_t smem = (((SK_TILE / 32u + a.la_words + 1u + 3u) & ~3u) + SK_TILE / 32u + a.la_words + 1u) * 4u;
     aec_skim_level0_kernel<<<(a.np + SK_TILE - 1u) / SK_TILE, SK_THREADS, smem, st>>>(a);
     const uint32_t grid = (a.np / 4u + SK_THREADS - 1u) / SK_THREADS;
     for (uint32_t j = 0; j + 1u < a.LV; j++)

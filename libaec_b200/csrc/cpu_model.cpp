@@ -253,7 +253,7 @@ extern "C" int model_scan_offsets(uint32_t n, uint32_t J, uint32_t rsi, uint32_t
     SkWalk s; s.pos = start_bit; s.found = 0; s.flags = 0; s.fast = 0;
     *found = 0; *out_flags = 0; *fast = 0; *end_pos = start_bit;
     if (max_rsi == 0) return 0;
-    const uint64_t base = start_bit & ~31ull;
+    const uint64_t base = start_bit & ~127ull;
     if (serial || base >= nbits) {
         /* the one-thread scan (aec_scan_offsets_kernel) */
         RsiDec st; st.pos = start_bit; st.zero_left = 0; st.status = DEC_OK;
@@ -272,7 +272,7 @@ extern "C" int model_scan_offsets(uint32_t n, uint32_t J, uint32_t rsi, uint32_t
     }
     const uint32_t LV = sk_levels(c);
     const uint64_t margin = sk_margin_bits(c);
-    uint64_t nh = (window_bits + 31ull) & ~31ull;
+    uint64_t nh = (window_bits + 127ull) & ~127ull;
     if (nh < 1024) nh = 1024;
     const uint64_t span = ((nbits - base) + 31ull) & ~31ull;
     const uint64_t nwin = (span + nh - 1) / nh;

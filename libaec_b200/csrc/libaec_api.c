@@ -335,6 +335,7 @@ int aec_decode_init(struct aec_stream *strm)
     if (rc != AEC_OK) return rc;
     struct internal_state *st = state_new(strm, 1);
     if (!st) return AEC_MEM_ERROR;
+    aecb200_ctx_accumulate_next(st->ctx, -1);           /* a pooled context may still hold another stream */
     strm->state = st;
     strm->total_in = 0;
     strm->total_out = 0;
@@ -417,7 +418,7 @@ static int cbuf_append(struct internal_state *st, const unsigned char *p, size_t
 
 /* one decode attempt over `in` (stream bytes starting at stream bit base_bits) */
 static int decode_attempt(struct aec_stream *strm, struct internal_state *st,
-                          const unsigned char *in, size_t in_len, uint64_t base_bits, int *filled)
+                          const unsigned char *in, size_t in_len, uint64_t base_bits, int *filled, int accumulate)
 {
     size_t want = (strm->avail_out / st->B) * st->B;
     int direct = want >= DEC_AHEAD_BYTES || st->oneshot;
@@ -443,6 +444,8 @@ static int decode_attempt(struct aec_stream *strm, struct internal_state *st,
         for (size_t i = 0; i < nidx; i++) rebased[i] = idx[first + i] - base_bits;
         idx = rebased;
     }
+    /* the buffered stream stays on the device between attempts: only new bytes are uploaded */
+    if (accumulate) aecb200_ctx_accumulate_next(st->ctx, (long long)(base_bits / 8));
     int rc = aecb200_decode_host_resume(st->ctx, &st->prm, in, in_len, idx, nidx,
                                         st->rsi_bit - base_bits, st->rsi_delivered,
                                         dst, want, &got, &rbit, &rdel);
@@ -489,7 +492,7 @@ int aec_decode(struct aec_stream *strm, int flush)
         if (st->oneshot && st->clen == 0) {
             /* whole stream is in the caller's buffer: decode from it directly */
             if (strm->avail_in == 0 || strm->avail_out < st->B) break;
-            rc = decode_attempt(strm, st, strm->next_in, strm->avail_in, 0, &filled);
+            rc = decode_attempt(strm, st, strm->next_in, strm->avail_in, 0, &filled, 0);
             if (rc != AEC_OK) return rc;
             strm->total_in += strm->avail_in;
             strm->next_in += strm->avail_in; strm->avail_in = 0;
@@ -499,7 +502,7 @@ int aec_decode(struct aec_stream *strm, int flush)
             /* nothing buffered and a large piece of the stream at hand: decode from the caller's
              * buffer, then keep only the bytes from the RSI of the next undelivered sample on */
             const size_t n = strm->avail_in;
-            rc = decode_attempt(strm, st, strm->next_in, n, st->cbase_bits, &filled);
+            rc = decode_attempt(strm, st, strm->next_in, n, st->cbase_bits, &filled, 0);
             if (rc != AEC_OK) return rc;
             size_t keep_from = (size_t)(((st->rsi_bit - st->cbase_bits) >> 5) << 2);
             if (keep_from > n) keep_from = n - n % 4;
@@ -516,7 +519,7 @@ int aec_decode(struct aec_stream *strm, int flush)
             st->new_input = 1;
         }
         if (!st->new_input || strm->avail_out < st->B) break;
-        rc = decode_attempt(strm, st, st->cbuf, st->clen, st->cbase_bits, &filled);
+        rc = decode_attempt(strm, st, st->cbuf, st->clen, st->cbase_bits, &filled, 1);
         if (rc != AEC_OK) return rc;
         st->new_input = filled;                         /* more may be decodable without new input */
         /* forget bytes in front of the current RSI (keep 32-bit alignment of the base) */

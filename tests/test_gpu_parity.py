@@ -426,3 +426,26 @@ def test_sz_batch_many_chunks_in_flight():
         assert back["status"] == 0
         for c, out in zip(chunks, back["out"]):
             assert np.array_equal(out, c), (bpp, ppb, pps)
+
+
+def test_streaming_decode_keeps_the_stream_on_the_device():
+    """AEC_NO_FLUSH decoding with windows far smaller than the buffered input: the bytes of the stream
+    are uploaded once (they accumulate in HBM), not once per attempt, and the output is the oracle's."""
+    p, _ = datagen.CONFIGS["c1"]
+    raw = datagen.generate("c1", (6 << 20) // 4)
+    op = po.Params(p.bits_per_sample, p.block_size, p.rsi, p.flags)
+    comp = po.orc_encode(op, raw)["out"]
+    lib = L.load_library()
+    import ctypes as C
+    ctx_before = C.c_void_p(lib.aecb200_pool_get())
+    before = lib.aecb200_ctx_accumulated_uploads(ctx_before)
+    lib.aecb200_pool_put(ctx_before)
+    dec = L.Decoder(p)
+    out = dec.run(comp, in_chunk=200_000, out_chunk=300_000, out_cap=raw.size)
+    assert dec.close() == 0 and np.array_equal(out, raw)
+    ctx_after = C.c_void_p(lib.aecb200_pool_get())
+    sent = lib.aecb200_ctx_accumulated_uploads(ctx_after) - before
+    lib.aecb200_pool_put(ctx_after)
+    assert ctx_after.value == ctx_before.value
+    # every stream byte goes up about once (re-staging after trims allowed), not once per output window
+    assert comp.size * 0.5 <= sent <= comp.size * 3, (sent, comp.size)
