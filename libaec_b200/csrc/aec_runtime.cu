@@ -86,6 +86,7 @@ struct aecb200_ctx {
     uint64_t acc_start = 0;
     size_t acc_len = 0;
     bool acc_valid = false;
+    aecb200_ctx *aux = nullptr;          /* second context (stream + workspace): decodes RSIs already discovered while the scan goes on */
     long long acc_stream_byte0 = -1;     /* >= 0: the next aecb200_decode_host_resume call accumulates; in[0] is this stream byte */
     uint64_t acc_uploaded = 0;           /* bytes sent to the device by accumulating calls (diagnostics) */
     bool in_stage_ready = false;         /* the next host encode finds its input in in_stage already */
@@ -99,6 +100,7 @@ struct aecb200_ctx {
     cudaStream_t s_idx[4] = {nullptr, nullptr, nullptr, nullptr};   /* group-index builds of the decode pipeline */
     cudaStream_t s_walk = nullptr;                                   /* RSI boundary walk (aec_skim.cu) */
     cudaEvent_t ev_skim[4] = {nullptr, nullptr, nullptr, nullptr};   /* tables ready [0,1], walk done [2,3] per table set */
+    cudaEvent_t ev_prog[4] = {nullptr, nullptr, nullptr, nullptr};   /* walk of window i done, ring of four (progress hook) */
     std::vector<cudaEvent_t> ev;
     size_t pipe_piece = (size_t)16 << 20; /* bytes of raw samples per piece; 0 = never pipeline */
 
@@ -239,7 +241,7 @@ int aecb200_ctx_create(aecb200_ctx **out, int device)
     e = dg.enter(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) { ctx->own_stream = true; e = cudaMallocHost(&ctx->h_res, 16 * sizeof(uint64_t)); }
+    if (e == cudaSuccess) { ctx->own_stream = true; e = cudaMallocHost(&ctx->h_res, 32 * sizeof(uint64_t)); }
     if (e != cudaSuccess) {
         fprintf(stderr, "aecb200: no usable CUDA device (%s); this library has no CPU fallback\n",
                 cudaGetErrorString(e));
@@ -265,6 +267,7 @@ void aecb200_ctx_destroy(aecb200_ctx *ctx)
     ctx->misc.release(); ctx->in_stage.release(); ctx->out_stage.release(); ctx->offs.release();
     ctx->rsi_count.release(); ctx->skim_tab.release(); ctx->plan.release();
     ctx->raw_stage.release(); ctx->out2_stage.release(); ctx->acc_stage.release();
+    if (ctx->aux) { aecb200_ctx_destroy(ctx->aux); ctx->aux = nullptr; }
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -272,6 +275,7 @@ void aecb200_ctx_destroy(aecb200_ctx *ctx)
     for (cudaStream_t st : ctx->s_idx) if (st) cudaStreamDestroy(st);
     if (ctx->s_walk) cudaStreamDestroy(ctx->s_walk);
     for (cudaEvent_t e : ctx->ev_skim) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_prog) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -616,9 +620,27 @@ int aecb200_decode_finish(aecb200_ctx *ctx, size_t *out_written)
     return AEC_OK;
 }
 
+/* Hook of the un-indexed host decode: called between windows with the number of RSIs whose offsets are
+ * final, so that they can be decoded and sent back while the discovery goes on. */
+struct ScanProgress {
+    virtual int consume(uint64_t complete_rsis, cudaEvent_t offsets_ready) = 0;
+    virtual ~ScanProgress() {}
+};
+
+static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
+                             const void *d_in, size_t in_bytes, uint64_t start_bit,
+                             uint64_t *d_rsi_offsets, size_t max_rsi, size_t *found, ScanProgress *prog);
+
 int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
                                 const void *d_in, size_t in_bytes, uint64_t start_bit,
                                 uint64_t *d_rsi_offsets, size_t max_rsi, size_t *found)
+{
+    return scan_offsets_impl(ctx, p, d_in, in_bytes, start_bit, d_rsi_offsets, max_rsi, found, nullptr);
+}
+
+static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
+                             const void *d_in, size_t in_bytes, uint64_t start_bit,
+                             uint64_t *d_rsi_offsets, size_t max_rsi, size_t *found, ScanProgress *prog)
 {
     if (!ctx || !p) return AEC_CONF_ERROR;
     AecCfg c;
@@ -669,6 +691,8 @@ int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
     if (!ctx->s_walk) CK(cudaStreamCreateWithFlags(&ctx->s_walk, cudaStreamNonBlocking), "cudaStreamCreate(walk)");
     for (cudaEvent_t &e : ctx->ev_skim)
         if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    for (cudaEvent_t &e : ctx->ev_prog)
+        if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
     AecSkimArgs a;
     memset(&a, 0, sizeof a);
     a.cfg = c;
@@ -693,7 +717,22 @@ int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
         CK(cudaStreamWaitEvent(ctx->s_walk, ctx->ev_skim[k], 0), "cudaStreamWaitEvent");
         CK(aec_skim_walk_launch(a, ctx->s_walk), "walk launch");
         CK(cudaEventRecord(ctx->ev_skim[2 + k], ctx->s_walk), "cudaEventRecord");
+        if (prog) {
+            const int s4 = (int)(i & 3u);
+            CK(cudaMemcpyAsync(&ctx->h_res[16 + 4 * s4], state, 32, cudaMemcpyDeviceToHost, ctx->s_walk), "memcpy(scan progress)");
+            CK(cudaEventRecord(ctx->ev_prog[s4], ctx->s_walk), "cudaEventRecord");
+        }
         ctx->launches += LV + 2u;
+        if (prog && i >= 2) {
+            /* The walk through the window two back has finished long ago; two windows of work are queued
+             * behind it, so the device stays busy while the host hands that window's RSIs on (a copy to
+             * pageable memory holds the host for its whole duration).  Every RSI the walk found except
+             * the last has its successor's offset too. */
+            const int sp = (int)((i - 2) & 3u);
+            CK(cudaEventSynchronize(ctx->ev_prog[sp]), "scan progress sync");
+            const uint64_t f = ctx->h_res[16 + 4 * sp + 1];
+            if (f > 1) { rc = prog->consume(f - 1, ctx->ev_prog[sp]); if (rc != AEC_OK) return rc; }
+        }
     }
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_skim[2 + (int)((nwin - 1) & 1u) % nsets], 0), "cudaStreamWaitEvent");
     CK(cudaMemcpyAsync(&ctx->h_res[12], state, 32, cudaMemcpyDeviceToHost, ctx->stream), "memcpy(scan)");
@@ -892,6 +931,45 @@ int aecb200_encode_host_piece(aecb200_ctx *ctx, const aecb200_params *p,
                             rsi_offsets, offsets_cap, n_offsets);
 }
 
+/* RSIs the boundary discovery has finished with are decoded on the context's second stream/workspace and
+ * copied to the caller while the discovery goes on (ScanProgress hook of scan_offsets_impl). */
+struct EarlyDecode : ScanProgress {
+    bool on = false, failed = false, pending = false;
+    aecb200_ctx *ctx = nullptr;
+    const aecb200_params *p = nullptr;
+    const uint8_t *d_stream = nullptr;
+    size_t nbytes = 0, rsi_out = 0, pending_expect = 0;
+    uint8_t *out = nullptr;
+    uint64_t R = 0, full_rsis = 0, min_rsis = 1, done = 0;
+    void finish_pending()
+    {
+        if (!pending) return;
+        size_t got = 0;
+        const int rc = aecb200_decode_finish(ctx->aux, &got);
+        pending = false;
+        if (rc != AEC_OK || got != pending_expect) failed = true;
+    }
+    int consume(uint64_t complete, cudaEvent_t offsets_ready) override
+    {
+        if (failed) return AEC_OK;
+        if (complete > full_rsis) complete = full_rsis;             /* only RSIs wanted in full */
+        if (complete < done + min_rsis) return AEC_OK;
+        finish_pending();
+        if (failed) return AEC_OK;
+        aecb200_ctx *aux = ctx->aux;
+        if (cudaStreamWaitEvent(aux->stream, offsets_ready, 0) != cudaSuccess) { failed = true; return AEC_OK; }
+        const uint64_t r0 = done, r1 = complete;
+        const size_t nb = (size_t)(r1 - r0) * rsi_out;
+        uint8_t *d_out = (uint8_t *)ctx->out_stage.p + (size_t)r0 * rsi_out;
+        int rc = aecb200_decode_device(aux, p, d_stream, nbytes, (const uint64_t *)ctx->offs.p + r0, (size_t)(r1 - r0), d_out, nb);
+        if (rc != AEC_OK) { failed = true; return AEC_OK; }
+        if (cudaMemcpyAsync(out + (size_t)r0 * rsi_out, d_out, nb, cudaMemcpyDeviceToHost, aux->stream) != cudaSuccess) failed = true;
+        pending = true; pending_expect = nb; done = r1;
+        ctx->launches += 2;
+        return AEC_OK;
+    }
+};
+
 #define AECB200_NOT_PIPELINED 1000
 static int decode_host_pipelined(aecb200_ctx *ctx, const aecb200_params *p, const AecCfg &c,
                                  const void *in, size_t in_bytes,
@@ -977,6 +1055,7 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
     size_t nrsi = 0;
     uint64_t scan_end = 0;
     uint64_t *h_offs = nullptr;
+    EarlyDecode early;
     ctx->found_offs.clear();
     if (rsi_offsets) {
         /* caller's index is relative to bit 0 of `in`: entries from the RSI that starts at start_bit */
@@ -993,8 +1072,31 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
             if (e != cudaSuccess) { free(h_offs); return fail_cuda(ctx, e, "H2D offsets"); }
         }
     } else {
-        rc = aecb200_scan_offsets_device(ctx, p, d_stream, nbytes, start_bit - base_bit,
-                                         (uint64_t *)ctx->offs.p, (size_t)need_rsi, &nrsi);
+        /* Large outputs: RSIs whose offsets are final are decoded on a second context and their
+         * samples sent back while the discovery of the later ones goes on (the download of a README-size
+         * buffer takes a fifth of the discovery time). */
+        const size_t rsi_out = (size_t)c.R * c.B;
+        if (skip_samples == 0 && acc0 < 0 && ctx->pipe_piece && (size_t)(out_samples * c.B) >= 2 * ctx->pipe_piece &&
+            !ctx->careful_only) {
+            if (!ctx->aux && aecb200_ctx_create(&ctx->aux, ctx->device) != AEC_OK) ctx->aux = nullptr;
+            if (ctx->aux) {
+                early.on = true;
+                early.ctx = ctx; early.p = p; early.R = c.R;
+                early.d_stream = d_stream; early.nbytes = nbytes;
+                early.out = (uint8_t *)out; early.rsi_out = rsi_out;
+                early.full_rsis = out_samples / c.R;
+                early.min_rsis = (ctx->pipe_piece + rsi_out - 1) / rsi_out;
+            }
+        }
+        rc = scan_offsets_impl(ctx, p, d_stream, nbytes, start_bit - base_bit,
+                               (uint64_t *)ctx->offs.p, (size_t)need_rsi, &nrsi, early.on ? &early : nullptr);
+        if (early.on) {
+            early.finish_pending();
+            if (early.failed || rc != AEC_OK) {          /* anything unusual: decode everything on the plain path */
+                cudaStreamSynchronize(ctx->aux->stream);
+                early.done = 0;
+            }
+        }
         if (rc != AEC_OK && rc != AEC_DATA_ERROR) return rc;
         scan_end = ctx->scan_end;
         h_offs = (uint64_t *)malloc((nrsi + 1) * sizeof(uint64_t));
@@ -1008,20 +1110,28 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
         for (size_t i = 0; i < nrsi; i++) ctx->found_offs[i] = h_offs[i] + base_bit;
     }
     size_t written = 0;
-    rc = aecb200_decode_device(ctx, p, d_stream, nbytes, (const uint64_t *)ctx->offs.p, nrsi,
-                               ctx->out_stage.p, (size_t)(out_samples * c.B));
+    const uint64_t early_rsis = early.done < nrsi ? early.done : 0;    /* already decoded and on their way to `out` */
+    const size_t early_bytes = (size_t)early_rsis * c.R * c.B;
+    rc = aecb200_decode_device(ctx, p, d_stream, nbytes, (const uint64_t *)ctx->offs.p + early_rsis, nrsi - early_rsis,
+                               (uint8_t *)ctx->out_stage.p + early_bytes, (size_t)(out_samples * c.B) - early_bytes);
     if (rc == AEC_OK) rc = aecb200_decode_finish(ctx, &written);
-    if (rc != AEC_OK) { free(h_offs); return rc; }
+    if (rc != AEC_OK) { free(h_offs); if (early.on) cudaStreamSynchronize(ctx->aux->stream); return rc; }
+    written += early_bytes;
     uint64_t W = written / c.B;                                    /* samples decoded from start_bit */
     /* only RSIs that delivered samples count as discovered (the scan also notes where the zero padding
      * behind the last RSI begins) */
     if (ctx->found_offs.size() > (size_t)((W + c.R - 1) / c.R)) ctx->found_offs.resize((size_t)((W + c.R - 1) / c.R));
     size_t newbytes = W > skip_samples ? (size_t)((W - skip_samples) * c.B) : 0;
-    if (newbytes) {
-        cudaError_t e = cudaMemcpyAsync(out, (uint8_t *)ctx->out_stage.p + skip_samples * c.B, newbytes,
-                                        cudaMemcpyDeviceToHost, ctx->stream);
+    if (newbytes > early_bytes) {
+        /* (early pieces only exist with skip_samples == 0) */
+        cudaError_t e = cudaMemcpyAsync((uint8_t *)out + early_bytes, (uint8_t *)ctx->out_stage.p + skip_samples * c.B + early_bytes,
+                                        newbytes - early_bytes, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { free(h_offs); return fail_cuda(ctx, e, "D2H"); }
+    }
+    if (early.on) {
+        cudaError_t e = cudaStreamSynchronize(ctx->aux->stream);         /* the early pieces have arrived */
+        if (e != cudaSuccess) { free(h_offs); return fail_cuda(ctx, e, "D2H (early pieces)"); }
     }
     if (out_len) *out_len = newbytes;
     if (W < skip_samples) W = skip_samples;
