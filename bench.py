@@ -239,8 +239,10 @@ def run_ours(args):
     p, _ = datagen.CONFIGS[args.workload]
     B = p.bytes_per_sample
     R = p.rsi * p.block_size
-    per_gpu = (args.mib << 20) // B
-    total = per_gpu * world                      # weak scaling: fixed work per GPU
+    if args.strong:
+        total = (args.mib << 20) // B            # strong scaling: --mib is the WHOLE job, split over the ranks
+    else:
+        total = ((args.mib << 20) // B) * world  # weak scaling: fixed work per GPU
     start, count = shard_samples(total, R, rank, world)
     raw = datagen.generate(args.workload, count, start)
     nrsi = (count + R - 1) // R
@@ -500,7 +502,8 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if args.strong else "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": bench_config(args),
         "detail": {"raw_bytes_per_gpu": raw.size, "compressed_bytes_per_gpu": comp_bytes, "ratio": raw.size / comp_bytes,
@@ -527,6 +530,8 @@ def main():
     ap.add_argument("--workload", default="c1")
     ap.add_argument("--mib", type=int, default=256, help="raw MiB per GPU")
     ap.add_argument("--device-only", action="store_true", help="skip the e2e and CPU-baseline legs (for ncu runs)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --mib is the size of the whole job (e.g. 8192 for BASELINE config 5), split over the GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

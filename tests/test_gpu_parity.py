@@ -300,7 +300,8 @@ def _device_roundtrip(torch, codec, name, nsamples, check_oracle):
         assert np.array_equal(d_offs.cpu().numpy().astype(np.uint64), want["offsets"]), name
     # three decode routes must agree bit for bit: warp-per-RSI kernel from the encoder's group
     # index, the same kernel from an index rebuilt on the device, and the careful kernel alone
-    for route in ("encoder-index", "rebuilt-index", "careful"):
+    routes = ("encoder-index", "rebuilt-index", "careful") if raw.size <= (256 << 20) else ("encoder-index", "rebuilt-index")
+    for route in routes:
         d_back = torch.zeros(raw.size + 16, dtype=torch.uint8, device="cuda")
         codec.set_careful_decode(route == "careful")
         grp = d_grp if route == "encoder-index" else None
@@ -308,7 +309,7 @@ def _device_roundtrip(torch, codec, name, nsamples, check_oracle):
         st, written = codec.decode_finish()
         assert st == 0 and written == raw.size, (name, route)
         # decode == input for unsigned / full-width signed data (sign extension is a no-op here)
-        assert np.array_equal(d_back[:raw.size].cpu().numpy(), raw), (name, route)
+        assert torch.equal(d_back[:raw.size], d_in), (name, route)
     codec.set_careful_decode(False)
     # the sequential boundary scan finds the same index
     if nrsi <= 4096:
@@ -359,7 +360,8 @@ def test_device_decode_routes_random_cases(torch_cuda):
     codec.close()
 
 
-@pytest.mark.parametrize("name,mib", [("c1", 256), ("c2", 256), ("c4", 192), ("c5_noise", 128)])
+@pytest.mark.parametrize("name,mib", [("c1", 256), ("c2", 256), ("c3", 256), ("c4", 1024), ("c5_noise", 512),
+                                      ("c5_restricted", 256), ("c5_restricted2", 128)])
 def test_device_path_full_size_round_trip(torch_cuda, name, mib):
     """Full BASELINE sizes through size-independent properties: encode ->
     decode round trip is exact, ratio is the one the CPU reference gets, and
@@ -369,7 +371,11 @@ def test_device_path_full_size_round_trip(torch_cuda, name, mib):
     p, _ = datagen.CONFIGS[name]
     ns = (mib << 20) // p.bytes_per_sample
     ratio = _device_roundtrip(torch_cuda, codec, name, ns, False)
-    expect = {"c1": 3.48, "c2": 11.25, "c4": 2.18, "c5_noise": 0.99}[name]
+    expect = {"c1": 3.48, "c2": 11.25, "c3": 2.60, "c4": 2.18, "c5_noise": 0.99, "c5_restricted": 4.27,
+              "c5_restricted2": None}[name]
+    if expect is None:
+        assert ratio > 1.0
+        return
     assert abs(ratio - expect) < 0.05 * expect, (name, ratio)
     codec.close()
 

@@ -79,3 +79,22 @@ def test_clip_free_blocks_are_zigzag_codes():
         if rngv < (1 << 23):                                             # "small": every code below 2^24
             assert all(map_exact(int(u[i - 1]), int(u[i]), M) < (1 << 24) for i in range(1, J + 1))
     assert hit > 1000
+
+
+def test_se_cost_wrap_is_unreachable():
+    """encode.c:428-429 adds the second-extension cost in uint64 with wrap-around: s*(s+1)/2 overflows when
+    a pair sum s reaches 2^32.  The length is compared with the uncompressed length after EVERY pair
+    (encode.c:430-431), so a wrapped total could only win if ONE pair's term came out small after the wrap.
+    The smallest term (s*(s+1) mod 2^64)/2 + d1 + 1 over all s >= 2^32 is 2^31 + 2, far above the largest
+    uncompressed length (64 * 32 bits): replicating the u64 arithmetic (aec_core.cuh) is enough, no stream
+    can ever show the difference."""
+    import math
+    smallest = None
+    for m in range(1, 5):                                   # s*(s+1) crosses m * 2^64 near sqrt(m * 2^64)
+        root = math.isqrt(m << 64)
+        for s in range(max(root - 3, 1 << 32), min(root + 4, (1 << 33) - 1)):
+            term = ((s * (s + 1)) % (1 << 64)) // 2 + max(0, s - ((1 << 32) - 1)) + 1
+            smallest = term if smallest is None else min(smallest, term)
+    # between two crossings the remainder grows by about 2s per step, so the minima sit at the crossings
+    assert smallest == (1 << 31) + 2
+    assert smallest > 64 * 32
