@@ -14,7 +14,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/aec_b200.h"
@@ -68,7 +71,109 @@ struct DevBuf {
 
 } // namespace
 
+namespace {
+
+/* A few helper threads that copy between pageable caller memory and pinned bounce slots.  cudaMemcpyAsync
+ * on pageable memory goes through one staging thread of the driver (8-11 GB/s up, ~20 GB/s down on the
+ * round's boxes, profiles/r2_summary.md); four threads move 44 GB/s, which keeps PCIe busy for callers
+ * that hand over malloc'd buffers -- every caller of libaec.h.  One copy at a time per process; a
+ * second caller that finds the pool busy copies on its own thread. */
+class HostCopyPool {
+public:
+    static HostCopyPool &get() { static HostCopyPool p; return p; }
+    void copy(void *dst, const void *src, size_t n)
+    {
+        if (n < ((size_t)1 << 20) || !busy.try_lock()) { memcpy(dst, src, n); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (th.empty())
+                for (int i = 0; i < HELPERS; i++) th.emplace_back([this, i] { worker(i); });
+            jdst = (uint8_t *)dst; jsrc = (const uint8_t *)src; jn = n;
+            pending = HELPERS;
+            gen++;
+        }
+        cv.notify_all();
+        part(HELPERS);                                   /* the caller takes the last part */
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            done_cv.wait(lk, [this] { return pending == 0; });
+        }
+        busy.unlock();
+    }
+    ~HostCopyPool()
+    {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; gen++; }
+        cv.notify_all();
+        for (std::thread &t : th) t.join();
+    }
+private:
+    static constexpr int HELPERS = 3;
+    void part(int i)
+    {
+        const size_t per = ((jn / (HELPERS + 1)) + 63) & ~(size_t)63;
+        const size_t a = per * (size_t)i < jn ? per * (size_t)i : jn;
+        const size_t b = (i == HELPERS) ? jn : (a + per < jn ? a + per : jn);
+        if (b > a) memcpy(jdst + a, jsrc + a, b - a);
+    }
+    void worker(int i)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return gen != seen; });
+                seen = gen;
+                if (stop) return;
+            }
+            part(i);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--pending == 0) done_cv.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> th;
+    std::mutex mu, busy;
+    std::condition_variable cv, done_cv;
+    uint8_t *jdst = nullptr; const uint8_t *jsrc = nullptr; size_t jn = 0;
+    int pending = 0; uint64_t gen = 0; bool stop = false;
+};
+
+constexpr size_t BOUNCE_SLOT = (size_t)8 << 20;
+
+struct Bounce {                 /* two pinned slots per direction, each with the event of its last device copy */
+    uint8_t *slot[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool used[4] = {false, false, false, false};
+    unsigned turn[2] = {0, 0};
+    cudaError_t ensure()
+    {
+        for (int i = 0; i < 4; i++) {
+            if (!slot[i]) { cudaError_t e = cudaMallocHost((void **)&slot[i], BOUNCE_SLOT); if (e != cudaSuccess) return e; }
+            if (!ev[i]) { cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+        }
+        return cudaSuccess;
+    }
+    void release()
+    {
+        for (int i = 0; i < 4; i++) {
+            if (ev[i]) { cudaEventSynchronize(ev[i]); cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+            if (slot[i]) { cudaFreeHost(slot[i]); slot[i] = nullptr; }
+        }
+    }
+};
+
+bool host_pointer_is_pageable(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+} // namespace
+
 struct aecb200_ctx {
+    Bounce bounce;
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
@@ -90,6 +195,7 @@ struct aecb200_ctx {
     long long acc_stream_byte0 = -1;     /* >= 0: the next aecb200_decode_host_resume call accumulates; in[0] is this stream byte */
     uint64_t acc_uploaded = 0;           /* bytes sent to the device by accumulating calls (diagnostics) */
     bool in_stage_ready = false;         /* the next host encode finds its input in in_stage already */
+    bool no_bounce = false;              /* pageable host buffers go straight to cudaMemcpyAsync (AECB200_NO_BOUNCE, tests) */
     uint64_t tile_limit = 0;             /* next encode codes only this many leading tiles (k repair) */
     bool want_summary = false;
     bool careful_only = false;           /* decode with the lane-per-RSI kernel only (tests) */
@@ -145,6 +251,59 @@ struct DeviceGuard {
     ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
 };
 #define ENTER_DEVICE() DeviceGuard dg_; CK(dg_.enter(ctx->device), "cudaSetDevice")
+
+/* Host -> device.  Pinned (or small) sources: one asynchronous copy.  Pageable sources: 8 MiB pieces through
+ * two pinned slots, filled by the host-copy pool while the previous slot is on its way; returns when the
+ * last piece is staged (the caller's buffer is no longer needed), its device copy still in flight on `st`. */
+cudaError_t copy_h2d(aecb200_ctx *ctx, void *d_dst, const void *h_src, size_t n, cudaStream_t st)
+{
+    if (n < ((size_t)2 << 20) || ctx->no_bounce || !host_pointer_is_pageable(h_src))
+        return cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, st);
+    Bounce &b = ctx->bounce;
+    cudaError_t e = b.ensure();
+    if (e != cudaSuccess) return e;
+    for (size_t off = 0; off < n; off += BOUNCE_SLOT) {
+        const size_t len = n - off < BOUNCE_SLOT ? n - off : BOUNCE_SLOT;
+        const int k = (int)(b.turn[0]++ & 1u);
+        if (b.used[k] && (e = cudaEventSynchronize(b.ev[k])) != cudaSuccess) return e;
+        HostCopyPool::get().copy(b.slot[k], (const uint8_t *)h_src + off, len);
+        if ((e = cudaMemcpyAsync((uint8_t *)d_dst + off, b.slot[k], len, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(b.ev[k], st)) != cudaSuccess) return e;
+        b.used[k] = true;
+    }
+    return cudaSuccess;
+}
+
+/* Device -> host.  Pinned (or small) destinations: one asynchronous copy (complete when `st` is synchronised).
+ * Pageable destinations: through the two download slots; the data is in place when the call returns. */
+cudaError_t copy_d2h(aecb200_ctx *ctx, void *h_dst, const void *d_src, size_t n, cudaStream_t st)
+{
+    if (n < ((size_t)2 << 20) || ctx->no_bounce || !host_pointer_is_pageable(h_dst))
+        return cudaMemcpyAsync(h_dst, d_src, n, cudaMemcpyDeviceToHost, st);
+    Bounce &b = ctx->bounce;
+    cudaError_t e = b.ensure();
+    if (e != cudaSuccess) return e;
+    size_t prev_off = 0, prev_len = 0;
+    int prev_k = -1;
+    for (size_t off = 0; off < n || prev_k >= 0; off += BOUNCE_SLOT) {
+        int k = -1;
+        size_t len = 0;
+        if (off < n) {
+            len = n - off < BOUNCE_SLOT ? n - off : BOUNCE_SLOT;
+            k = 2 + (int)(b.turn[1]++ & 1u);
+            if (b.used[k] && (e = cudaEventSynchronize(b.ev[k])) != cudaSuccess) return e;   /* (always complete: see below) */
+            if ((e = cudaMemcpyAsync(b.slot[k], (const uint8_t *)d_src + off, len, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(b.ev[k], st)) != cudaSuccess) return e;
+            b.used[k] = true;
+        }
+        if (prev_k >= 0) {                               /* the piece before: wait for it, hand it to the caller */
+            if ((e = cudaEventSynchronize(b.ev[prev_k])) != cudaSuccess) return e;
+            HostCopyPool::get().copy((uint8_t *)h_dst + prev_off, b.slot[prev_k], prev_len);
+        }
+        prev_k = k; prev_off = off; prev_len = len;
+    }
+    return cudaSuccess;
+}
 
 uint32_t next_pow2(uint32_t v)
 {
@@ -250,6 +409,7 @@ int aecb200_ctx_create(aecb200_ctx **out, int device)
         return AECB200_CUDA_ERROR;
     }
     /* test hooks: force one of the RSI boundary discovery paths / a small table window */
+    if (getenv("AECB200_NO_BOUNCE")) ctx->no_bounce = true;
     if (const char *m = getenv("AECB200_SCAN_MODE")) ctx->scan_mode = atoi(m);
     if (const char *w = getenv("AECB200_SCAN_WINDOW_BITS")) { long long v = atoll(w); if (v > 0) ctx->scan_window_bits = (uint64_t)v; }
     *out = ctx;
@@ -268,6 +428,7 @@ void aecb200_ctx_destroy(aecb200_ctx *ctx)
     ctx->rsi_count.release(); ctx->skim_tab.release(); ctx->plan.release();
     ctx->raw_stage.release(); ctx->out2_stage.release(); ctx->acc_stage.release();
     if (ctx->aux) { aecb200_ctx_destroy(ctx->aux); ctx->aux = nullptr; }
+    ctx->bounce.release();
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -819,7 +980,7 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
         }
         aecb200_carry seed = {phase, carry->k, carry->word};
         if (npieces == 1) {
-            if (!staged) CK(cudaMemcpyAsync(ctx->in_stage.p, in, use_bytes, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+            if (!staged) CK(copy_h2d(ctx, ctx->in_stage.p, in, use_bytes, ctx->stream), "H2D");
             rc = aecb200_encode_device(ctx, p, ctx->in_stage.p, use_bytes, ctx->out_stage.p, ctx->out_stage.cap & ~(size_t)3,
                                        &seed, d_offs);
             if (rc != AEC_OK) return rc;
@@ -833,7 +994,7 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
             PipeGuard guard(ctx);
             for (size_t i = 0; i < npieces; i++) {       /* all uploads are queued now and run back to back */
                 const size_t o = i * piece, nb = (o + piece <= use_bytes) ? piece : use_bytes - o;
-                CK(cudaMemcpyAsync((uint8_t *)ctx->in_stage.p + o, (const uint8_t *)in + o, nb, cudaMemcpyHostToDevice, ctx->s_in), "H2D");
+                CK(copy_h2d(ctx, (uint8_t *)ctx->in_stage.p + o, (const uint8_t *)in + o, nb, ctx->s_in), "H2D");
                 CK(cudaEventRecord(ctx->ev[i], ctx->s_in), "cudaEventRecord");
             }
             for (size_t i = 0; i < npieces; i++) {
@@ -853,8 +1014,7 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
                     size_t fin = (size_t)(end_bits >> 5) << 2;
                     if (fin > out_cap) fin = out_cap;
                     if (fin > copied) {
-                        CK(cudaMemcpyAsync((uint8_t *)out + copied, (uint8_t *)ctx->out_stage.p + copied, fin - copied,
-                                           cudaMemcpyDeviceToHost, ctx->s_out), "D2H");
+                        CK(copy_d2h(ctx, (uint8_t *)out + copied, (uint8_t *)ctx->out_stage.p + copied, fin - copied, ctx->s_out), "D2H");
                         copied = fin;
                     }
                     if (end_bits & 31u) {
@@ -886,8 +1046,7 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
     uint32_t tailword = 0;
     if (use_bytes) {
         if (ncopy > copied)
-            CK(cudaMemcpyAsync((uint8_t *)out + copied, (uint8_t *)ctx->out_stage.p + copied, ncopy - copied,
-                               cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+            CK(copy_d2h(ctx, (uint8_t *)out + copied, (uint8_t *)ctx->out_stage.p + copied, ncopy - copied, ctx->stream), "D2H");
         if (!final && (end_bits & 7u)) {
             CK(cudaMemcpyAsync(&ctx->h_res[10], (uint8_t *)ctx->out_stage.p + (end_bits / 8), 1,
                                cudaMemcpyDeviceToHost, ctx->stream), "D2H tail");
@@ -963,7 +1122,7 @@ struct EarlyDecode : ScanProgress {
         uint8_t *d_out = (uint8_t *)ctx->out_stage.p + (size_t)r0 * rsi_out;
         int rc = aecb200_decode_device(aux, p, d_stream, nbytes, (const uint64_t *)ctx->offs.p + r0, (size_t)(r1 - r0), d_out, nb);
         if (rc != AEC_OK) { failed = true; return AEC_OK; }
-        if (cudaMemcpyAsync(out + (size_t)r0 * rsi_out, d_out, nb, cudaMemcpyDeviceToHost, aux->stream) != cudaSuccess) failed = true;
+        if (copy_d2h(aux, out + (size_t)r0 * rsi_out, d_out, nb, aux->stream) != cudaSuccess) failed = true;
         pending = true; pending_expect = nb; done = r1;
         ctx->launches += 2;
         return AEC_OK;
@@ -1049,7 +1208,7 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
     } else {
         CK(ctx->in_stage.ensure(in_pad + 16), "cudaMalloc(in)");
         CK(cudaMemsetAsync((uint8_t *)ctx->in_stage.p + (in_pad - 4), 0, 4, ctx->stream), "memset(in tail)");
-        CK(cudaMemcpyAsync(ctx->in_stage.p, (const uint8_t *)in + base_byte, nbytes, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+        CK(copy_h2d(ctx, ctx->in_stage.p, (const uint8_t *)in + base_byte, nbytes, ctx->stream), "H2D");
         d_stream = (const uint8_t *)ctx->in_stage.p;
     }
     size_t nrsi = 0;
@@ -1124,8 +1283,8 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
     size_t newbytes = W > skip_samples ? (size_t)((W - skip_samples) * c.B) : 0;
     if (newbytes > early_bytes) {
         /* (early pieces only exist with skip_samples == 0) */
-        cudaError_t e = cudaMemcpyAsync((uint8_t *)out + early_bytes, (uint8_t *)ctx->out_stage.p + skip_samples * c.B + early_bytes,
-                                        newbytes - early_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = copy_d2h(ctx, (uint8_t *)out + early_bytes, (uint8_t *)ctx->out_stage.p + skip_samples * c.B + early_bytes,
+                                 newbytes - early_bytes, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { free(h_offs); return fail_cuda(ctx, e, "D2H"); }
     }
@@ -1189,8 +1348,7 @@ static int decode_host_pipelined(aecb200_ctx *ctx, const aecb200_params *p, cons
         size_t upto = r1 < need_rsi ? (size_t)(rsi_offsets[r1] / 8) + 256 : in_bytes;
         if (upto > in_bytes || i + 1 == npieces) upto = in_bytes;
         if (upto > up) {
-            CK(cudaMemcpyAsync((uint8_t *)ctx->in_stage.p + up, (const uint8_t *)in + up, upto - up,
-                               cudaMemcpyHostToDevice, ctx->s_in), "H2D");
+            CK(copy_h2d(ctx, (uint8_t *)ctx->in_stage.p + up, (const uint8_t *)in + up, upto - up, ctx->s_in), "H2D");
             up = upto;
         }
         CK(cudaEventRecord(ctx->ev[i], ctx->s_in), "cudaEventRecord");
@@ -1232,7 +1390,7 @@ static int decode_host_pipelined(aecb200_ctx *ctx, const aecb200_params *p, cons
         if (rc == AEC_OK) rc = aecb200_decode_finish(ctx, &got);
         if (rc != AEC_OK || got != nb)
             return (rc == AEC_OK || rc == AEC_DATA_ERROR) ? AECB200_NOT_PIPELINED : rc;
-        CK(cudaMemcpyAsync((uint8_t *)out + o, (uint8_t *)ctx->out_stage.p + o, nb, cudaMemcpyDeviceToHost, ctx->s_out), "D2H");
+        CK(copy_d2h(ctx, (uint8_t *)out + o, (uint8_t *)ctx->out_stage.p + o, nb, ctx->s_out), "D2H");
         total += nb;
     }
     CK(cudaStreamSynchronize(ctx->s_out), "sync(out)");
@@ -1313,7 +1471,7 @@ int aecb200_sz_compress_host(aecb200_ctx *ctx, int options_mask, int bits_per_pi
         ENTER_DEVICE();
         CK(ctx->raw_stage.ensure(source_len + 16), "cudaMalloc(sz source)");
         CK(ctx->in_stage.ensure(padded_len + 16), "cudaMalloc(in)");
-        CK(cudaMemcpyAsync(ctx->raw_stage.p, source, source_len, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+        CK(copy_h2d(ctx, ctx->raw_stage.p, source, source_len, ctx->stream), "H2D");
         CK(aec_sz_pack_launch((const uint8_t *)ctx->raw_stage.p, source_len, (uint8_t *)ctx->in_stage.p, padded_len, g.ws, g.line,
                               g.full_line, g.px, (g.prm.flags & AECF_PREPROCESS) ? 1u : 0u, ctx->stream), "sz pack launch");
         ctx->launches += 1;
@@ -1358,7 +1516,7 @@ int aecb200_sz_decompress_host(aecb200_ctx *ctx, int options_mask, int bits_per_
         CK(ctx->out_stage.ensure((size_t)(out_samples * c.B) + 16), "cudaMalloc(out)");
         CK(ctx->offs.ensure((need_rsi + 1) * 8), "cudaMalloc(offsets)");
         CK(cudaMemsetAsync((uint8_t *)ctx->in_stage.p + (in_pad - 4), 0, 4, ctx->stream), "memset(in tail)");
-        CK(cudaMemcpyAsync(ctx->in_stage.p, source, source_len, cudaMemcpyHostToDevice, ctx->stream), "H2D");
+        CK(copy_h2d(ctx, ctx->in_stage.p, source, source_len, ctx->stream), "H2D");
         size_t nrsi = 0;
         rc = aecb200_scan_offsets_device(ctx, &g.prm, ctx->in_stage.p, source_len, 0, (uint64_t *)ctx->offs.p, (size_t)need_rsi, &nrsi);
         if (rc != AEC_OK && rc != AEC_DATA_ERROR) return rc;
@@ -1380,7 +1538,7 @@ int aecb200_sz_decompress_host(aecb200_ctx *ctx, int options_mask, int bits_per_
                                 ragged ? g.line : (size_t)1 << 62, ragged ? g.full_line : (size_t)1 << 62, ctx->stream),
            "sz unpack launch");
         ctx->launches += 1;
-        CK(cudaMemcpyAsync(dest, ctx->out2_stage.p, n, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+        CK(copy_d2h(ctx, dest, ctx->out2_stage.p, n, ctx->stream), "D2H");
         CK(cudaStreamSynchronize(ctx->stream), "sync");
     }
     return AEC_OK;
