@@ -416,6 +416,15 @@ class DeviceCodec:
         st = self.lib.aecb200_ctx_create(C.byref(self.ctx), C.c_int(device))
         if st != AEC_OK:
             raise RuntimeError(f"aecb200_ctx_create failed ({st}): no usable CUDA device, and there is no CPU fallback")
+        if stream is None:
+            # Callers hand over torch tensors: unless told otherwise run on torch's current stream of the
+            # context's device, so that the codec's work is ordered after the fills / copies torch has queued
+            # on those tensors (a private stream would race with them).
+            import sys
+            torch = sys.modules.get("torch")
+            if torch is not None and torch.cuda.is_available():
+                dev = int(self.lib.aecb200_ctx_device(self.ctx))
+                stream = torch.cuda.current_stream(dev).cuda_stream
         if stream is not None:
             self.lib.aecb200_ctx_set_stream(self.ctx, C.c_void_p(int(stream)))
         if encode_padding:

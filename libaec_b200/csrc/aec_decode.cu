@@ -269,6 +269,28 @@ __device__ __forceinline__ void warp_decode_block(const AecCfg &c, Rd64 &rd, uin
          * fetched eight at a time with all loads in flight together.  (Through get() every sample waited
          * for a load issued one refill earlier: with a word consumed per sample the lanes of
          * incompressible data spent 57 % of their stall samples there, profiles/r2_summary.md.) */
+        if (c.n == 32u) {
+            /* whole words at one bit phase: sample i is a funnel shift of words i and i+1 */
+            const uint64_t pos = rd.pos();
+            const uint32_t wi = (uint32_t)(pos >> 5), sh = (uint32_t)(pos & 31u);
+            uint32_t prevw = rd.ld(wi);
+            for (uint32_t i0 = 0; i0 < J; i0 += 8u) {
+                uint32_t wv[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) wv[j] = rd.ldraw(wi + 1u + i0 + (uint32_t)j);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (i0 + (uint32_t)j < J) {
+                        const uint32_t wj = __byte_perm(wv[j], 0, 0x0123);
+                        const uint32_t v = __funnelshift_l(wj, prevw, sh);
+                        prevw = wj;
+                        row[i0 + j] = (i0 + (uint32_t)j >= ref) ? la.add(v) : v;
+                    }
+                }
+            }
+            rd.init(rd.w, rd.nwords, pos + 32ull * J);
+            return;
+        }
         uint32_t i = 0;
         while (i < J) {
             uint32_t wv[8];

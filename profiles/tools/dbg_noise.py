@@ -16,7 +16,7 @@ for name, mib in (("c5_noise", 32), ("c1", 64)):
     d_comp = torch.empty(cap, dtype=torch.uint8, device="cuda")
     bad_dev = bad_host = 0
     for rep in range(12):
-        d_comp.fill_(0xA5)
+        d_comp.fill_(0xA5); torch.cuda.synchronize()
         codec.encode_enqueue(p, d_raw, raw.size, d_comp)
         st, bits, _ = codec.encode_finish()
         got = d_comp[: want.size].cpu().numpy()

@@ -400,6 +400,7 @@ def test_encoder_repeated_large_runs_byte_exact(torch_cuda, name, mib, reps):
     d_comp = torch.empty(cap, dtype=torch.uint8, device="cuda")
     for rep in range(reps):
         d_comp.fill_(0xA5)
+        torch.cuda.synchronize()        # the codec runs on a stream of its own: the fill must not overtake the encode
         assert codec.encode_enqueue(p, d_raw, raw.size, d_comp) == 0
         st, bits, _ = codec.encode_finish()
         assert st == 0 and (bits + 7) // 8 == want.size, (name, rep, bits, want.size)
