@@ -217,6 +217,12 @@ int aecb200_encode_host_piece(aecb200_ctx *ctx, const aecb200_params *p,
                               aecb200_carry *carry,
                               uint64_t *rsi_offsets, size_t offsets_cap, size_t *n_offsets);
 
+/* AEC_NO_FLUSH encoding accumulates on the device: aecb200_ctx_stage_input appends bytes that do not yet
+ * make a whole RSI to the context's input stage (offset = bytes staged so far); aecb200_encode_host_piece
+ * with in == NULL then codes in_bytes staged bytes without another upload. */
+int aecb200_ctx_stage_input(aecb200_ctx *ctx, size_t offset, const void *src, size_t n);
+uint64_t aecb200_ctx_staged_uploads(aecb200_ctx *ctx);
+
 /* Whole-buffer decode.  rsi_offsets == NULL: discover RSI boundaries on the
  * device first (sequential, slow).  *out_len = bytes delivered. */
 int aecb200_decode_host(aecb200_ctx *ctx, const aecb200_params *p,

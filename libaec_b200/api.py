@@ -101,7 +101,8 @@ DEVICE_SYMBOLS = ["aecb200_device_count", "aecb200_current_device", "aecb200_ctx
                   "aecb200_encode_repair_device", "aecb200_place_bits_planned", "aecb200_set_device",
                   "aecb200_sz_compress_host", "aecb200_sz_decompress_host", "aecb200_sz_compress_batch",
                   "aecb200_sz_decompress_batch", "aecb200_pool_get", "aecb200_pool_put",
-                  "aecb200_ctx_accumulate_next", "aecb200_ctx_accumulated_uploads"]
+                  "aecb200_ctx_accumulate_next", "aecb200_ctx_accumulated_uploads",
+                  "aecb200_ctx_stage_input", "aecb200_ctx_staged_uploads"]
 SZ_SYMBOLS = ["SZ_BufftoBuffCompress", "SZ_BufftoBuffDecompress", "SZ_encoder_enabled", "SZ_Compress"]
 
 
@@ -134,6 +135,7 @@ def load_library() -> C.CDLL:
         lib.aecb200_pool_put.restype = None
         lib.aecb200_ctx_accumulate_next.restype = None
         lib.aecb200_ctx_accumulated_uploads.restype = C.c_uint64
+        lib.aecb200_ctx_staged_uploads.restype = C.c_uint64
         _lib = lib
     return _lib
 

@@ -194,6 +194,7 @@ struct aecb200_ctx {
     aecb200_ctx *aux = nullptr;          /* second context (stream + workspace): decodes RSIs already discovered while the scan goes on */
     long long acc_stream_byte0 = -1;     /* >= 0: the next aecb200_decode_host_resume call accumulates; in[0] is this stream byte */
     uint64_t acc_uploaded = 0;           /* bytes sent to the device by accumulating calls (diagnostics) */
+    uint64_t staged_uploads = 0;         /* bytes of encoder input accumulated on the device (diagnostics) */
     bool in_stage_ready = false;         /* the next host encode finds its input in in_stage already */
     bool no_bounce = false;              /* pageable host buffers go straight to cudaMemcpyAsync (AECB200_NO_BOUNCE, tests) */
     uint64_t tile_limit = 0;             /* next encode codes only this many leading tiles (k repair) */
@@ -1068,6 +1069,21 @@ static int encode_host_impl(aecb200_ctx *ctx, const aecb200_params *p,
     return nbytes <= out_cap ? AEC_OK : AEC_STREAM_ERROR;
 }
 
+/* AEC_NO_FLUSH encoding accumulates its input on the device: bytes that do not yet make a whole RSI are
+ * sent to the context's input stage as they arrive (offset = bytes staged so far); once an RSI is
+ * complete (or the stream is flushed) aecb200_encode_host_piece is called with in == NULL and codes
+ * the staged bytes without another upload. */
+int aecb200_ctx_stage_input(aecb200_ctx *ctx, size_t offset, const void *src, size_t n)
+{
+    if (!ctx || (!src && n)) return AEC_CONF_ERROR;
+    ENTER_DEVICE();
+    CK(ctx->in_stage.ensure_preserve(offset + n + 16, offset, ctx->stream), "cudaMalloc(in)");
+    if (n) CK(cudaMemcpyAsync((uint8_t *)ctx->in_stage.p + offset, src, n, cudaMemcpyHostToDevice, ctx->stream), "H2D (accumulate)");
+    ctx->staged_uploads += n;
+    return AEC_OK;
+}
+uint64_t aecb200_ctx_staged_uploads(aecb200_ctx *ctx) { return ctx ? ctx->staged_uploads : 0; }
+
 int aecb200_encode_host(aecb200_ctx *ctx, const aecb200_params *p,
                         const void *in, size_t in_bytes,
                         void *out, size_t out_cap, size_t *out_len, size_t *in_consumed,
@@ -1086,6 +1102,7 @@ int aecb200_encode_host_piece(aecb200_ctx *ctx, const aecb200_params *p,
                               uint64_t *rsi_offsets, size_t offsets_cap, size_t *n_offsets)
 {
     if (!ctx || !p || !carry) return AEC_CONF_ERROR;
+    if (!in && in_bytes) ctx->in_stage_ready = true;    /* staged by aecb200_ctx_stage_input */
     return encode_host_impl(ctx, p, in, in_bytes, final, out, out_cap, out_len, in_consumed, carry,
                             rsi_offsets, offsets_cap, n_offsets);
 }

@@ -7,7 +7,7 @@
  * reference drives two resumable per-sample state machines from these calls;
  * here the calls only do buffer bookkeeping on the host:
  *
- *   encode: input is collected until at least one whole RSI (or AEC_FLUSH) is
+ *   encode: input is collected -- on the device -- until at least one whole RSI (or AEC_FLUSH) is
  *           available, whole RSIs are coded on the GPU in one launch with the
  *           (bit phase, k) carry of the stream so far, and the produced bytes
  *           are handed out over as many calls as the caller's windows need.
@@ -42,8 +42,7 @@ struct internal_state {
     size_t qhead, qtail, qcap;
 
     /* encoder */
-    unsigned char *ibuf;   /* less than one RSI of whole samples */
-    size_t ilen;
+    size_t ilen;           /* bytes of whole samples (less than one RSI) accumulated on the device so far */
     aecb200_carry carry;
     uint64_t emitted_bytes;   /* complete stream bytes produced so far */
     int any_samples;
@@ -148,7 +147,7 @@ static void state_free(struct internal_state *st)
 {
     if (!st) return;
     ctx_put(st->ctx);
-    free(st->q); free(st->ibuf); free(st->offs); free(st->cbuf);
+    free(st->q); free(st->offs); free(st->cbuf);
     free(st);
 }
 
@@ -190,8 +189,6 @@ int aec_encode_init(struct aec_stream *strm)
     if (rc != AEC_OK) return rc;
     struct internal_state *st = state_new(strm, 0);
     if (!st) return AEC_MEM_ERROR;
-    st->ibuf = (unsigned char *)malloc(st->rsi_bytes ? st->rsi_bytes : 1);
-    if (!st->ibuf) { state_free(st); return AEC_MEM_ERROR; }
     strm->state = st;
     strm->total_in = 0;
     strm->total_out = 0;
@@ -257,22 +254,24 @@ int aec_encode(struct aec_stream *strm, int flush)
             if (flush == AEC_FLUSH) st->finished = 1;
             continue;
         }
-        /* top the RSI buffer up */
+        /* less than an RSI at hand: the samples accumulate ON THE DEVICE (the context's input stage)
+         * until the RSI is complete, then they are coded from there without another upload */
         size_t take = st->rsi_bytes - st->ilen;
         if (take > whole) take = whole;
         if (take) {
-            memcpy(st->ibuf + st->ilen, strm->next_in, take);
+            rc = aecb200_ctx_stage_input(st->ctx, st->ilen, strm->next_in, take);
+            if (rc != AEC_OK) return rc == AECB200_CUDA_ERROR ? AEC_MEM_ERROR : rc;
             st->ilen += take;
             strm->next_in += take; strm->avail_in -= take; strm->total_in += take;
         }
         if (st->ilen == st->rsi_bytes) {
-            rc = encode_piece(strm, st, st->ibuf, st->ilen, 0);
+            rc = encode_piece(strm, st, NULL, st->ilen, 0);
             if (rc != AEC_OK) return rc;
             st->ilen = 0;
             continue;
         }
         if (flush == AEC_FLUSH && strm->avail_in < st->B) {
-            rc = encode_piece(strm, st, st->ibuf, st->ilen, 1);
+            rc = encode_piece(strm, st, NULL, st->ilen, 1);
             if (rc != AEC_OK) return rc;
             st->ilen = 0;
             st->finished = 1;

@@ -456,3 +456,24 @@ def test_streaming_decode_keeps_the_stream_on_the_device():
     assert ctx_after.value == ctx_before.value
     # every stream byte goes up about once (re-staging after trims allowed), not once per output window
     assert comp.size * 0.5 <= sent <= comp.size * 3, (sent, comp.size)
+
+
+def test_streaming_encode_accumulates_on_the_device():
+    """AEC_NO_FLUSH with windows smaller than an RSI: the samples go to the device as they arrive (no host
+    RSI buffer), are coded from there once an RSI is complete, and the stream is the oracle's."""
+    import ctypes as C
+    p = L.Params(16, 16, 64, L.AEC_DATA_PREPROCESS)
+    rng = np.random.default_rng(9)
+    raw = (np.cumsum(rng.integers(-4, 5, size=40_000)) + 30000).astype("<u2").view(np.uint8)
+    want = po.orc_encode(po.Params(16, 16, 64, po.AEC_DATA_PREPROCESS), raw)["out"]
+    lib = L.load_library()
+    ctx = C.c_void_p(lib.aecb200_pool_get())
+    before = lib.aecb200_ctx_staged_uploads(ctx)
+    lib.aecb200_pool_put(ctx)
+    enc = L.Encoder(p)
+    out = enc.run(raw, in_chunk=250, out_chunk=97, out_cap=want.size + 64)     # an RSI is 2048 bytes
+    assert enc.close() == 0 and np.array_equal(out, want)
+    ctx2 = C.c_void_p(lib.aecb200_pool_get())
+    sent = lib.aecb200_ctx_staged_uploads(ctx2) - before
+    lib.aecb200_pool_put(ctx2)
+    assert ctx2.value == ctx.value and sent >= raw.size * 0.9, (sent, raw.size)
