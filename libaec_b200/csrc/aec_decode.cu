@@ -714,11 +714,12 @@ aec_decode_warp_kernel(const AecDecArgs a)
 }
 
 /* Group index of RSIs with known start offsets: lane-per-RSI skim. */
-__global__ void aec_build_group_index_kernel(const AecDecArgs a, uint64_t *grp_index)
+__global__ void aec_build_group_index_kernel(const AecDecArgs a, uint64_t *grp_index, int only_missing)
 {
     const AecCfg &c = a.cfg;
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.nrsi) return;
+    if (only_missing && grp_index[r * 32ull] != 0xFFFFFFFFFFFFFFFFull) return;   /* SK_GRP_MISSING: see aec_skim_core.cuh */
     const uint32_t G = a.grp_G;
     BitRd br;
     br.init(a.in_words, (a.in_bytes + 3) >> 2, a.in_bytes * 8ull);
@@ -871,10 +872,10 @@ cudaError_t aec_decode_warp_launch(const AecDecArgs &a, int num_sms, cudaStream_
     }
 }
 
-cudaError_t aec_build_group_index_launch(const AecDecArgs &a, uint64_t *grp_index, cudaStream_t st)
+cudaError_t aec_build_group_index_launch(const AecDecArgs &a, uint64_t *grp_index, cudaStream_t st, int only_missing)
 {
     if (a.nrsi == 0) return cudaSuccess;
-    aec_build_group_index_kernel<<<(unsigned)((a.nrsi + 127) / 128), 128, 0, st>>>(a, grp_index);
+    aec_build_group_index_kernel<<<(unsigned)((a.nrsi + 127) / 128), 128, 0, st>>>(a, grp_index, only_missing);
     return cudaGetLastError();
 }
 

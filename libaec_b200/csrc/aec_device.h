@@ -119,8 +119,12 @@ struct AecSkimArgs {
     uint32_t la_words;          /* filled by the launcher: words staged beyond a tile */
     uint32_t bulk;              /* filled by the launcher: tiles can be staged with cp.async.bulk (16-byte aligned) */
     uint32_t *T;                /* [LV][np] */
-    uint32_t *H;                /* [np] RSI lengths (first-CDS entries between the kernels) */
-    uint64_t *state;            /* [0] next RSI bit, [1] RSIs found, [2] flags (1 ended, 2 data error), [3] RSIs taken from the tables */
+    uint32_t *H;                /* [np] RSI lengths */
+    uint32_t *R;                /* [np] entries of a first CDS of an RSI (the one with the reference sample) */
+    uint64_t *grp_index;        /* optional [max_rsi * 32]: group index of the RSIs found (AecDecArgs::grp_index) */
+    uint32_t grp_G;             /* blocks per group = ceil(rsi / 32) */
+    uint64_t *state;            /* [0] next RSI bit, [1] RSIs found, [2] flags (1 ended, 2 data error), [3] RSIs taken from the tables,
+                                 * [4] RSIs found before the current window's walk */
     uint64_t *offsets;          /* [max_rsi] */
     uint64_t max_rsi;
 };
@@ -157,8 +161,9 @@ uint32_t aec_decode_group_blocks(const AecCfg &c);     /* G = ceil(rsi / 32) */
 uint32_t aec_decode_warp_warps(const AecCfg &c);       /* 0 when the fast kernel cannot be used */
 /* fast path: one warp per RSI from the group index; RSIs it cannot finish are appended to rsi_list */
 cudaError_t aec_decode_warp_launch(const AecDecArgs &a, int num_sms, cudaStream_t st);
-/* build the group index of RSIs whose start offsets are known (one lane skims one RSI) */
-cudaError_t aec_build_group_index_launch(const AecDecArgs &a, uint64_t *grp_index, cudaStream_t st);
+/* build the group index of RSIs whose start offsets are known (one lane skims one RSI); only_missing: leave RSIs
+ * alone whose first entry is not SK_GRP_MISSING (the boundary discovery has written theirs from its tables) */
+cudaError_t aec_build_group_index_launch(const AecDecArgs &a, uint64_t *grp_index, cudaStream_t st, int only_missing = 0);
 /* Sequential RSI-boundary scan for streams without an offset index:
  * fills offsets[0..max_rsi) and result[0] = RSIs found, result[1] = status. */
 cudaError_t aec_scan_offsets_launch(const AecCfg &c, const uint32_t *in_words, uint64_t in_bytes,

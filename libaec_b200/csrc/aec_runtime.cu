@@ -216,6 +216,7 @@ struct aecb200_ctx {
     int scan_mode = 0;                   /* 0 auto, 1 always the one-thread scan, 2 always the parallel tables */
     uint64_t scan_window_bits = 1ull << 25;
     uint64_t scan_end = 0, scan_fast = 0;
+    bool scan_grp = false;               /* the last scan also wrote the group index */
     std::vector<uint64_t> found_offs;    /* RSI offsets the last host decode discovered itself (bits from in[0]) */
 
     /* bookkeeping of the last enqueued operation */
@@ -791,7 +792,8 @@ struct ScanProgress {
 
 static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
                              const void *d_in, size_t in_bytes, uint64_t start_bit,
-                             uint64_t *d_rsi_offsets, size_t max_rsi, size_t *found, ScanProgress *prog);
+                             uint64_t *d_rsi_offsets, size_t max_rsi, size_t *found, ScanProgress *prog,
+                             uint64_t *d_grp = nullptr);
 
 int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
                                 const void *d_in, size_t in_bytes, uint64_t start_bit,
@@ -800,11 +802,16 @@ int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
     return scan_offsets_impl(ctx, p, d_in, in_bytes, start_bit, d_rsi_offsets, max_rsi, found, nullptr);
 }
 
+/* d_grp (optional, max_rsi * 32 entries): the group index of the RSIs found is written from the chain tables
+ * as well (ctx->scan_grp tells whether it was: the one-thread scan of short streams does not); RSIs that
+ * had to be skimmed serially are marked SK_GRP_MISSING for aec_build_group_index_launch(only_missing). */
 static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
                              const void *d_in, size_t in_bytes, uint64_t start_bit,
-                             uint64_t *d_rsi_offsets, size_t max_rsi, size_t *found, ScanProgress *prog)
+                             uint64_t *d_rsi_offsets, size_t max_rsi, size_t *found, ScanProgress *prog,
+                             uint64_t *d_grp)
 {
     if (!ctx || !p) return AEC_CONF_ERROR;
+    ctx->scan_grp = false;
     AecCfg c;
     int rc = make_cfg(ctx, p, 0, &c);
     if (rc != AEC_OK) return rc;
@@ -847,7 +854,7 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
     if (np_max >= 0x7FFFFFFFull) { snprintf(ctx->err, sizeof ctx->err, "scan window too large"); return AEC_CONF_ERROR; }
     /* two table sets: the walk through window i (one thread, a dependent load per RSI) runs on a side
      * stream next to the table kernels of window i+1 */
-    const size_t set_words = (size_t)(LV + 1u) * (size_t)np_max;
+    const size_t set_words = (size_t)(LV + 2u) * (size_t)np_max;       /* the levels, H and R */
     const int nsets = nwin > 1 ? 2 : 1;
     CK(ctx->skim_tab.ensure(set_words * 4u * (size_t)nsets), "cudaMalloc(skim tables)");
     if (!ctx->s_walk) CK(cudaStreamCreateWithFlags(&ctx->s_walk, cudaStreamNonBlocking), "cudaStreamCreate(walk)");
@@ -864,10 +871,14 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
     a.state = state;
     a.offsets = d_rsi_offsets;
     a.max_rsi = max_rsi;
+    a.grp_index = d_grp;
+    a.grp_G = aec_decode_group_blocks(c);
+    ctx->scan_grp = d_grp != nullptr;
     for (uint64_t i = 0; i < nwin; i++) {
         const int k = (int)(i & 1u) % nsets;
         a.T = (uint32_t *)ctx->skim_tab.p + (size_t)k * set_words;
         a.H = a.T + (size_t)LV * (size_t)np_max;
+        a.R = a.H + (size_t)np_max;
         a.wb = base + i * nh;
         const uint64_t rem = ((nbits - a.wb) + 31ull) & ~31ull;
         a.np = (uint32_t)(nh + margin < rem ? nh + margin : rem);
@@ -1109,7 +1120,25 @@ int aecb200_encode_host_piece(aecb200_ctx *ctx, const aecb200_params *p,
 
 /* RSIs the boundary discovery has finished with are decoded on the context's second stream/workspace and
  * copied to the caller while the discovery goes on (ScanProgress hook of scan_offsets_impl). */
+/* group index entries of RSIs the discovery could not take from its tables (marked SK_GRP_MISSING) */
+static int complete_group_index(aecb200_ctx *ctx, cudaStream_t st, const AecCfg &c, const uint8_t *d_stream, size_t nbytes,
+                                const uint64_t *d_offs, size_t nrsi, uint64_t *d_grp)
+{
+    AecDecArgs a;
+    memset(&a, 0, sizeof a);
+    a.cfg = c;
+    a.in_words = (const uint32_t *)d_stream;
+    a.in_bytes = nbytes;
+    a.rsi_offsets = d_offs;
+    a.nrsi = nrsi;
+    a.grp_G = aec_decode_group_blocks(c);
+    CK(aec_build_group_index_launch(a, d_grp, st, 1), "group index launch");
+    ctx->launches += 1;
+    return AEC_OK;
+}
+
 struct EarlyDecode : ScanProgress {
+    AecCfg c;
     bool on = false, failed = false, pending = false;
     aecb200_ctx *ctx = nullptr;
     const aecb200_params *p = nullptr;
@@ -1137,7 +1166,14 @@ struct EarlyDecode : ScanProgress {
         const uint64_t r0 = done, r1 = complete;
         const size_t nb = (size_t)(r1 - r0) * rsi_out;
         uint8_t *d_out = (uint8_t *)ctx->out_stage.p + (size_t)r0 * rsi_out;
-        int rc = aecb200_decode_device(aux, p, d_stream, nbytes, (const uint64_t *)ctx->offs.p + r0, (size_t)(r1 - r0), d_out, nb);
+        const uint64_t *d_grp = nullptr;
+        if (ctx->scan_grp) {
+            if (complete_group_index(aux, aux->stream, c, d_stream, nbytes, (const uint64_t *)ctx->offs.p + r0, (size_t)(r1 - r0),
+                                     (uint64_t *)ctx->grp.p + r0 * 32) != AEC_OK) { failed = true; return AEC_OK; }
+            d_grp = (const uint64_t *)ctx->grp.p + r0 * 32;
+        }
+        int rc = aecb200_decode_device_indexed(aux, p, d_stream, nbytes, (const uint64_t *)ctx->offs.p + r0, (size_t)(r1 - r0),
+                                               d_grp, d_out, nb);
         if (rc != AEC_OK) { failed = true; return AEC_OK; }
         if (copy_d2h(aux, out + (size_t)r0 * rsi_out, d_out, nb, aux->stream) != cudaSuccess) failed = true;
         pending = true; pending_expect = nb; done = r1;
@@ -1231,6 +1267,7 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
     size_t nrsi = 0;
     uint64_t scan_end = 0;
     uint64_t *h_offs = nullptr;
+    bool scan_grp = false;
     EarlyDecode early;
     ctx->found_offs.clear();
     if (rsi_offsets) {
@@ -1264,8 +1301,12 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
                 early.min_rsis = (ctx->pipe_piece + rsi_out - 1) / rsi_out;
             }
         }
+        CK(ctx->grp.ensure((size_t)need_rsi * 32 * 8), "cudaMalloc(group index)");
+        early.c = c;
         rc = scan_offsets_impl(ctx, p, d_stream, nbytes, start_bit - base_bit,
-                               (uint64_t *)ctx->offs.p, (size_t)need_rsi, &nrsi, early.on ? &early : nullptr);
+                               (uint64_t *)ctx->offs.p, (size_t)need_rsi, &nrsi, early.on ? &early : nullptr,
+                               ctx->careful_only ? nullptr : (uint64_t *)ctx->grp.p);
+        scan_grp = ctx->scan_grp;
         if (early.on) {
             early.finish_pending();
             if (early.failed || rc != AEC_OK) {          /* anything unusual: decode everything on the plain path */
@@ -1288,8 +1329,17 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
     size_t written = 0;
     const uint64_t early_rsis = early.done < nrsi ? early.done : 0;    /* already decoded and on their way to `out` */
     const size_t early_bytes = (size_t)early_rsis * c.R * c.B;
-    rc = aecb200_decode_device(ctx, p, d_stream, nbytes, (const uint64_t *)ctx->offs.p + early_rsis, nrsi - early_rsis,
-                               (uint8_t *)ctx->out_stage.p + early_bytes, (size_t)(out_samples * c.B) - early_bytes);
+    const uint64_t *d_grp = nullptr;
+    if (scan_grp && nrsi > early_rsis) {
+        /* the discovery wrote the group index of the RSIs it took from its tables; skim the few others */
+        rc = complete_group_index(ctx, ctx->stream, c, d_stream, nbytes, (const uint64_t *)ctx->offs.p + early_rsis,
+                                  nrsi - early_rsis, (uint64_t *)ctx->grp.p + early_rsis * 32);
+        if (rc != AEC_OK) { free(h_offs); return rc; }
+        d_grp = (const uint64_t *)ctx->grp.p + early_rsis * 32;
+    }
+    rc = aecb200_decode_device_indexed(ctx, p, d_stream, nbytes, (const uint64_t *)ctx->offs.p + early_rsis, nrsi - early_rsis,
+                                       d_grp, (uint8_t *)ctx->out_stage.p + early_bytes,
+                                       (size_t)(out_samples * c.B) - early_bytes);
     if (rc == AEC_OK) rc = aecb200_decode_finish(ctx, &written);
     if (rc != AEC_OK) { free(h_offs); if (early.on) cudaStreamSynchronize(ctx->aux->stream); return rc; }
     written += early_bytes;

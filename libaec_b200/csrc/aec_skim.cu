@@ -125,7 +125,7 @@ aec_skim_level0_kernel(const AecSkimArgs a)
             r0 = c.pp ? sk_entry(c, w, pre, nwords, q, limit, 1u) : t0;
         }
         a.T[p] = t0;
-        a.H[p] = r0;
+        a.R[p] = r0;
     }
 }
 
@@ -174,7 +174,7 @@ aec_skim_rsi_kernel(const AecSkimArgs a)
     for (int i = 0; i < SK_NC; i++) {
         p[i] = (t + (uint32_t)i * grid_span) * step;
         live[i] = p[i] < a.nh_eff;
-        const uint32_t first = live[i] ? a.H[p[i]] : 0u;       /* still the first-CDS entry */
+        const uint32_t first = live[i] ? a.R[p[i]] : 0u;
         uint32_t b = sk_blk(first);
         if (b == 0u) b = rsi < 64u ? rsi : 64u;                 /* run-of-zero-segment at block 0 */
         live[i] = live[i] && first >= 0x1000u && b <= rsi;
@@ -236,12 +236,34 @@ __global__ void aec_skim_walk_kernel(const AecSkimArgs a)
     if (a.state[2] & 1ull) return;
     const AecCfg &c = a.cfg;
     SkWalk s; s.pos = a.state[0]; s.found = a.state[1]; s.flags = 0; s.fast = a.state[3];
+    a.state[4] = s.found;
     BitRd br;
     br.init(a.in_words, (a.nbits + 31ull) >> 5, a.nbits);
     const uint32_t *H = a.H;
     while (sk_walk_step(c, br, a.nbits, a.wb, a.nh_eff, a.last, a.offsets, a.max_rsi, s,
-                        [H](uint64_t rel) { return __ldcg(H + rel); })) { }
+                        [H](uint64_t rel) { return __ldcg(H + rel); }, a.grp_index)) { }
     a.state[0] = s.pos; a.state[1] = s.found; a.state[2] = s.flags; a.state[3] = s.fast;
+}
+
+/* Group index of the RSIs the walk has just taken from the tables: lane l of a warp finds where block l * G of
+ * its RSI starts by the same descent through the levels (no second pass over the stream). */
+__global__ void __launch_bounds__(SK_THREADS)
+aec_skim_group_index_kernel(const AecSkimArgs a)
+{
+    const AecCfg &c = a.cfg;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t r0 = a.state[4], r1 = a.state[1];
+    const uint64_t warps = (uint64_t)gridDim.x * (SK_THREADS / 32);
+    for (uint64_t r = r0 + (uint64_t)blockIdx.x * (SK_THREADS / 32) + (threadIdx.x >> 5); r < r1; r += warps) {
+        uint64_t *g = a.grp_index + r * 32ull;
+        const uint64_t mark = g[0];
+        __syncwarp();
+        if (mark != SK_GRP_FAST) continue;              /* skimmed serially: the builder kernel does this RSI */
+        const uint64_t start = a.offsets[r];
+        const uint32_t p = (uint32_t)(start - a.wb);
+        const uint32_t m = lane * a.grp_G;
+        g[lane] = m < c.rsi ? sk_group_entry(c, a.T, a.R, a.LV, a.np, a.wb, p, m) : 0ull;
+    }
 }
 
 } // namespace
@@ -272,5 +294,6 @@ cudaError_t aec_skim_walk_launch(const AecSkimArgs &a, cudaStream_t st)
 {
     if (a.np == 0) return cudaSuccess;
     aec_skim_walk_kernel<<<1, 32, 0, st>>>(a);
+    if (a.grp_index) aec_skim_group_index_kernel<<<64, SK_THREADS, 0, st>>>(a);
     return cudaGetLastError();
 }

@@ -147,6 +147,50 @@ AEC_HD uint32_t sk_rsi_len(const AecCfg &c, const uint32_t *T, uint32_t LV, uint
     return q - p;
 }
 
+#define SK_GRP_POISON 0x00FFFFFFFFFFFFFFull     /* an entry the fast decoder refuses (it hands the RSI to the careful kernel) */
+#define SK_GRP_FAST    0xFFFFFFFFFFFFFFFEull     /* walk -> group kernel: this RSI came from the tables, its entries are still to be written */
+#define SK_GRP_MISSING 0xFFFFFFFFFFFFFFFFull     /* walk -> builder: this RSI was skimmed serially, build its entries by skimming */
+
+/* Group index entry (aec_device.h: AecDecArgs::grp_index) of the group that starts at block m of the RSI at
+ * window-relative p, from the chain tables: bits 55..0 absolute bit offset of the first CDS the lane parses,
+ * bits 63..56 blocks at the head of the group that still belong to a zero run begun before it.  R[p] = entry
+ * of the RSI's first CDS, wb = the window's first bit. */
+AEC_HD uint64_t sk_group_entry(const AecCfg &c, const uint32_t *T, const uint32_t *R, uint32_t LV, uint32_t np, uint64_t wb,
+                               uint32_t p, uint32_t m)
+{
+    if (m == 0u) return wb + p;
+    const uint32_t first = R[p];
+    if (first < 0x1000u) return SK_GRP_POISON;
+    uint32_t c0 = sk_blk(first);
+    if (c0 == 0u) c0 = c.rsi < 64u ? c.rsi : 64u;
+    uint32_t q = p + sk_len(first);
+    if (c0 > m) return ((uint64_t)(c0 - m) << 56) | (wb + q);      /* the group starts inside the first CDS's zero run */
+    uint32_t rem = m - c0;
+    for (int guard = 0; rem != 0u && guard < 8192; guard++) {
+        for (int j = (int)LV - 1; j >= 0; j--) {
+            const uint32_t *Tj = T + (size_t)j * np;
+            for (;;) {
+                if (q >= np) break;
+                const uint32_t e = Tj[q];
+                if (!sk_jump(e) || sk_blk(e) > rem) break;
+                q += sk_len(e); rem -= sk_blk(e);
+                if (j != (int)LV - 1) break;
+            }
+        }
+        if (rem == 0u) break;
+        if (q >= np) return SK_GRP_POISON;
+        const uint32_t e = T[q];
+        const uint32_t b = m - rem;                     /* block number of the CDS at q */
+        uint32_t cnt;
+        if (sk_ros(e)) { const uint32_t seg = 64u - (b & 63u), left = c.rsi - b; cnt = left < seg ? left : seg; }
+        else if (sk_jump(e)) cnt = sk_blk(e);
+        else return SK_GRP_POISON;
+        if (cnt > rem) return ((uint64_t)(cnt - rem) << 56) | (wb + q + sk_len(e));   /* a zero run straddles the group start */
+        q += sk_len(e); rem -= cnt;
+    }
+    return rem == 0u ? wb + q : SK_GRP_POISON;
+}
+
 /* levels of the chain tables: level j = 2^j CDSs; 2^LV - 1 >= rsi - 1 up to the cap */
 AEC_HD uint32_t sk_levels(const AecCfg &c)
 {
@@ -174,7 +218,7 @@ struct SkWalk { uint64_t pos, found, flags, fast; };
 
 template <class LoadH>
 AEC_HD bool sk_walk_step(const AecCfg &c, BitRd &br, uint64_t nbits, uint64_t wb, uint32_t nh_eff, uint32_t last,
-                         uint64_t *offsets, uint64_t max_rsi, SkWalk &s, LoadH load_h)
+                         uint64_t *offsets, uint64_t max_rsi, SkWalk &s, LoadH load_h, uint64_t *grp = nullptr)
 {
     if (s.found >= max_rsi) { s.flags = 1; return false; }
     const uint64_t start = c.pad ? ((s.pos + 7ull) & ~7ull) : s.pos;
@@ -183,6 +227,7 @@ AEC_HD bool sk_walk_step(const AecCfg &c, BitRd &br, uint64_t nbits, uint64_t wb
     offsets[s.found++] = start;                         /* even a truncated RSI may still deliver leading samples */
     const uint64_t rel = start - wb;
     const uint32_t h = rel < nh_eff ? load_h(rel) : 0u;
+    if (grp) grp[(s.found - 1) * 32ull] = h ? SK_GRP_FAST : SK_GRP_MISSING;
     if (h) { s.pos = start + h; s.fast++; return true; }
     /* not in the tables: skim this RSI CDS by CDS (truncated or damaged stream, chain leaving the window) */
     RsiDec st; st.pos = start; st.zero_left = 0; st.status = DEC_OK;

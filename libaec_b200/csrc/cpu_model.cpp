@@ -235,10 +235,43 @@ extern "C" int model_decode(uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags
 /* ------------------------------------------------------------------------ */
 #include "aec_skim_core.cuh"
 
+/* the group index the way aec_build_group_index_kernel builds it: one skim of the RSI from its start offset */
+static void group_index_by_skim(const AecCfg &c, BitRd &br, uint64_t start, uint64_t *g)
+{
+    const uint32_t G = (c.rsi + 31u) / 32u;
+    RsiDec st; st.pos = start; st.zero_left = 0; st.status = DEC_OK;
+    for (uint32_t i = 0; i < 32; i++) g[i] = 0;
+    for (uint32_t b = 0; b < c.rsi; b++) {
+        if (b % G == 0) g[b / G] = ((uint64_t)st.zero_left << 56) | (st.pos & 0x00FFFFFFFFFFFFFFull);
+        if (!aec_skim_block(c, br, st, b)) {
+            for (uint32_t q = b / G + 1; q * G < c.rsi; q++) g[q] = 0x00FFFFFFFFFFFFFFull;
+            break;
+        }
+    }
+}
+
+extern "C" int model_scan_offsets_grp(uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags,
+                                      const uint8_t *in, size_t in_bytes, uint64_t start_bit,
+                                      uint64_t *offsets, uint64_t max_rsi, uint64_t window_bits, int serial,
+                                      uint64_t *found, uint64_t *out_flags, uint64_t *fast, uint64_t *end_pos,
+                                      uint64_t *grp, uint64_t *grp_ref);
+
 extern "C" int model_scan_offsets(uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags,
                                   const uint8_t *in, size_t in_bytes, uint64_t start_bit,
                                   uint64_t *offsets, uint64_t max_rsi, uint64_t window_bits, int serial,
                                   uint64_t *found, uint64_t *out_flags, uint64_t *fast, uint64_t *end_pos)
+{
+    return model_scan_offsets_grp(n, J, rsi, flags, in, in_bytes, start_bit, offsets, max_rsi, window_bits, serial,
+                                  found, out_flags, fast, end_pos, nullptr, nullptr);
+}
+
+/* grp (optional, max_rsi * 32): the group index from the tables (skim for RSIs the tables could not give);
+ * grp_ref (optional): the same index built by skimming every RSI, for comparison */
+extern "C" int model_scan_offsets_grp(uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags,
+                                      const uint8_t *in, size_t in_bytes, uint64_t start_bit,
+                                      uint64_t *offsets, uint64_t max_rsi, uint64_t window_bits, int serial,
+                                      uint64_t *found, uint64_t *out_flags, uint64_t *fast, uint64_t *end_pos,
+                                      uint64_t *grp, uint64_t *grp_ref)
 {
     AecCfg c;
     if (aec_cfg_init(&c, n, J, rsi, flags, 0, 0) != 0) return -1;
@@ -277,14 +310,15 @@ extern "C" int model_scan_offsets(uint32_t n, uint32_t J, uint32_t rsi, uint32_t
     const uint64_t span = ((nbits - base) + 31ull) & ~31ull;
     const uint64_t nwin = (span + nh - 1) / nh;
     const uint32_t TILE = 8192, la = sk_lookahead_words(c), nwords = TILE / 32u + la;
-    std::vector<uint32_t> T, H, w(nwords + 1), pre(nwords + 2);
+    std::vector<uint32_t> T, H, Rv, w(nwords + 1), pre(nwords + 2);
+    const uint32_t G = (c.rsi + 31u) / 32u;
     for (uint64_t wi = 0; wi < nwin && !(s.flags & 1ull); wi++) {
         const uint64_t wb = base + wi * nh;
         const uint64_t rem = ((nbits - wb) + 31ull) & ~31ull;
         const uint32_t np = (uint32_t)(nh + margin < rem ? nh + margin : rem);
         const uint32_t last = (wi + 1 == nwin) ? 1u : 0u;
         const uint32_t nh_eff = last ? np : (uint32_t)nh;
-        T.assign((size_t)LV * np, 0u); H.assign(np, 0u);
+        T.assign((size_t)LV * np, 0u); H.assign(np, 0u); Rv.assign(np, 0u);
         for (uint32_t tile0 = 0; tile0 < np; tile0 += TILE) {           /* level-0 kernel, one CTA */
             const uint64_t word0 = (wb + tile0) >> 5;
             for (uint32_t i = 0; i <= nwords; i++) {
@@ -301,15 +335,29 @@ extern "C" int model_scan_offsets(uint32_t n, uint32_t J, uint32_t rsi, uint32_t
                     t0 = sk_entry(c, w.data(), pre.data(), nwords, q, limit, 0u);
                     r0 = c.pp ? sk_entry(c, w.data(), pre.data(), nwords, q, limit, 1u) : t0;
                 }
-                T[tile0 + q] = t0; H[tile0 + q] = r0;
+                T[tile0 + q] = t0; Rv[tile0 + q] = r0;
             }
         }
         for (uint32_t j = 0; j + 1 < LV; j++)
             for (uint32_t p = 0; p < np; p++) T[(size_t)(j + 1) * np + p] = sk_double(T.data() + (size_t)j * np, np, p);
-        for (uint32_t p = 0; p < nh_eff; p += c.pad ? 8u : 1u) H[p] = sk_rsi_len(c, T.data(), LV, np, p, H[p]);
+        for (uint32_t p = 0; p < nh_eff; p += c.pad ? 8u : 1u) H[p] = sk_rsi_len(c, T.data(), LV, np, p, Rv[p]);
         const uint32_t *Hp = H.data();
+        const uint64_t f0 = s.found;
         while (sk_walk_step(c, br, nbits, wb, nh_eff, last, offsets, max_rsi, s,
-                            [Hp](uint64_t rel) { return Hp[rel]; })) { }
+                            [Hp](uint64_t rel) { return Hp[rel]; }, grp)) { }
+        if (grp) {                                                      /* aec_skim_group_index_kernel */
+            for (uint64_t r = f0; r < s.found; r++) {
+                uint64_t *g = grp + r * 32;
+                if (g[0] != SK_GRP_FAST) continue;
+                const uint32_t p = (uint32_t)(offsets[r] - wb);
+                for (uint32_t l = 0; l < 32; l++)
+                    g[l] = l * G < c.rsi ? sk_group_entry(c, T.data(), Rv.data(), LV, np, wb, p, l * G) : 0ull;
+            }
+        }
+    }
+    for (uint64_t r = 0; r < s.found; r++) {
+        if (grp && grp[r * 32] == SK_GRP_MISSING) group_index_by_skim(c, br, offsets[r], grp + r * 32);   /* builder, only_missing */
+        if (grp_ref) group_index_by_skim(c, br, offsets[r], grp_ref + r * 32);
     }
     *found = s.found; *out_flags = s.flags; *fast = s.fast; *end_pos = s.pos;
     return 0;

@@ -105,6 +105,14 @@ def test_unindexed_buffer_decode_of_the_configs(name, mib):
     dec = L.buffer_decode(p, enc["out"], raw.size)
     assert dec["status"] == 0 and dec["out"].size == raw.size
     assert np.array_equal(dec["out"], raw)
+    # the group index the discovery wrote from its tables is the one the warp-per-RSI kernel accepts: hardly any
+    # RSI goes to the careful kernel
+    import ctypes as C
+    lib = L.load_library()
+    ctx = C.c_void_p(lib.aecb200_pool_get())
+    handed = lib.aecb200_ctx_last_handover(ctx)
+    lib.aecb200_pool_put(ctx)
+    assert handed <= 2, (name, handed)
     codec = L.DeviceCodec()
     R = p.rsi * p.block_size
     nrsi = (raw.size // B + R - 1) // R

@@ -106,3 +106,44 @@ def test_tables_resume_inside_the_stream(model):
         o1, _, _, _ = scan(model, p, enc["out"], 100, 0, 1, start_bit=int(offs[2]))
         o2, _, _, _ = scan(model, p, enc["out"], 100, 1024, 0, start_bit=int(offs[2]))
         assert np.array_equal(o1, o2) and o1[0] == offs[2], (seed, p)
+
+
+def scan_grp(m, p, comp, max_rsi, window):
+    src = np.ascontiguousarray(comp)
+    offs = np.zeros(max(max_rsi, 1), np.uint64)
+    grp = np.zeros(max(max_rsi, 1) * 32, np.uint64)
+    ref = np.zeros(max(max_rsi, 1) * 32, np.uint64)
+    found, flags, fast, end = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    rc = m.model_scan_offsets_grp(C.c_uint32(p.bits_per_sample), C.c_uint32(p.block_size), C.c_uint32(p.rsi),
+                                  C.c_uint32(p.flags), src.ctypes.data_as(C.c_void_p), C.c_size_t(src.size),
+                                  C.c_uint64(0), offs.ctypes.data_as(C.c_void_p), C.c_uint64(max_rsi),
+                                  C.c_uint64(window), C.c_int(0), C.byref(found), C.byref(flags), C.byref(fast),
+                                  C.byref(end), grp.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    n = found.value
+    return grp[: n * 32].reshape(n, 32), ref[: n * 32].reshape(n, 32), fast.value
+
+
+def test_group_index_from_the_tables_equals_the_skimmed_one(model):
+    """The group index the warp-per-RSI decoder reads (where every lane's blocks start, how many of them
+    still belong to an earlier zero run), written from the chain tables, against the one a skim of every
+    RSI gives: zero-run heavy data, run-of-zero-segment codes, short last RSIs, padded streams."""
+    done = 0
+    for seed in range(120):
+        case = multi_rsi_case(seed)
+        if case is None:
+            continue
+        p, raw, count = case
+        enc = po.orc_encode(p, raw, pad_rsi_build=bool(p.flags & AEC_PAD_RSI))
+        R = p.rsi * p.block_size
+        nrsi = (count + R - 1) // R
+        G = (p.rsi + 31) // 32
+        used = (p.rsi + G - 1) // G                         # lanes that own blocks
+        for window in (4096, 1 << 25):
+            grp, ref, fast = scan_grp(model, p, enc["out"], nrsi, window)
+            assert grp.shape[0] == nrsi
+            assert np.array_equal(grp[:, :used], ref[:, :used]), (seed, p, window)
+            if window == 1 << 25 and nrsi > 2:
+                assert fast >= nrsi - 2
+        done += 1
+    assert done > 40
