@@ -633,6 +633,7 @@ static int encode_device_impl(aecb200_ctx *ctx, const aecb200_params *p, const v
 int aecb200_encode_finish(aecb200_ctx *ctx, aecb200_carry *end)
 {
     if (!ctx || !ctx->enc_pending) return AEC_CONF_ERROR;
+    ENTER_DEVICE();                 /* a caller-supplied stream may be the legacy default stream, which means "of the current device" */
     CK(cudaStreamSynchronize(ctx->stream), "encode sync");
     ctx->enc_pending = false;
     if (end) { end->bits = ctx->h_res[0]; end->k = (uint32_t)ctx->h_res[1]; end->word = 0; }
@@ -774,6 +775,7 @@ uint64_t aecb200_ctx_last_handover(aecb200_ctx *ctx) { return ctx ? (ctx->h_res[
 int aecb200_decode_finish(aecb200_ctx *ctx, size_t *out_written)
 {
     if (!ctx || !ctx->dec_pending) return AEC_CONF_ERROR;
+    ENTER_DEVICE();
     CK(cudaStreamSynchronize(ctx->stream), "decode sync");
     ctx->dec_pending = false;
     uint64_t got = ctx->dec_expect;
