@@ -121,6 +121,8 @@ struct AecSkimArgs {
     uint32_t *T;                /* [LV][np] */
     uint32_t *H;                /* [np] RSI lengths */
     uint32_t *R;                /* [np] entries of a first CDS of an RSI (the one with the reference sample) */
+    uint32_t *H8;               /* optional: two buffers of [np] behind each other; the second ends up holding the length of
+                                 * eight RSIs in a row (streams of many short RSIs: the walk then takes an eighth of the steps) */
     uint64_t *grp_index;        /* optional [max_rsi * 32]: group index of the RSIs found (AecDecArgs::grp_index) */
     uint32_t grp_G;             /* blocks per group = ceil(rsi / 32) */
     uint64_t *state;            /* [0] next RSI bit, [1] RSIs found, [2] flags (1 ended, 2 data error), [3] RSIs taken from the tables,

@@ -217,6 +217,7 @@ struct aecb200_ctx {
     uint64_t scan_window_bits = 1ull << 25;
     uint64_t scan_end = 0, scan_fast = 0;
     bool scan_grp = false;               /* the last scan also wrote the group index */
+    int scan_skip8 = -1;                 /* eight-RSI jumps of the walk: -1 by RSI density, 0 never, 1 always (AECB200_SCAN_SKIP8) */
     std::vector<uint64_t> found_offs;    /* RSI offsets the last host decode discovered itself (bits from in[0]) */
 
     /* bookkeeping of the last enqueued operation */
@@ -412,6 +413,7 @@ int aecb200_ctx_create(aecb200_ctx **out, int device)
     }
     /* test hooks: force one of the RSI boundary discovery paths / a small table window */
     if (getenv("AECB200_NO_BOUNCE")) ctx->no_bounce = true;
+    if (const char *k = getenv("AECB200_SCAN_SKIP8")) ctx->scan_skip8 = atoi(k);
     if (const char *m = getenv("AECB200_SCAN_MODE")) ctx->scan_mode = atoi(m);
     if (const char *w = getenv("AECB200_SCAN_WINDOW_BITS")) { long long v = atoll(w); if (v > 0) ctx->scan_window_bits = (uint64_t)v; }
     *out = ctx;
@@ -856,7 +858,12 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
     if (np_max >= 0x7FFFFFFFull) { snprintf(ctx->err, sizeof ctx->err, "scan window too large"); return AEC_CONF_ERROR; }
     /* two table sets: the walk through window i (one thread, a dependent load per RSI) runs on a side
      * stream next to the table kernels of window i+1 */
-    const size_t set_words = (size_t)(LV + 2u) * (size_t)np_max;       /* the levels, H and R */
+    /* Streams of many short RSIs (well-compressed data, small chunks): the one-load-per-RSI walk would take
+     * longer than the tables; three more passes give the length of eight RSIs in a row and the walk an
+     * eighth of its steps.  Decided from what the caller expects: RSIs asked for per window of stream. */
+    const double rsis_per_window = (double)max_rsi * (double)(nh < span ? nh : span) / (double)span;
+    const bool skip8 = ctx->scan_skip8 == 1 || (ctx->scan_skip8 < 0 && rsis_per_window > 2500.0);
+    const size_t set_words = (size_t)(LV + 2u + (skip8 ? 2u : 0u)) * (size_t)np_max;   /* the levels, H and R (and two doubling buffers) */
     const int nsets = nwin > 1 ? 2 : 1;
     CK(ctx->skim_tab.ensure(set_words * 4u * (size_t)nsets), "cudaMalloc(skim tables)");
     if (!ctx->s_walk) CK(cudaStreamCreateWithFlags(&ctx->s_walk, cudaStreamNonBlocking), "cudaStreamCreate(walk)");
@@ -881,6 +888,7 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
         a.T = (uint32_t *)ctx->skim_tab.p + (size_t)k * set_words;
         a.H = a.T + (size_t)LV * (size_t)np_max;
         a.R = a.H + (size_t)np_max;
+        a.H8 = skip8 ? a.R + (size_t)np_max : nullptr;
         a.wb = base + i * nh;
         const uint64_t rem = ((nbits - a.wb) + 31ull) & ~31ull;
         a.np = (uint32_t)(nh + margin < rem ? nh + margin : rem);
@@ -897,7 +905,7 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
             CK(cudaMemcpyAsync(&ctx->h_res[16 + 4 * s4], state, 32, cudaMemcpyDeviceToHost, ctx->s_walk), "memcpy(scan progress)");
             CK(cudaEventRecord(ctx->ev_prog[s4], ctx->s_walk), "cudaEventRecord");
         }
-        ctx->launches += LV + 2u;
+        ctx->launches += LV + 2u + (skip8 ? 4u : 0u) + (d_grp ? 1u : 0u);
         if (prog && i >= 2) {
             /* The walk through the window two back has finished long ago; two windows of work are queued
              * behind it, so the device stays busy while the host hands that window's RSIs on (a copy to

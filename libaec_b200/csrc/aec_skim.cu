@@ -158,21 +158,28 @@ aec_skim_double_kernel(const AecSkimArgs a, uint32_t level)
  * Same walk as sk_rsi_len (aec_skim_core.cuh), NC candidates per thread in lock step so that their
  * table look-ups -- each a dependent, mostly uncached load -- are in flight together. */
 constexpr int SK_NC = 4;
+#ifndef AEC_SK_ROUNDS
+#define AEC_SK_ROUNDS 2
+#endif
+constexpr int SK_ROUNDS = AEC_SK_ROUNDS;   /* a CTA takes SK_ROUNDS x SK_NC x 256 CONSECUTIVE candidates: the chains of neighbouring
+                                     * candidates stay within a few thousand positions of each other at every level, so the
+                                     * look-ups of one CTA fall into a handful of compact table regions that its L1 keeps */
 __global__ void __launch_bounds__(SK_THREADS)
 aec_skim_rsi_kernel(const AecSkimArgs a)
 {
     if (a.state[2] & 1ull) return;
     const AecCfg &c = a.cfg;
     const uint32_t step = c.pad ? 8u : 1u;              /* padded RSIs start on byte boundaries */
-    const uint32_t t = blockIdx.x * SK_THREADS + threadIdx.x;
-    /* candidate i of thread t: consecutive threads take consecutive positions (coalesced H accesses) */
-    const uint32_t grid_span = gridDim.x * SK_THREADS;
+    const uint32_t np = a.np, rsi = c.rsi;
+    const int top = (int)a.LV - 1;
+    for (int round = 0; round < SK_ROUNDS; round++) {
+    /* candidate i of this thread: consecutive threads take consecutive positions (coalesced R / H accesses) */
+    const uint32_t base = (blockIdx.x * (uint32_t)SK_ROUNDS + (uint32_t)round) * (uint32_t)(SK_NC * SK_THREADS) + threadIdx.x;
     uint32_t p[SK_NC], q[SK_NC], rem[SK_NC];
     bool live[SK_NC];
-    const uint32_t np = a.np, rsi = c.rsi;
 #pragma unroll
     for (int i = 0; i < SK_NC; i++) {
-        p[i] = (t + (uint32_t)i * grid_span) * step;
+        p[i] = (base + (uint32_t)i * SK_THREADS) * step;
         live[i] = p[i] < a.nh_eff;
         const uint32_t first = live[i] ? a.R[p[i]] : 0u;
         uint32_t b = sk_blk(first);
@@ -181,7 +188,6 @@ aec_skim_rsi_kernel(const AecSkimArgs a)
         q[i] = p[i] + sk_len(first);
         rem[i] = live[i] ? rsi - b : 0u;
     }
-    const int top = (int)a.LV - 1;
     for (int guard = 0; guard < 4096; guard++) {
         for (int j = top; j >= 0; j--) {
             const uint32_t *Tj = a.T + (size_t)j * np;
@@ -226,6 +232,7 @@ aec_skim_rsi_kernel(const AecSkimArgs a)
         if (c.pad) end = (end + 7u) & ~7u;                      /* windows start on byte boundaries */
         a.H[p[i]] = (live[i] && rem[i] == 0u) ? end - p[i] : 0u;
     }
+    }   /* round */
 }
 
 /* state: [0] bit position of the next RSI, [1] RSIs found, [2] flags (1 ended, 2 data error),
@@ -240,9 +247,31 @@ __global__ void aec_skim_walk_kernel(const AecSkimArgs a)
     BitRd br;
     br.init(a.in_words, (a.nbits + 31ull) >> 5, a.nbits);
     const uint32_t *H = a.H;
+    const uint32_t *H8 = a.H8 ? a.H8 + a.np : nullptr;
     while (sk_walk_step(c, br, a.nbits, a.wb, a.nh_eff, a.last, a.offsets, a.max_rsi, s,
-                        [H](uint64_t rel) { return __ldcg(H + rel); }, a.grp_index)) { }
+                        [H](uint64_t rel) { return __ldcg(H + rel); }, a.grp_index, H8 != nullptr,
+                        [H8](uint64_t rel) { return __ldcg(H8 + rel); })) { }
     a.state[0] = s.pos; a.state[1] = s.found; a.state[2] = s.flags; a.state[3] = s.fast;
+}
+
+/* RSI lengths doubled: dst[p] = src[p] + src[p + src[p]] for the candidates of the window */
+__global__ void __launch_bounds__(SK_THREADS)
+aec_skim_hdouble_kernel(const AecSkimArgs a, const uint32_t *src, uint32_t *dst)
+{
+    if (a.state[2] & 1ull) return;
+    uint32_t p = blockIdx.x * SK_THREADS + threadIdx.x;
+    if (a.cfg.pad) p <<= 3;
+    if (p >= a.nh_eff) return;
+    dst[p] = sk_hdouble(src, a.nh_eff, p);
+}
+
+/* the offsets the walk skipped over (heads of its long jumps know where they start) */
+__global__ void __launch_bounds__(SK_THREADS)
+aec_skim_fill_kernel(const AecSkimArgs a)
+{
+    const uint64_t r0 = a.state[4], r1 = a.state[1];
+    for (uint64_t r = r0 + (uint64_t)blockIdx.x * SK_THREADS + threadIdx.x; r < r1; r += (uint64_t)gridDim.x * SK_THREADS)
+        sk_fill(a.H, a.wb, a.offsets, r, r1);
 }
 
 /* Group index of the RSIs the walk has just taken from the tables: lane l of a warp finds where block l * G of
@@ -284,8 +313,15 @@ cudaError_t aec_skim_window_launch(const AecSkimArgs &args, cudaStream_t st)
     for (uint32_t j = 0; j + 1u < a.LV; j++)
         aec_skim_double_kernel<<<grid, SK_THREADS, 0, st>>>(a, j);
     const uint32_t cand = a.cfg.pad ? (a.nh_eff + 7u) / 8u : a.nh_eff;
-    const uint32_t per_cta = SK_THREADS * SK_NC;
+    const uint32_t per_cta = SK_THREADS * SK_NC * SK_ROUNDS;
     aec_skim_rsi_kernel<<<(cand + per_cta - 1u) / per_cta, SK_THREADS, 0, st>>>(a);
+    if (a.H8) {
+        /* H -> 2 RSIs -> 4 -> 8, between two buffers; the last result lands in the second one */
+        const uint32_t g2 = (cand + SK_THREADS - 1u) / SK_THREADS;
+        aec_skim_hdouble_kernel<<<g2, SK_THREADS, 0, st>>>(a, a.H, a.H8 + a.np);
+        aec_skim_hdouble_kernel<<<g2, SK_THREADS, 0, st>>>(a, a.H8 + a.np, a.H8);
+        aec_skim_hdouble_kernel<<<g2, SK_THREADS, 0, st>>>(a, a.H8, a.H8 + a.np);
+    }
     return cudaGetLastError();
 }
 
@@ -294,6 +330,7 @@ cudaError_t aec_skim_walk_launch(const AecSkimArgs &a, cudaStream_t st)
 {
     if (a.np == 0) return cudaSuccess;
     aec_skim_walk_kernel<<<1, 32, 0, st>>>(a);
+    if (a.H8) aec_skim_fill_kernel<<<64, SK_THREADS, 0, st>>>(a);
     if (a.grp_index) aec_skim_group_index_kernel<<<64, SK_THREADS, 0, st>>>(a);
     return cudaGetLastError();
 }

@@ -212,18 +212,45 @@ AEC_HD uint32_t sk_lookahead_words(const AecCfg &c)
     return (uint32_t)((c.idl + 1ull + (uint64_t)(c.J + 1u) * c.n + 31ull) / 32ull) + 2u;
 }
 
+#define SK_OFF_PENDING 0xFFFFFFFFFFFFFFFFull    /* walk -> fill: this RSI's offset follows from its predecessor's H */
+#define SK_SKIP 8u                             /* RSIs per long jump of the walk */
+
+/* one doubling step of the RSI lengths: from p over two (four, eight) RSIs, all of which start inside the
+ * part of the window that has lengths (0: not available) */
+AEC_HD uint32_t sk_hdouble(const uint32_t *src, uint32_t nh_eff, uint32_t p)
+{
+    const uint32_t h = src[p];
+    if (h == 0u) return 0u;
+    const uint64_t q = (uint64_t)p + h;
+    if (q >= nh_eff) return 0u;
+    const uint32_t h2 = src[q];
+    return h2 ? h + h2 : 0u;
+}
+
 /* One RSI of the walk: the serial part of the discovery.  Returns false when the walk ends.
  * state: pos, found, flags (1 ended, 2 data error), fast. */
 struct SkWalk { uint64_t pos, found, flags, fast; };
 
-template <class LoadH>
+template <class LoadH, class LoadH8>
 AEC_HD bool sk_walk_step(const AecCfg &c, BitRd &br, uint64_t nbits, uint64_t wb, uint32_t nh_eff, uint32_t last,
-                         uint64_t *offsets, uint64_t max_rsi, SkWalk &s, LoadH load_h, uint64_t *grp = nullptr)
+                         uint64_t *offsets, uint64_t max_rsi, SkWalk &s, LoadH load_h, uint64_t *grp, bool have_h8, LoadH8 load_h8)
 {
     if (s.found >= max_rsi) { s.flags = 1; return false; }
     const uint64_t start = c.pad ? ((s.pos + 7ull) & ~7ull) : s.pos;
     if (start >= nbits) { s.flags = 1; return false; }
     if (start >= wb + nh_eff && !last) return false;    /* the next window takes over */
+    if (have_h8 && s.found + SK_SKIP <= max_rsi && start - wb < nh_eff) {
+        /* eight RSIs with one look-up: their offsets are filled in afterwards, in parallel (sk_fill) */
+        const uint32_t h8 = load_h8(start - wb);
+        if (h8) {
+            offsets[s.found] = start;
+            for (uint32_t t = 1; t < SK_SKIP; t++) offsets[s.found + t] = SK_OFF_PENDING;
+            if (grp) for (uint32_t t = 0; t < SK_SKIP; t++) grp[(s.found + t) * 32ull] = SK_GRP_FAST;
+            s.found += SK_SKIP; s.fast += SK_SKIP;
+            s.pos = start + h8;
+            return true;
+        }
+    }
     offsets[s.found++] = start;                         /* even a truncated RSI may still deliver leading samples */
     const uint64_t rel = start - wb;
     const uint32_t h = rel < nh_eff ? load_h(rel) : 0u;
@@ -236,6 +263,17 @@ AEC_HD bool sk_walk_step(const AecCfg &c, BitRd &br, uint64_t nbits, uint64_t wb
     s.pos = st.pos;
     if (st.status != DEC_OK) { s.flags = 1ull | (st.status == DEC_ERROR ? 2ull : 0ull); return false; }
     return true;
+}
+
+/* offsets the walk left pending behind RSI r (the head of a long jump): one H look-up each */
+AEC_HD void sk_fill(const uint32_t *H, uint64_t wb, uint64_t *offsets, uint64_t r, uint64_t found)
+{
+    if (offsets[r] == SK_OFF_PENDING || r + 1 >= found || offsets[r + 1] != SK_OFF_PENDING) return;
+    uint64_t q = offsets[r];
+    for (uint64_t t = 1; t < SK_SKIP && r + t < found && offsets[r + t] == SK_OFF_PENDING; t++) {
+        q += H[q - wb];
+        offsets[r + t] = q;
+    }
 }
 
 #endif /* AEC_SKIM_CORE_CUH */

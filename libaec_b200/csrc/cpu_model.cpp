@@ -235,6 +235,9 @@ extern "C" int model_decode(uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags
 /* ------------------------------------------------------------------------ */
 #include "aec_skim_core.cuh"
 
+static int g_skip8 = 0;
+extern "C" void model_set_skip8(int on) { g_skip8 = on; }   /* the walk's eight-RSI jumps (aec_skim_hdouble_kernel, aec_skim_fill_kernel) */
+
 /* the group index the way aec_build_group_index_kernel builds it: one skim of the RSI from its start offset */
 static void group_index_by_skim(const AecCfg &c, BitRd &br, uint64_t start, uint64_t *g)
 {
@@ -342,9 +345,21 @@ extern "C" int model_scan_offsets_grp(uint32_t n, uint32_t J, uint32_t rsi, uint
             for (uint32_t p = 0; p < np; p++) T[(size_t)(j + 1) * np + p] = sk_double(T.data() + (size_t)j * np, np, p);
         for (uint32_t p = 0; p < nh_eff; p += c.pad ? 8u : 1u) H[p] = sk_rsi_len(c, T.data(), LV, np, p, Rv[p]);
         const uint32_t *Hp = H.data();
+        std::vector<uint32_t> Ha, Hb;
+        if (g_skip8) {
+            Ha.assign(np, 0u); Hb.assign(np, 0u);
+            const uint32_t stp = c.pad ? 8u : 1u;
+            for (uint32_t p = 0; p < nh_eff; p += stp) Hb[p] = sk_hdouble(H.data(), nh_eff, p);
+            for (uint32_t p = 0; p < nh_eff; p += stp) Ha[p] = sk_hdouble(Hb.data(), nh_eff, p);
+            for (uint32_t p = 0; p < nh_eff; p += stp) Hb[p] = sk_hdouble(Ha.data(), nh_eff, p);
+        }
+        const uint32_t *H8p = g_skip8 ? Hb.data() : nullptr;
         const uint64_t f0 = s.found;
         while (sk_walk_step(c, br, nbits, wb, nh_eff, last, offsets, max_rsi, s,
-                            [Hp](uint64_t rel) { return Hp[rel]; }, grp)) { }
+                            [Hp](uint64_t rel) { return Hp[rel]; }, grp, H8p != nullptr,
+                            [H8p](uint64_t rel) { return H8p[rel]; })) { }
+        if (g_skip8)
+            for (uint64_t r = f0; r < s.found; r++) sk_fill(Hp, wb, offsets, r, s.found);
         if (grp) {                                                      /* aec_skim_group_index_kernel */
             for (uint64_t r = f0; r < s.found; r++) {
                 uint64_t *g = grp + r * 32;

@@ -147,3 +147,40 @@ def test_group_index_from_the_tables_equals_the_skimmed_one(model):
                 assert fast >= nrsi - 2
         done += 1
     assert done > 40
+
+
+def test_eight_rsi_jumps_of_the_walk(model):
+    """Streams of many short RSIs: the walk jumps eight RSIs per look-up (RSI lengths doubled three times) and
+    the offsets in between are filled in afterwards; same offsets, same group index."""
+    model.model_set_skip8(1)
+    try:
+        done = 0
+        for seed in range(120):
+            case = multi_rsi_case(seed, max_total=40_000)
+            if case is None:
+                continue
+            p, raw, count = case
+            if p.rsi > 16:
+                continue                                    # many RSIs per stream wanted here
+            vals = np.tile(raw, 6)[: raw.size * 6 // p.bytes_per_sample * p.bytes_per_sample]
+            enc = po.orc_encode(p, vals, want_offsets=True, pad_rsi_build=bool(p.flags & AEC_PAD_RSI))
+            R = p.rsi * p.block_size
+            nrsi = (vals.size // p.bytes_per_sample + R - 1) // R
+            rng = np.random.default_rng(seed)
+            for cut in (enc["out"].size, int(rng.integers(1, enc["out"].size + 1))):
+                c = enc["out"][:cut]
+                o1, e1, _, end1 = scan(model, p, c, nrsi + 3, 0, 1)
+                for window in (2048, 1 << 25):
+                    o2, e2, fast, end2 = scan(model, p, c, nrsi + 3, window, 0)
+                    assert e1 == e2 and np.array_equal(o1, o2), (seed, p, cut, window)
+                o3, _, _, _ = scan(model, p, c, 11, 1 << 25, 0)
+                assert np.array_equal(o3, o1[:11]), (seed, p, cut)
+            grp, ref, fast = scan_grp(model, p, enc["out"], nrsi, 1 << 25)
+            G = (p.rsi + 31) // 32
+            used = (p.rsi + G - 1) // G
+            assert np.array_equal(grp[:, :used], ref[:, :used]), (seed, p)
+            assert nrsi < 20 or fast >= nrsi - 9, (seed, p, fast, nrsi)
+            done += 1
+        assert done > 15
+    finally:
+        model.model_set_skip8(0)
