@@ -217,6 +217,7 @@ struct aecb200_ctx {
     uint64_t scan_window_bits = 1ull << 25;
     uint64_t scan_end = 0, scan_fast = 0;
     bool scan_grp = false;               /* the last scan also wrote the group index */
+    uint64_t up_first_bits = 0;          /* un-indexed host decode: stream bits that were uploaded on `stream`; the rest is on s_in */
     int scan_skip8 = -1;                 /* eight-RSI jumps of the walk: -1 by RSI density, 0 never, 1 always (AECB200_SCAN_SKIP8) */
     std::vector<uint64_t> found_offs;    /* RSI offsets the last host decode discovered itself (bits from in[0]) */
 
@@ -832,8 +833,13 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
     uint64_t *h_state = &ctx->h_res[8];
     h_state[0] = start_bit; h_state[1] = 0; h_state[2] = 0; h_state[3] = 0;
     CK(cudaMemcpyAsync(state, h_state, 32, cudaMemcpyHostToDevice, ctx->stream), "memcpy(scan state)");
+    uint64_t up_first_bits = ctx->up_first_bits;        /* stream bits uploaded on the context's stream; the rest follows on s_in (ev[0]) */
     const uint64_t base = start_bit & ~127ull;          /* windows start 16-byte aligned (bulk copies of the tiles) */
     const bool parallel = ctx->scan_mode == 2 || (ctx->scan_mode == 0 && in_bytes >= 2048);
+    if ((!parallel || base >= nbits) && up_first_bits) {
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[0], 0), "cudaStreamWaitEvent");
+        up_first_bits = 0;
+    }
     if (!parallel || base >= nbits) {
         /* short streams: one thread skims CDS after CDS (a dozen launches would cost more) */
         uint64_t *res = state;
@@ -895,6 +901,10 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
         a.last = (i + 1 == nwin) ? 1u : 0u;
         a.nh_eff = a.last ? a.np : (uint32_t)nh;
         if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_skim[2 + k], 0), "cudaStreamWaitEvent");   /* set k is free again */
+        if (up_first_bits && a.wb + a.np + 8192ull > up_first_bits) {      /* this window reads beyond the part uploaded first */
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[0], 0), "cudaStreamWaitEvent");
+            up_first_bits = 0;
+        }
         CK(aec_skim_window_launch(a, ctx->stream), "skim launch");
         CK(cudaEventRecord(ctx->ev_skim[k], ctx->stream), "cudaEventRecord");
         CK(cudaStreamWaitEvent(ctx->s_walk, ctx->ev_skim[k], 0), "cudaStreamWaitEvent");
@@ -1270,8 +1280,24 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
         d_stream = (const uint8_t *)ctx->acc_stage.p + (size_t)(A - ctx->acc_start);
     } else {
         CK(ctx->in_stage.ensure(in_pad + 16), "cudaMalloc(in)");
-        CK(cudaMemsetAsync((uint8_t *)ctx->in_stage.p + (in_pad - 4), 0, 4, ctx->stream), "memset(in tail)");
-        CK(copy_h2d(ctx, ctx->in_stage.p, (const uint8_t *)in + base_byte, nbytes, ctx->stream), "H2D");
+        /* Without an index the discovery starts at the front of the stream: upload what its first two windows
+         * read, start, and let the rest of the stream follow on the upload stream meanwhile (the window
+         * that first reaches beyond waits for it: scan_offsets_impl). */
+        size_t first = nbytes;
+        ctx->up_first_bits = 0;
+        if (!rsi_offsets && ctx->pipe_piece && nbytes > ((size_t)32 << 20) && pipe_prepare(ctx, 1) == AEC_OK) {
+            first = (size_t)((2 * ((ctx->scan_window_bits + 127ull) & ~127ull) + aec_skim_margin_bits(c)) / 8ull) + 65536;
+            first &= ~(size_t)15;
+            if (first >= nbytes) first = nbytes;
+        }
+        if (first == nbytes) CK(cudaMemsetAsync((uint8_t *)ctx->in_stage.p + (in_pad - 4), 0, 4, ctx->stream), "memset(in tail)");
+        CK(copy_h2d(ctx, ctx->in_stage.p, (const uint8_t *)in + base_byte, first, ctx->stream), "H2D");
+        if (first < nbytes) {
+            CK(cudaMemsetAsync((uint8_t *)ctx->in_stage.p + (in_pad - 4), 0, 4, ctx->s_in), "memset(in tail)");
+            CK(copy_h2d(ctx, (uint8_t *)ctx->in_stage.p + first, (const uint8_t *)in + base_byte + first, nbytes - first, ctx->s_in), "H2D");
+            CK(cudaEventRecord(ctx->ev[0], ctx->s_in), "cudaEventRecord");
+            ctx->up_first_bits = (uint64_t)first * 8ull;
+        }
         d_stream = (const uint8_t *)ctx->in_stage.p;
     }
     size_t nrsi = 0;
@@ -1316,6 +1342,11 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
         rc = scan_offsets_impl(ctx, p, d_stream, nbytes, start_bit - base_bit,
                                (uint64_t *)ctx->offs.p, (size_t)need_rsi, &nrsi, early.on ? &early : nullptr,
                                ctx->careful_only ? nullptr : (uint64_t *)ctx->grp.p);
+        if (ctx->up_first_bits) {                       /* whatever the scan did not wait for: the decode reads all of it */
+            ctx->up_first_bits = 0;
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[0], 0), "cudaStreamWaitEvent");
+            if (ctx->aux) CK(cudaStreamWaitEvent(ctx->aux->stream, ctx->ev[0], 0), "cudaStreamWaitEvent");
+        }
         scan_grp = ctx->scan_grp;
         if (early.on) {
             early.finish_pending();

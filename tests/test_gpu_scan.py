@@ -163,3 +163,51 @@ def test_decoder_reports_the_offsets_it_discovered():
         R = p.rsi * p.block_size * B
         got = L.decode_range(p, enc["out"], dec["offsets"], 3 * R + 5 * B, 2 * R)
         assert got["status"] == 0 and np.array_equal(got["out"], raw[3 * R + 5 * B: 5 * R + 5 * B])
+
+
+def test_damaged_streams_parallel_equals_serial_and_nothing_crashes():
+    """Bit flips anywhere in the stream.  What the reference delivers for damaged input is not defined by the
+    reference itself: its second-extension decoder indexes a 91-entry table with an unchecked fundamental
+    sequence (decode.c:589-600) and its inverse predictor runs on values beyond n bits (decode.c:96-131), so
+    sample values after the damage are not compared with anything.  What must hold: the tables tell the same
+    story as the one-thread scan (same offsets, same status), both decoders finish with a libaec status and
+    deliver the same number of bytes when both call the stream good, and no call fails in CUDA."""
+    import torch
+    codec = L.DeviceCodec()
+    rng = np.random.default_rng(2024)
+    done = 0
+    for seed in range(120):
+        case = _multi_rsi_case(seed)
+        if case is None:
+            continue
+        p, raw, count = case
+        pad_build = bool(p.flags & L.AEC_PAD_RSI)
+        comp = po.orc_encode(p, raw, pad_rsi_build=pad_build)["out"].copy()
+        R = p.rsi * p.block_size
+        nrsi = (count + R - 1) // R
+        nflip = int(rng.integers(1, 6))
+        for _ in range(nflip):
+            i = int(rng.integers(0, comp.size))
+            comp[i] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        st1, off1, _ = _scan(codec, torch, p, comp, nrsi + 3, 1, 0)
+        for window in (2048, 1 << 25):
+            st2, off2, _ = _scan(codec, torch, p, comp, nrsi + 3, 2, window)
+            assert st2 == st1 and np.array_equal(off2, off1), (seed, p, window)
+        B = p.bytes_per_sample
+        a = L.buffer_decode(P(p), comp, count * B)                      # tables + warp-per-RSI decoder
+        assert a["status"] in (L.AEC_OK, L.AEC_DATA_ERROR, L.AEC_MEM_ERROR), (seed, p, a["status"])
+        codec.set_careful_decode(True)
+        codec.set_scan_mode(1, 0)
+        pad = (-comp.size) % 4
+        d_in = torch.from_numpy(np.concatenate([comp, np.zeros(pad + 8, np.uint8)])).cuda()
+        d_off = torch.from_numpy(off1.astype(np.int64)).cuda() if off1.size else torch.zeros(1, dtype=torch.int64, device="cuda")
+        d_out = torch.zeros(count * B + 16, dtype=torch.uint8, device="cuda")
+        assert codec.decode_enqueue(P(p), d_in, comp.size, d_off, off1.size, d_out, count * B) == 0
+        stc, written = codec.decode_finish()
+        codec.set_careful_decode(False)
+        assert stc in (L.AEC_OK, L.AEC_DATA_ERROR, L.AEC_MEM_ERROR), (seed, p, stc)
+        if a["status"] == L.AEC_OK and stc == 0:
+            assert a["out"].size == written, (seed, p)
+        done += 1
+    assert done > 60
+    codec.close()
