@@ -123,14 +123,20 @@ struct AecSkimArgs {
     uint32_t *R;                /* [np] entries of a first CDS of an RSI (the one with the reference sample) */
     uint32_t *H8;               /* optional: two buffers of [np] behind each other; the second ends up holding the length of
                                  * eight RSIs in a row (streams of many short RSIs: the walk then takes an eighth of the steps) */
+    uint32_t sparse;            /* RSI lengths for marked chain ends only (LV >= 4; state[5] turns it off on the device) */
+    uint32_t set;               /* table set of this window (0/1): which list counter it uses */
+    uint32_t *cand_list;        /* optional [cand_cap]: positions that have an RSI length (what the long-jump passes run over) */
+    uint32_t cand_cap;
     uint64_t *grp_index;        /* optional [max_rsi * 32]: group index of the RSIs found (AecDecArgs::grp_index) */
     uint32_t grp_G;             /* blocks per group = ceil(rsi / 32) */
     uint64_t *state;            /* [0] next RSI bit, [1] RSIs found, [2] flags (1 ended, 2 data error), [3] RSIs taken from the tables,
-                                 * [4] RSIs found before the current window's walk */
+                                 * [4] RSIs found before the current window's walk, [5] bit 0: dense tables from now on,
+                                 * [6], [7] per table set: candidates listed; bit 63: this window's tables are dense */
     uint64_t *offsets;          /* [max_rsi] */
     uint64_t max_rsi;
 };
 uint32_t aec_skim_levels(const AecCfg &c);
+uint32_t aec_skim_sparse_min_levels(void);  /* sparse candidates need this many levels */
 uint64_t aec_skim_margin_bits(const AecCfg &c);
 /* level-0 tables, doubling and RSI lengths of one window; then the walk through it */
 cudaError_t aec_skim_window_launch(const AecSkimArgs &a, cudaStream_t st);

@@ -218,6 +218,7 @@ struct aecb200_ctx {
     uint64_t scan_end = 0, scan_fast = 0;
     bool scan_grp = false;               /* the last scan also wrote the group index */
     uint64_t up_first_bits = 0;          /* un-indexed host decode: stream bits that were uploaded on `stream`; the rest is on s_in */
+    int scan_sparse = 1;                 /* RSI lengths at marked chain ends only (AECB200_SCAN_SPARSE=0: every position, as before) */
     int scan_skip8 = -1;                 /* eight-RSI jumps of the walk: -1 by RSI density, 0 never, 1 always (AECB200_SCAN_SKIP8) */
     std::vector<uint64_t> found_offs;    /* RSI offsets the last host decode discovered itself (bits from in[0]) */
 
@@ -415,6 +416,7 @@ int aecb200_ctx_create(aecb200_ctx **out, int device)
     /* test hooks: force one of the RSI boundary discovery paths / a small table window */
     if (getenv("AECB200_NO_BOUNCE")) ctx->no_bounce = true;
     if (const char *k = getenv("AECB200_SCAN_SKIP8")) ctx->scan_skip8 = atoi(k);
+    if (const char *k = getenv("AECB200_SCAN_SPARSE")) ctx->scan_sparse = atoi(k) != 0;
     if (const char *m = getenv("AECB200_SCAN_MODE")) ctx->scan_mode = atoi(m);
     if (const char *w = getenv("AECB200_SCAN_WINDOW_BITS")) { long long v = atoll(w); if (v > 0) ctx->scan_window_bits = (uint64_t)v; }
     *out = ctx;
@@ -831,8 +833,9 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
     const uint64_t nbits = (uint64_t)in_bytes * 8ull;
     /* walk state: next RSI bit, RSIs found, flags, RSIs taken from the tables */
     uint64_t *h_state = &ctx->h_res[8];
-    h_state[0] = start_bit; h_state[1] = 0; h_state[2] = 0; h_state[3] = 0;
-    CK(cudaMemcpyAsync(state, h_state, 32, cudaMemcpyHostToDevice, ctx->stream), "memcpy(scan state)");
+    h_state[0] = start_bit;
+    for (int i = 1; i < 8; i++) h_state[i] = 0;         /* [4..7]: first RSI of the window, dense request, list counters */
+    CK(cudaMemcpyAsync(state, h_state, 64, cudaMemcpyHostToDevice, ctx->stream), "memcpy(scan state)");
     uint64_t up_first_bits = ctx->up_first_bits;        /* stream bits uploaded on the context's stream; the rest follows on s_in (ev[0]) */
     const uint64_t base = start_bit & ~127ull;          /* windows start 16-byte aligned (bulk copies of the tiles) */
     const bool parallel = ctx->scan_mode == 2 || (ctx->scan_mode == 0 && in_bytes >= 2048);
@@ -868,8 +871,13 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
      * longer than the tables; three more passes give the length of eight RSIs in a row and the walk an
      * eighth of its steps.  Decided from what the caller expects: RSIs asked for per window of stream. */
     const double rsis_per_window = (double)max_rsi * (double)(nh < span ? nh : span) / (double)span;
-    const bool skip8 = ctx->scan_skip8 == 1 || (ctx->scan_skip8 < 0 && rsis_per_window > 2500.0);
-    const size_t set_words = (size_t)(LV + 2u + (skip8 ? 2u : 0u)) * (size_t)np_max;   /* the levels, H and R (and two doubling buffers) */
+    /* Sparse candidates (aec_skim_core.cuh: SK_CAND) make the tables cheap enough for the walk to show: the long
+     * jumps, which then run over the list of candidates only, pay from a few hundred RSIs per window on. */
+    const bool sparse = ctx->scan_sparse && LV >= aec_skim_sparse_min_levels();
+    const bool skip8 = ctx->scan_skip8 == 1 || (ctx->scan_skip8 < 0 && rsis_per_window > (sparse ? 256.0 : 2500.0));
+    const size_t cand_cap = (sparse && skip8) ? (size_t)((np_max / 4u + 63u) & ~63ull) : 0;
+    /* the levels, H and R (and two doubling buffers, and the list of candidates) */
+    const size_t set_words = (size_t)(LV + 2u + (skip8 ? 2u : 0u)) * (size_t)np_max + cand_cap;
     const int nsets = nwin > 1 ? 2 : 1;
     CK(ctx->skim_tab.ensure(set_words * 4u * (size_t)nsets), "cudaMalloc(skim tables)");
     if (!ctx->s_walk) CK(cudaStreamCreateWithFlags(&ctx->s_walk, cudaStreamNonBlocking), "cudaStreamCreate(walk)");
@@ -895,6 +903,10 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
         a.H = a.T + (size_t)LV * (size_t)np_max;
         a.R = a.H + (size_t)np_max;
         a.H8 = skip8 ? a.R + (size_t)np_max : nullptr;
+        a.sparse = sparse ? 1u : 0u;
+        a.set = (uint32_t)k;
+        a.cand_list = cand_cap ? a.H8 + 2u * (size_t)np_max : nullptr;
+        a.cand_cap = (uint32_t)cand_cap;
         a.wb = base + i * nh;
         const uint64_t rem = ((nbits - a.wb) + 31ull) & ~31ull;
         a.np = (uint32_t)(nh + margin < rem ? nh + margin : rem);
@@ -915,7 +927,7 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
             CK(cudaMemcpyAsync(&ctx->h_res[16 + 4 * s4], state, 32, cudaMemcpyDeviceToHost, ctx->s_walk), "memcpy(scan progress)");
             CK(cudaEventRecord(ctx->ev_prog[s4], ctx->s_walk), "cudaEventRecord");
         }
-        ctx->launches += LV + 2u + (skip8 ? 4u : 0u) + (d_grp ? 1u : 0u);
+        ctx->launches += LV + 2u + (sparse ? 2u : 0u) + (skip8 ? (sparse ? 7u : 4u) : 0u) + (d_grp ? 1u : 0u);
         if (prog && i >= 2) {
             /* The walk through the window two back has finished long ago; two windows of work are queued
              * behind it, so the device stays busy while the host hands that window's RSIs on (a copy to

@@ -19,6 +19,11 @@
  *                               then a greedy descent through the levels until exactly `rsi` blocks
  *                               are accounted for (run-of-zero-segment codes stand for "up to the end of
  *                               the 64-block segment" and are resolved here, where the block number is known).
+ *      aec_skim_rsi_sparse_kernel  the same for the candidates only: an RSI starts where a chain of CDSs ends, and
+ *                               the top-level chains of ALL positions end on a few per cent of them (the
+ *                               doubling passes mark those in H, aec_skim_core.cuh: SK_CAND); the walk works
+ *                               out the rare start that was not marked itself and turns the stream to dense
+ *                               tables when that happens often.
  *   4. aec_skim_walk_kernel     the only serial part: one load of H per RSI from the stream's known
  *                               first bit; RSIs whose H is not available (truncated or corrupt stream,
  *                               a chain leaving the window) are skimmed CDS by CDS like the reference does.
@@ -36,6 +41,19 @@ namespace {
 
 constexpr int SK_THREADS = 256;
 constexpr uint32_t SK_TILE = 8192;          /* bit positions per CTA of the level-0 kernel */
+
+/* state[5] bit 0: the walk asked for dense tables (it runs on its own stream, next to the table kernels of the
+ * following window).  A window latches the request once, before its first kernel, into bit 63 of its list
+ * counter, so that all its kernels and its walk agree on what the tables hold. */
+constexpr unsigned long long SK_DENSE_BIT = 1ull << 63;
+__global__ void aec_skim_begin_kernel(const AecSkimArgs a)
+{
+    a.state[6 + a.set] = (*reinterpret_cast<volatile const uint64_t *>(a.state + 5) & 1ull) ? SK_DENSE_BIT : 0ull;
+}
+__device__ __forceinline__ bool sk_sparse_now(const AecSkimArgs &a)
+{
+    return a.sparse && !(a.state[6 + a.set] & SK_DENSE_BIT);
+}
 
 __global__ void __launch_bounds__(SK_THREADS)
 aec_skim_level0_kernel(const AecSkimArgs a)
@@ -113,6 +131,7 @@ aec_skim_level0_kernel(const AecSkimArgs a)
             __syncthreads();
         }
     }
+    const bool sparse = sk_sparse_now(a);
     /* bits of the stream that exist, relative to the tile */
     const uint64_t tile_abs = a.wb + tile0;
     const uint32_t limit = a.nbits > tile_abs ? (uint32_t)min((unsigned long long)(a.nbits - tile_abs), 0x7FFFFFFFull) : 0u;
@@ -126,6 +145,7 @@ aec_skim_level0_kernel(const AecSkimArgs a)
         }
         a.T[p] = t0;
         a.R[p] = r0;
+        if (sparse) a.H[p] = 0u;                        /* the doubling passes mark the candidates in here */
     }
 }
 
@@ -152,6 +172,19 @@ aec_skim_double_kernel(const AecSkimArgs a, uint32_t level)
         r[i] = (sk_jump(y[i]) && blk <= 0xFFFu && len <= 0xFFFFFu) ? ((len << 12) | blk) : 0u;
     }
     *reinterpret_cast<uint4 *>(dst + p) = make_uint4(r[0], r[1], r[2], r[3]);
+    if (!sk_sparse_now(a)) return;
+    /* candidates for RSI starts: behind a run-of-zero-segment code (level 0 is at hand in the first pass) and
+     * where the chains of the top level end (the last pass has just worked them out) */
+    if (level == 0u) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (sk_ros(xs[i])) { const uint32_t t = sk_mark_pos(a.cfg, p + i + sk_len(xs[i])); if (t < a.nh_eff) a.H[t] = SK_CAND; }
+    }
+    if (level + 2u == a.LV) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (sk_jump(r[i])) { const uint32_t t = sk_mark_pos(a.cfg, p + i + sk_len(r[i])); if (t < a.nh_eff) a.H[t] = SK_CAND; }
+    }
 }
 
 /* H[p] <- bits from p to the start of the next RSI when an RSI starts at p (0: not available).
@@ -164,23 +197,15 @@ constexpr int SK_NC = 4;
 constexpr int SK_ROUNDS = AEC_SK_ROUNDS;   /* a CTA takes SK_ROUNDS x SK_NC x 256 CONSECUTIVE candidates: the chains of neighbouring
                                      * candidates stay within a few thousand positions of each other at every level, so the
                                      * look-ups of one CTA fall into a handful of compact table regions that its L1 keeps */
-__global__ void __launch_bounds__(SK_THREADS)
-aec_skim_rsi_kernel(const AecSkimArgs a)
+/* The descent of sk_rsi_len for SK_NC starts p[i] at once (live[i]: there is a candidate); out[i] = RSI length or 0. */
+__device__ __forceinline__ void sk_descend_nc(const AecSkimArgs &a, const uint32_t (&p)[SK_NC], bool (&live)[SK_NC], uint32_t (&out)[SK_NC])
 {
-    if (a.state[2] & 1ull) return;
     const AecCfg &c = a.cfg;
-    const uint32_t step = c.pad ? 8u : 1u;              /* padded RSIs start on byte boundaries */
     const uint32_t np = a.np, rsi = c.rsi;
     const int top = (int)a.LV - 1;
-    for (int round = 0; round < SK_ROUNDS; round++) {
-    /* candidate i of this thread: consecutive threads take consecutive positions (coalesced R / H accesses) */
-    const uint32_t base = (blockIdx.x * (uint32_t)SK_ROUNDS + (uint32_t)round) * (uint32_t)(SK_NC * SK_THREADS) + threadIdx.x;
-    uint32_t p[SK_NC], q[SK_NC], rem[SK_NC];
-    bool live[SK_NC];
+    uint32_t q[SK_NC], rem[SK_NC];
 #pragma unroll
     for (int i = 0; i < SK_NC; i++) {
-        p[i] = (base + (uint32_t)i * SK_THREADS) * step;
-        live[i] = p[i] < a.nh_eff;
         const uint32_t first = live[i] ? a.R[p[i]] : 0u;
         uint32_t b = sk_blk(first);
         if (b == 0u) b = rsi < 64u ? rsi : 64u;                 /* run-of-zero-segment at block 0 */
@@ -227,12 +252,110 @@ aec_skim_rsi_kernel(const AecSkimArgs a)
     }
 #pragma unroll
     for (int i = 0; i < SK_NC; i++) {
-        if (p[i] >= a.nh_eff) continue;
         uint32_t end = q[i];
         if (c.pad) end = (end + 7u) & ~7u;                      /* windows start on byte boundaries */
-        a.H[p[i]] = (live[i] && rem[i] == 0u) ? end - p[i] : 0u;
+        out[i] = (live[i] && rem[i] == 0u) ? end - p[i] : 0u;
     }
-    }   /* round */
+}
+
+__global__ void __launch_bounds__(SK_THREADS)
+aec_skim_rsi_kernel(const AecSkimArgs a)
+{
+    if (a.state[2] & 1ull) return;
+    if (sk_sparse_now(a)) return;                       /* aec_skim_rsi_sparse_kernel has done the candidates */
+    const uint32_t step = a.cfg.pad ? 8u : 1u;          /* padded RSIs start on byte boundaries */
+    for (int round = 0; round < SK_ROUNDS; round++) {
+        /* candidate i of this thread: consecutive threads take consecutive positions (coalesced R / H accesses) */
+        const uint32_t base = (blockIdx.x * (uint32_t)SK_ROUNDS + (uint32_t)round) * (uint32_t)(SK_NC * SK_THREADS) + threadIdx.x;
+        uint32_t p[SK_NC], out[SK_NC];
+        bool live[SK_NC];
+#pragma unroll
+        for (int i = 0; i < SK_NC; i++) {
+            p[i] = (base + (uint32_t)i * SK_THREADS) * step;
+            live[i] = p[i] < a.nh_eff;
+        }
+        sk_descend_nc(a, p, live, out);
+#pragma unroll
+        for (int i = 0; i < SK_NC; i++)
+            if (p[i] < a.nh_eff) a.H[p[i]] = out[i];
+    }
+}
+
+/* The candidates only.  A CTA collects the marked positions of SK_CHUNK consecutive candidate slots in shared
+ * memory -- in batches of up to SK_LIST, so that a window full of marks (fixed-length CDSs: chains that never
+ * merge) still fits -- works out their RSI lengths SK_NC per thread like the dense pass, and appends the
+ * positions that have one to the window's list (the long-jump passes run over that list). */
+constexpr uint32_t SK_CHUNK = 32768;
+constexpr uint32_t SK_LIST = 4096;
+__global__ void __launch_bounds__(SK_THREADS)
+aec_skim_rsi_sparse_kernel(const AecSkimArgs a)
+{
+    if (a.state[2] & 1ull) return;
+    if (!sk_sparse_now(a)) return;
+    __shared__ uint32_t s_list[SK_LIST];                /* the batch; its front is reused for the positions to be listed */
+    __shared__ uint32_t s_n, s_m;
+    __shared__ unsigned long long s_at;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t sh = a.cfg.pad ? 3u : 0u;
+    const uint32_t slots = (a.nh_eff + (1u << sh) - 1u) >> sh;
+    const uint32_t slot0 = blockIdx.x * SK_CHUNK;
+    const uint32_t slot1 = slot0 + SK_CHUNK < slots ? slot0 + SK_CHUNK : slots;
+    constexpr uint32_t PER_PASS = SK_THREADS * 4u;      /* slots looked at between two checks of the batch's fill */
+    uint32_t next = slot0;
+    while (next < slot1) {
+        if (tid == 0) { s_n = 0u; s_m = 0u; }
+        __syncthreads();
+        /* collect: whole passes of 1024 slots while the batch surely has room for another one */
+        while (next < slot1) {
+            const uint32_t sl = next + tid * 4u;
+            if (sh == 0u && sl + 3u < slot1) {
+                const uint4 h = *reinterpret_cast<const uint4 *>(a.H + sl);     /* slot0 and nh_eff are multiples of 4 words apart: aligned */
+                if (h.x == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl;
+                if (h.y == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl + 1u;
+                if (h.z == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl + 2u;
+                if (h.w == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl + 3u;
+            } else {
+                for (uint32_t k = 0; k < 4u; k++)
+                    if (sl + k < slot1 && a.H[(sl + k) << sh] == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = (sl + k) << sh;
+            }
+            next += PER_PASS;
+            __syncthreads();
+            if (s_n + PER_PASS > SK_LIST) break;
+            __syncthreads();                            /* nobody adds to s_n before everybody has read it */
+        }
+        __syncthreads();
+        const uint32_t n = s_n;
+        for (uint32_t base = 0; base < n; base += SK_NC * SK_THREADS) {
+            uint32_t p[SK_NC], out[SK_NC];
+            bool live[SK_NC], have[SK_NC];
+#pragma unroll
+            for (int i = 0; i < SK_NC; i++) {
+                const uint32_t k = base + (uint32_t)i * SK_THREADS + tid;
+                live[i] = have[i] = k < n;
+                p[i] = live[i] ? s_list[k] : 0u;
+            }
+            __syncthreads();                            /* this round's entries are read: the front of s_list takes the results */
+            sk_descend_nc(a, p, live, out);
+#pragma unroll
+            for (int i = 0; i < SK_NC; i++) {
+                if (!have[i]) continue;
+                a.H[p[i]] = out[i];                     /* replaces the mark */
+                if (out[i] && a.cand_list) s_list[atomicAdd(&s_m, 1u)] = p[i];
+            }
+        }
+        __syncthreads();
+        if (a.cand_list) {
+            const uint32_t m = s_m;
+            if (tid == 0) s_at = m ? atomicAdd(reinterpret_cast<unsigned long long *>(a.state + 6 + a.set), (unsigned long long)m) : 0ull;
+            __syncthreads();
+            const unsigned long long at = s_at;
+            for (uint32_t j = tid; j < m; j += SK_THREADS) {
+                if (at + j < a.cand_cap) a.cand_list[at + j] = s_list[j];
+                else a.H[s_list[j]] = 0u;               /* no room in the list: not a candidate (the walk works it out itself) */
+            }
+        }
+        __syncthreads();
+    }
 }
 
 /* state: [0] bit position of the next RSI, [1] RSIs found, [2] flags (1 ended, 2 data error),
@@ -242,16 +365,19 @@ __global__ void aec_skim_walk_kernel(const AecSkimArgs a)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (a.state[2] & 1ull) return;
     const AecCfg &c = a.cfg;
-    SkWalk s; s.pos = a.state[0]; s.found = a.state[1]; s.flags = 0; s.fast = a.state[3];
+    SkWalk s; s.pos = a.state[0]; s.found = a.state[1]; s.flags = 0; s.fast = a.state[3]; s.slow = 0;
     a.state[4] = s.found;
+    const uint64_t found0 = s.found;
     BitRd br;
     br.init(a.in_words, (a.nbits + 31ull) >> 5, a.nbits);
     const uint32_t *H = a.H;
     const uint32_t *H8 = a.H8 ? a.H8 + a.np : nullptr;
     while (sk_walk_step(c, br, a.nbits, a.wb, a.nh_eff, a.last, a.offsets, a.max_rsi, s,
                         [H](uint64_t rel) { return __ldcg(H + rel); }, a.grp_index, H8 != nullptr,
-                        [H8](uint64_t rel) { return __ldcg(H8 + rel); })) { }
+                        [H8](uint64_t rel) { return __ldcg(H8 + rel); }, sk_sparse_now(a),
+                        [&a, &c](uint64_t rel) { return sk_rsi_len(c, a.T, a.LV, a.np, (uint32_t)rel, __ldcg(a.R + rel)); })) { }
     a.state[0] = s.pos; a.state[1] = s.found; a.state[2] = s.flags; a.state[3] = s.fast;
+    if (sk_sparse_now(a) && sk_walk_wants_dense(s.slow, s.found - found0)) a.state[5] = 1ull;
 }
 
 /* RSI lengths doubled: dst[p] = src[p] + src[p + src[p]] for the candidates of the window */
@@ -259,10 +385,29 @@ __global__ void __launch_bounds__(SK_THREADS)
 aec_skim_hdouble_kernel(const AecSkimArgs a, const uint32_t *src, uint32_t *dst)
 {
     if (a.state[2] & 1ull) return;
-    uint32_t p = blockIdx.x * SK_THREADS + threadIdx.x;
-    if (a.cfg.pad) p <<= 3;
-    if (p >= a.nh_eff) return;
-    dst[p] = sk_hdouble(src, a.nh_eff, p);
+    if (sk_sparse_now(a)) return;                       /* aec_skim_hdouble_list_kernel does the listed positions */
+    const uint32_t sh = a.cfg.pad ? 3u : 0u;
+    const uint32_t slots = (a.nh_eff + (1u << sh) - 1u) >> sh;
+    /* a fixed grid that strides: when the window is sparse the launch costs next to nothing */
+    for (uint32_t sl = blockIdx.x * SK_THREADS + threadIdx.x; sl < slots; sl += gridDim.x * SK_THREADS) {
+        const uint32_t p = sl << sh;
+        dst[p] = sk_hdouble(src, a.nh_eff, p);
+    }
+}
+
+/* the same over the window's list of candidates that have an RSI length: the buffers hold values at listed
+ * positions only (the walk trusts them only where H is not 0) */
+__global__ void __launch_bounds__(SK_THREADS)
+aec_skim_hdouble_list_kernel(const AecSkimArgs a, const uint32_t *src, uint32_t *dst)
+{
+    if (a.state[2] & 1ull) return;
+    if (!sk_sparse_now(a)) return;
+    uint64_t n = a.state[6 + a.set];                    /* sparse: bit 63 is clear */
+    if (n > a.cand_cap) n = a.cand_cap;
+    for (uint64_t i = (uint64_t)blockIdx.x * SK_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * SK_THREADS) {
+        const uint32_t p = a.cand_list[i];
+        dst[p] = sk_hdouble_listed(a.H, src, a.nh_eff, p);
+    }
 }
 
 /* the offsets the walk skipped over (heads of its long jumps know where they start) */
@@ -298,6 +443,7 @@ aec_skim_group_index_kernel(const AecSkimArgs a)
 } // namespace
 
 uint32_t aec_skim_levels(const AecCfg &c) { return sk_levels(c); }
+uint32_t aec_skim_sparse_min_levels(void) { return SK_SPARSE_MIN_LEVELS; }
 uint64_t aec_skim_margin_bits(const AecCfg &c) { return sk_margin_bits(c); }
 
 cudaError_t aec_skim_window_launch(const AecSkimArgs &args, cudaStream_t st)
@@ -308,16 +454,29 @@ cudaError_t aec_skim_window_launch(const AecSkimArgs &args, cudaStream_t st)
     /* the bulk copy wants 16-byte aligned addresses on both sides */
     a.bulk = ((reinterpret_cast<uintptr_t>(a.in_words) & 15u) == 0 && (a.wb & 127ull) == 0) ? 1u : 0u;
     const uint32_t smem = (((SK_TILE / 32u + a.la_words + 1u + 3u) & ~3u) + SK_TILE / 32u + a.la_words + 1u) * 4u;
+    if (a.sparse) aec_skim_begin_kernel<<<1, 1, 0, st>>>(a);
     aec_skim_level0_kernel<<<(a.np + SK_TILE - 1u) / SK_TILE, SK_THREADS, smem, st>>>(a);
     const uint32_t grid = (a.np / 4u + SK_THREADS - 1u) / SK_THREADS;
     for (uint32_t j = 0; j + 1u < a.LV; j++)
         aec_skim_double_kernel<<<grid, SK_THREADS, 0, st>>>(a, j);
     const uint32_t cand = a.cfg.pad ? (a.nh_eff + 7u) / 8u : a.nh_eff;
     const uint32_t per_cta = SK_THREADS * SK_NC * SK_ROUNDS;
+    /* candidates first; the dense pass only runs when the walk has asked for it (or sparse is off) */
+    if (a.sparse) aec_skim_rsi_sparse_kernel<<<(cand + SK_CHUNK - 1u) / SK_CHUNK, SK_THREADS, 0, st>>>(a);
     aec_skim_rsi_kernel<<<(cand + per_cta - 1u) / per_cta, SK_THREADS, 0, st>>>(a);
     if (a.H8) {
         /* H -> 2 RSIs -> 4 -> 8, between two buffers; the last result lands in the second one */
-        const uint32_t g2 = (cand + SK_THREADS - 1u) / SK_THREADS;
+        uint32_t g2 = (cand + SK_THREADS - 1u) / SK_THREADS;
+        if (g2 > 148u * 32u) g2 = 148u * 32u;
+        if (a.sparse) {
+            /* one look-up chain per listed candidate: enough threads for all of them to be in flight at once */
+            uint32_t g3 = (a.cand_cap / 8u + SK_THREADS - 1u) / SK_THREADS;
+            if (g3 > 4096u) g3 = 4096u;
+            if (g3 < 1u) g3 = 1u;
+            aec_skim_hdouble_list_kernel<<<g3, SK_THREADS, 0, st>>>(a, a.H, a.H8 + a.np);
+            aec_skim_hdouble_list_kernel<<<g3, SK_THREADS, 0, st>>>(a, a.H8 + a.np, a.H8);
+            aec_skim_hdouble_list_kernel<<<g3, SK_THREADS, 0, st>>>(a, a.H8, a.H8 + a.np);
+        }
         aec_skim_hdouble_kernel<<<g2, SK_THREADS, 0, st>>>(a, a.H, a.H8 + a.np);
         aec_skim_hdouble_kernel<<<g2, SK_THREADS, 0, st>>>(a, a.H8 + a.np, a.H8);
         aec_skim_hdouble_kernel<<<g2, SK_THREADS, 0, st>>>(a, a.H8, a.H8 + a.np);

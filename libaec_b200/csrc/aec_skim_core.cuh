@@ -227,33 +227,60 @@ AEC_HD uint32_t sk_hdouble(const uint32_t *src, uint32_t nh_eff, uint32_t p)
     return h2 ? h + h2 : 0u;
 }
 
-/* One RSI of the walk: the serial part of the discovery.  Returns false when the walk ends.
- * state: pos, found, flags (1 ended, 2 data error), fast. */
-struct SkWalk { uint64_t pos, found, flags, fast; };
+/* Sparse candidates.  An RSI can only start where a CDS chain ends, and chains that start anywhere merge
+ * quickly: after 2^j CDSs the chains of ALL positions of a window end on about 2 / 2^j of its positions.
+ * The doubling passes therefore mark, in H itself, the positions where the top-level chains end (and where a
+ * run-of-zero-segment code ends, after which no chain was followed); RSI lengths are worked out for the marked
+ * positions only, the rest of H stays 0 = "not available".  A true RSI start that is not marked (fewer than
+ * 2^top plain CDSs before it: the first RSIs of a window, RSIs made of zero runs) is worked out by the walk
+ * itself with the same descent; when that happens often the walk switches the stream to dense tables. */
+#define SK_CAND 0xFFFFFFFFu                    /* H[p] between the marking and the RSI-length pass: an RSI may start at p */
+#define SK_SPARSE_MIN_LEVELS 4u                /* sparse candidates need a top level of 8 CDSs or more (<= 19 % marked) */
 
-template <class LoadH, class LoadH8>
+AEC_HD uint32_t sk_mark_pos(const AecCfg &c, uint32_t t) { return c.pad ? ((t + 7u) & ~7u) : t; }
+
+/* the doubling step of the RSI lengths when only listed positions (H != 0) carry values in src */
+AEC_HD uint32_t sk_hdouble_listed(const uint32_t *H, const uint32_t *src, uint32_t nh_eff, uint32_t p)
+{
+    const uint32_t v = src[p];
+    if (v == 0u) return 0u;
+    const uint64_t q = (uint64_t)p + v;
+    if (q >= nh_eff || H[q] == 0u) return 0u;
+    const uint32_t v2 = src[q];
+    return v2 ? v + v2 : 0u;
+}
+
+/* One RSI of the walk: the serial part of the discovery.  Returns false when the walk ends.
+ * state: pos, found, flags (1 ended, 2 data error), fast; slow = RSI lengths the walk had to work out itself. */
+struct SkWalk { uint64_t pos, found, flags, fast, slow; };
+
+/* load_h8 is trusted only where load_h is not 0 (with sparse candidates the long-jump buffers hold values at
+ * listed positions only); descend(rel) = the RSI length from the chain tables for a start the tables did
+ * not prepare (sparse candidates), 0 when there is none. */
+template <class LoadH, class LoadH8, class Descend>
 AEC_HD bool sk_walk_step(const AecCfg &c, BitRd &br, uint64_t nbits, uint64_t wb, uint32_t nh_eff, uint32_t last,
-                         uint64_t *offsets, uint64_t max_rsi, SkWalk &s, LoadH load_h, uint64_t *grp, bool have_h8, LoadH8 load_h8)
+                         uint64_t *offsets, uint64_t max_rsi, SkWalk &s, LoadH load_h, uint64_t *grp, bool have_h8, LoadH8 load_h8,
+                         bool sparse, Descend descend)
 {
     if (s.found >= max_rsi) { s.flags = 1; return false; }
     const uint64_t start = c.pad ? ((s.pos + 7ull) & ~7ull) : s.pos;
     if (start >= nbits) { s.flags = 1; return false; }
     if (start >= wb + nh_eff && !last) return false;    /* the next window takes over */
-    if (have_h8 && s.found + SK_SKIP <= max_rsi && start - wb < nh_eff) {
+    const uint64_t rel = start - wb;
+    const bool inside = rel < nh_eff;
+    uint32_t h = inside ? load_h(rel) : 0u;
+    const uint32_t h8 = (inside && have_h8) ? load_h8(rel) : 0u;      /* both loads in flight together */
+    if (have_h8 && h && h8 && s.found + SK_SKIP <= max_rsi) {
         /* eight RSIs with one look-up: their offsets are filled in afterwards, in parallel (sk_fill) */
-        const uint32_t h8 = load_h8(start - wb);
-        if (h8) {
-            offsets[s.found] = start;
-            for (uint32_t t = 1; t < SK_SKIP; t++) offsets[s.found + t] = SK_OFF_PENDING;
-            if (grp) for (uint32_t t = 0; t < SK_SKIP; t++) grp[(s.found + t) * 32ull] = SK_GRP_FAST;
-            s.found += SK_SKIP; s.fast += SK_SKIP;
-            s.pos = start + h8;
-            return true;
-        }
+        offsets[s.found] = start;
+        for (uint32_t t = 1; t < SK_SKIP; t++) offsets[s.found + t] = SK_OFF_PENDING;
+        if (grp) for (uint32_t t = 0; t < SK_SKIP; t++) grp[(s.found + t) * 32ull] = SK_GRP_FAST;
+        s.found += SK_SKIP; s.fast += SK_SKIP;
+        s.pos = start + h8;
+        return true;
     }
     offsets[s.found++] = start;                         /* even a truncated RSI may still deliver leading samples */
-    const uint64_t rel = start - wb;
-    const uint32_t h = rel < nh_eff ? load_h(rel) : 0u;
+    if (inside && h == 0u && sparse) { h = descend(rel); s.slow++; }
     if (grp) grp[(s.found - 1) * 32ull] = h ? SK_GRP_FAST : SK_GRP_MISSING;
     if (h) { s.pos = start + h; s.fast++; return true; }
     /* not in the tables: skim this RSI CDS by CDS (truncated or damaged stream, chain leaving the window) */
@@ -264,6 +291,9 @@ AEC_HD bool sk_walk_step(const AecCfg &c, BitRd &br, uint64_t nbits, uint64_t wb
     if (st.status != DEC_OK) { s.flags = 1ull | (st.status == DEC_ERROR ? 2ull : 0ull); return false; }
     return true;
 }
+
+/* after a window: so many starts were not among the candidates that dense tables are cheaper from here on */
+AEC_HD bool sk_walk_wants_dense(uint64_t slow, uint64_t found) { return slow > 16ull && slow * 4ull > found; }
 
 /* offsets the walk left pending behind RSI r (the head of a long jump): one H look-up each */
 AEC_HD void sk_fill(const uint32_t *H, uint64_t wb, uint64_t *offsets, uint64_t r, uint64_t found)

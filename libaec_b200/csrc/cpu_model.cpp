@@ -237,6 +237,13 @@ extern "C" int model_decode(uint32_t n, uint32_t J, uint32_t rsi, uint32_t flags
 
 static int g_skip8 = 0;
 extern "C" void model_set_skip8(int on) { g_skip8 = on; }   /* the walk's eight-RSI jumps (aec_skim_hdouble_kernel, aec_skim_fill_kernel) */
+static int g_sparse = 1;
+extern "C" void model_set_sparse(int on) { g_sparse = on; } /* RSI lengths at marked chain ends only (aec_skim_rsi_sparse_kernel) */
+static uint64_t g_slow = 0, g_dense_windows = 0, g_marked = 0, g_positions = 0;
+extern "C" void model_sparse_stats(uint64_t *slow, uint64_t *dense_windows, uint64_t *marked, uint64_t *positions)
+{
+    *slow = g_slow; *dense_windows = g_dense_windows; *marked = g_marked; *positions = g_positions;
+}
 
 /* the group index the way aec_build_group_index_kernel builds it: one skim of the RSI from its start offset */
 static void group_index_by_skim(const AecCfg &c, BitRd &br, uint64_t start, uint64_t *g)
@@ -286,7 +293,8 @@ extern "C" int model_scan_offsets_grp(uint32_t n, uint32_t J, uint32_t rsi, uint
     memcpy(words.data(), in, in_bytes);
     BitRd br;
     br.init(words.data(), total_words, nbits);
-    SkWalk s; s.pos = start_bit; s.found = 0; s.flags = 0; s.fast = 0;
+    SkWalk s; s.pos = start_bit; s.found = 0; s.flags = 0; s.fast = 0; s.slow = 0;
+    g_slow = g_dense_windows = g_marked = g_positions = 0;
     *found = 0; *out_flags = 0; *fast = 0; *end_pos = start_bit;
     if (max_rsi == 0) return 0;
     const uint64_t base = start_bit & ~127ull;
@@ -315,6 +323,8 @@ extern "C" int model_scan_offsets_grp(uint32_t n, uint32_t J, uint32_t rsi, uint
     const uint32_t TILE = 8192, la = sk_lookahead_words(c), nwords = TILE / 32u + la;
     std::vector<uint32_t> T, H, Rv, w(nwords + 1), pre(nwords + 2);
     const uint32_t G = (c.rsi + 31u) / 32u;
+    const bool sparse_ok = g_sparse && LV >= SK_SPARSE_MIN_LEVELS;
+    bool dense = false;                                                 /* state[5]: the walk found too many unmarked starts */
     for (uint64_t wi = 0; wi < nwin && !(s.flags & 1ull); wi++) {
         const uint64_t wb = base + wi * nh;
         const uint64_t rem = ((nbits - wb) + 31ull) & ~31ull;
@@ -343,21 +353,50 @@ extern "C" int model_scan_offsets_grp(uint32_t n, uint32_t J, uint32_t rsi, uint
         }
         for (uint32_t j = 0; j + 1 < LV; j++)
             for (uint32_t p = 0; p < np; p++) T[(size_t)(j + 1) * np + p] = sk_double(T.data() + (size_t)j * np, np, p);
-        for (uint32_t p = 0; p < nh_eff; p += c.pad ? 8u : 1u) H[p] = sk_rsi_len(c, T.data(), LV, np, p, Rv[p]);
+        const bool sparse = sparse_ok && !dense;
+        const uint32_t stp = c.pad ? 8u : 1u;
+        std::vector<uint32_t> list;
+        if (sparse) {
+            /* marks: where the top-level chains end (last doubling pass) and where run-of-zero-segment codes end (first pass) */
+            const uint32_t *Tt = T.data() + (size_t)(LV - 1u) * np;
+            for (uint32_t p = 0; p < np; p++) {
+                if (sk_jump(Tt[p])) { const uint32_t t = sk_mark_pos(c, p + sk_len(Tt[p])); if (t < nh_eff) H[t] = SK_CAND; }
+                if (sk_ros(T[p])) { const uint32_t t = sk_mark_pos(c, p + sk_len(T[p])); if (t < nh_eff) H[t] = SK_CAND; }
+            }
+            for (uint32_t p = 0; p < nh_eff; p += stp) {
+                if (H[p] != SK_CAND) { H[p] = 0u; continue; }
+                H[p] = sk_rsi_len(c, T.data(), LV, np, p, Rv[p]);
+                g_marked++;
+                if (H[p]) list.push_back(p);
+            }
+            g_positions += nh_eff / stp;
+        } else {
+            for (uint32_t p = 0; p < nh_eff; p += stp) H[p] = sk_rsi_len(c, T.data(), LV, np, p, Rv[p]);
+            g_dense_windows++;
+        }
         const uint32_t *Hp = H.data();
         std::vector<uint32_t> Ha, Hb;
-        if (g_skip8) {
+        if (g_skip8 && sparse) {
+            /* the long-jump buffers hold values at listed positions only; everything else is stale */
+            Ha.assign(np, 0xDEADBEEFu); Hb.assign(np, 0xDEADBEEFu);
+            for (uint32_t p : list) Hb[p] = sk_hdouble_listed(Hp, H.data(), nh_eff, p);
+            for (uint32_t p : list) Ha[p] = sk_hdouble_listed(Hp, Hb.data(), nh_eff, p);
+            for (uint32_t p : list) Hb[p] = sk_hdouble_listed(Hp, Ha.data(), nh_eff, p);
+        } else if (g_skip8) {
             Ha.assign(np, 0u); Hb.assign(np, 0u);
-            const uint32_t stp = c.pad ? 8u : 1u;
             for (uint32_t p = 0; p < nh_eff; p += stp) Hb[p] = sk_hdouble(H.data(), nh_eff, p);
             for (uint32_t p = 0; p < nh_eff; p += stp) Ha[p] = sk_hdouble(Hb.data(), nh_eff, p);
             for (uint32_t p = 0; p < nh_eff; p += stp) Hb[p] = sk_hdouble(Ha.data(), nh_eff, p);
         }
         const uint32_t *H8p = g_skip8 ? Hb.data() : nullptr;
-        const uint64_t f0 = s.found;
+        const uint64_t f0 = s.found, slow0 = s.slow;
+        const uint32_t *Tp = T.data(), *Rp = Rv.data();
         while (sk_walk_step(c, br, nbits, wb, nh_eff, last, offsets, max_rsi, s,
                             [Hp](uint64_t rel) { return Hp[rel]; }, grp, H8p != nullptr,
-                            [H8p](uint64_t rel) { return H8p[rel]; })) { }
+                            [H8p](uint64_t rel) { return H8p[rel]; }, sparse_ok,
+                            [&c, Tp, Rp, LV, np](uint64_t rel) { return sk_rsi_len(c, Tp, LV, np, (uint32_t)rel, Rp[rel]); })) { }
+        if (sparse_ok && sk_walk_wants_dense(s.slow - slow0, s.found - f0)) dense = true;
+        g_slow = s.slow;
         if (g_skip8)
             for (uint64_t r = f0; r < s.found; r++) sk_fill(Hp, wb, offsets, r, s.found);
         if (grp) {                                                      /* aec_skim_group_index_kernel */

@@ -10,7 +10,7 @@ import pytest
 
 from cases import pack_samples, random_case, random_params, synth_values
 from oracle import pyoracle as po
-from oracle.pyoracle import AEC_DATA_SIGNED, AEC_PAD_RSI
+from oracle.pyoracle import AEC_DATA_PREPROCESS, AEC_DATA_SIGNED, AEC_PAD_RSI
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -184,3 +184,78 @@ def test_eight_rsi_jumps_of_the_walk(model):
         assert done > 15
     finally:
         model.model_set_skip8(0)
+
+
+def sparse_stats(m):
+    v = [C.c_uint64(0) for _ in range(4)]
+    m.model_sparse_stats(*[C.byref(x) for x in v])
+    return tuple(x.value for x in v)                     # slow, dense windows, marked, positions
+
+
+@pytest.mark.parametrize("skip8", [0, 1])
+def test_sparse_candidates_give_the_same_offsets_as_dense_tables(model, skip8):
+    """RSI lengths at marked chain ends only (SK_CAND): same offsets, same group index as with a length for every
+    position; few positions are marked; zero-heavy streams, whose RSI starts follow no plain chain, make the walk
+    work the lengths out itself and then ask for dense tables -- with the same result."""
+    model.model_set_skip8(skip8)
+    try:
+        done = switched = 0
+        for seed in range(60):
+            rng = np.random.default_rng(91_000 + seed)
+            p = random_params(rng, allow_pad=bool(seed & 1))
+            rsi = int(rng.integers(9, 130))
+            p = type(p)(p.bits_per_sample, p.block_size, rsi, p.flags)
+            R = p.rsi * p.block_size
+            nrsi = int(rng.integers(24, 60))
+            if nrsi * R > 400_000:
+                nrsi = max(20, 400_000 // R)
+            count = nrsi * R - int(rng.integers(0, R))
+            kind = int(rng.integers(0, 6)) if seed % 3 else 4          # every third stream: 90 % zeros
+            vals = synth_values(rng, p.bits_per_sample, count, kind, bool(p.flags & AEC_DATA_SIGNED))
+            if kind == 4 and seed % 2:                                 # whole zero segments between the data
+                v2 = vals.reshape(-1)[: count // R * R].copy()
+                zero = vals.min()
+                for r0 in range(0, v2.size, R * 2):
+                    v2[r0 + R // 3: r0 + R] = zero
+                vals = np.concatenate([v2, vals[v2.size:]])
+            raw = np.ascontiguousarray(pack_samples(vals, p))
+            enc = po.orc_encode(p, raw, want_offsets=True, pad_rsi_build=bool(p.flags & AEC_PAD_RSI))
+            assert enc["status"] == 0
+            comp = enc["out"]
+            window = max(4096, (comp.size * 8 // 5) // 128 * 128)      # about five windows
+            o1, e1, _, _ = scan(model, p, comp, nrsi + 3, 0, 1)
+            k = min(o1.size, enc["offsets"].size)
+            assert np.array_equal(o1[:k], enc["offsets"][:k])
+            model.model_set_sparse(0)
+            od, ed, fd, _ = scan(model, p, comp, nrsi + 3, window, 0)
+            gd, ref, _ = scan_grp(model, p, comp, nrsi, window)
+            model.model_set_sparse(1)
+            os_, es, fs, _ = scan(model, p, comp, nrsi + 3, window, 0)
+            slow, dense_windows, marked, positions = sparse_stats(model)
+            gs, _, _ = scan_grp(model, p, comp, nrsi, window)
+            assert e1 == ed == es and np.array_equal(o1, od) and np.array_equal(o1, os_), (seed, p, kind)
+            G = (p.rsi + 31) // 32
+            used = (p.rsi + G - 1) // G
+            assert np.array_equal(gs[:, :used], ref[:, :used]) and np.array_equal(gd[:, :used], ref[:, :used]), (seed, p)
+            assert fs >= fd - 1, (seed, p, fs, fd)                     # nothing falls back to the CDS-by-CDS skim that did not before
+            assert marked <= positions                                 # how few depends on the data: fixed-length CDSs (uncompressed
+            #                                                            blocks) shift every position alike and their chains never merge
+            done += 1
+        assert done == 60
+        # RSIs that begin with 70 zero blocks and end with 30 data blocks: fewer than 2^top plain CDSs lead up to every RSI
+        # start, nothing marks it; the walk works the lengths out itself and asks for dense tables after the first window
+        p = po.Params(8, 8, 100, AEC_DATA_PREPROCESS)
+        R, nrsi = p.rsi * p.block_size, 400
+        rng = np.random.default_rng(5)
+        v = (100 + np.cumsum(rng.integers(-2, 3, size=nrsi * R))).reshape(nrsi, R)
+        v[:, : 70 * p.block_size] = v[:, 70 * p.block_size: 70 * p.block_size + 1]
+        raw = np.ascontiguousarray(pack_samples((v.reshape(-1) & 255).astype(np.uint64), p))
+        comp = po.orc_encode(p, raw)["out"]
+        o1, e1, _, _ = scan(model, p, comp, nrsi + 3, 0, 1)
+        o2, e2, fast, _ = scan(model, p, comp, nrsi + 3, (comp.size * 8 // 4) // 128 * 128, 0)
+        slow, dense_windows, marked, positions = sparse_stats(model)
+        assert e1 == e2 and np.array_equal(o1, o2) and fast >= nrsi - 1
+        assert slow > 16 and dense_windows >= 2, (slow, dense_windows)
+    finally:
+        model.model_set_skip8(0)
+        model.model_set_sparse(1)
