@@ -55,32 +55,24 @@ __device__ __forceinline__ bool sk_sparse_now(const AecSkimArgs &a)
     return a.sparse && !(a.state[6 + a.set] & SK_DENSE_BIT);
 }
 
-__global__ void __launch_bounds__(SK_THREADS)
-aec_skim_level0_kernel(const AecSkimArgs a)
+/* Stage the stream words of `span` bit positions from window-relative bit tile0 (plus the look-ahead) as
+ * big-endian words w[0..nwords] with their running popcount pre[0..nwords]; all threads of the CTA call it.
+ * One bulk asynchronous copy (cp.async.bulk, the TMA engine's 1-D form) brings the 16-byte aligned part
+ * straight into shared memory and signals an mbarrier; what lies behind the last whole 16 bytes of the
+ * stream comes by ordinary loads (zeros past the end). */
+__device__ __forceinline__ void sk_stage_words(const AecSkimArgs &a, uint32_t tile0, uint32_t nwords, uint32_t *w, uint32_t *pre,
+                                               uint32_t *s_part, unsigned long long *s_mbar)
 {
-    if (a.state[2] & 1ull) return;                      /* the walk has already ended */
-    const AecCfg &c = a.cfg;
-    extern __shared__ __align__(16) uint32_t sk_smem[];
-    const uint32_t nwords = SK_TILE / 32u + a.la_words;
-    uint32_t *w = sk_smem;                              /* [nwords + 1], padded to a multiple of 4 words */
-    uint32_t *pre = sk_smem + ((nwords + 1u + 3u) & ~3u);   /* [nwords + 1] */
-    __shared__ uint32_t s_part[SK_THREADS / 32];
-    __shared__ __align__(8) unsigned long long s_mbar;
     const uint32_t tid = threadIdx.x;
-    const uint32_t tile0 = blockIdx.x * SK_TILE;        /* window-relative */
     const uint64_t word0 = (a.wb + tile0) >> 5;
     const uint64_t total_words = (a.nbits + 31ull) >> 5;
-
-    /* Stage the tile's words: one bulk asynchronous copy (cp.async.bulk, the TMA engine's 1-D form)
-     * brings the 16-byte aligned part straight into shared memory and signals an mbarrier; what lies
-     * behind the last whole 16 bytes of the stream comes by ordinary loads (zeros past the end). */
     uint32_t nbulk = 0;                                 /* words the bulk copy delivers */
     if (a.bulk && word0 < total_words) {
         const uint64_t avail = (total_words - word0) & ~3ull;
         const uint32_t want = (nwords + 1u) & ~3u;
         nbulk = avail < want ? (uint32_t)avail : want;
     }
-    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_mbar);
     if (nbulk) {
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar) : "memory");
@@ -108,29 +100,43 @@ aec_skim_level0_kernel(const AecSkimArgs a)
         for (uint32_t i = tid; i < nbulk; i += SK_THREADS) w[i] = __byte_perm(w[i], 0, 0x0123);   /* to big endian */
     }
     __syncthreads();
-    {
-        /* nwords <= 256 + 70: two rounds of a block-wide exclusive scan */
-        uint32_t carry = 0;
-        for (uint32_t base = 0; base < nwords + 1u; base += SK_THREADS) {
-            const uint32_t i = base + tid;
-            const uint32_t v = i < nwords ? (uint32_t)__popc(w[i]) : 0u;
-            uint32_t inc = v;
+    /* rounds of a block-wide exclusive scan */
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nwords + 1u; base += SK_THREADS) {
+        const uint32_t i = base + tid;
+        const uint32_t v = i < nwords ? (uint32_t)__popc(w[i]) : 0u;
+        uint32_t inc = v;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, off);
-                if ((tid & 31u) >= (uint32_t)off) inc += o;
-            }
-            if ((tid & 31u) == 31u) s_part[tid >> 5] = inc;
-            __syncthreads();
-            uint32_t before = carry;
-            for (uint32_t ww = 0; ww < (tid >> 5); ww++) before += s_part[ww];
-            if (i <= nwords) pre[i] = before + inc - v;
-            uint32_t tot = 0;
-            for (uint32_t ww = 0; ww < SK_THREADS / 32; ww++) tot += s_part[ww];
-            carry += tot;
-            __syncthreads();
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+            if ((tid & 31u) >= (uint32_t)off) inc += o;
         }
+        if ((tid & 31u) == 31u) s_part[tid >> 5] = inc;
+        __syncthreads();
+        uint32_t before = carry;
+        for (uint32_t ww = 0; ww < (tid >> 5); ww++) before += s_part[ww];
+        if (i <= nwords) pre[i] = before + inc - v;
+        uint32_t tot = 0;
+        for (uint32_t ww = 0; ww < SK_THREADS / 32; ww++) tot += s_part[ww];
+        carry += tot;
+        __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(SK_THREADS)
+aec_skim_level0_kernel(const AecSkimArgs a)
+{
+    if (a.state[2] & 1ull) return;                      /* the walk has already ended */
+    const AecCfg &c = a.cfg;
+    extern __shared__ __align__(16) uint32_t sk_smem[];
+    const uint32_t nwords = SK_TILE / 32u + a.la_words;
+    uint32_t *w = sk_smem;                              /* [nwords + 1], padded to a multiple of 4 words */
+    uint32_t *pre = sk_smem + ((nwords + 1u + 3u) & ~3u);   /* [nwords + 1] */
+    __shared__ uint32_t s_part[SK_THREADS / 32];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tile0 = blockIdx.x * SK_TILE;        /* window-relative */
+    sk_stage_words(a, tile0, nwords, w, pre, s_part, &s_mbar);
     const bool sparse = sk_sparse_now(a);
     /* bits of the stream that exist, relative to the tile */
     const uint64_t tile_abs = a.wb + tile0;
@@ -141,11 +147,11 @@ aec_skim_level0_kernel(const AecSkimArgs a)
         uint32_t t0 = 0u, r0 = 0u;
         if (q < limit) {
             t0 = sk_entry(c, w, pre, nwords, q, limit, 0u);
-            r0 = c.pp ? sk_entry(c, w, pre, nwords, q, limit, 1u) : t0;
+            r0 = (c.pp && !sparse) ? sk_entry(c, w, pre, nwords, q, limit, 1u) : t0;
         }
         a.T[p] = t0;
-        a.R[p] = r0;
-        if (sparse) a.H[p] = 0u;                        /* the doubling passes mark the candidates in here */
+        if (sparse) a.H[p] = 0u;                        /* the doubling passes mark the candidates in here; R: candidates only, later */
+        else a.R[p] = r0;
     }
 }
 
@@ -197,8 +203,10 @@ constexpr int SK_NC = 4;
 constexpr int SK_ROUNDS = AEC_SK_ROUNDS;   /* a CTA takes SK_ROUNDS x SK_NC x 256 CONSECUTIVE candidates: the chains of neighbouring
                                      * candidates stay within a few thousand positions of each other at every level, so the
                                      * look-ups of one CTA fall into a handful of compact table regions that its L1 keeps */
-/* The descent of sk_rsi_len for SK_NC starts p[i] at once (live[i]: there is a candidate); out[i] = RSI length or 0. */
-__device__ __forceinline__ void sk_descend_nc(const AecSkimArgs &a, const uint32_t (&p)[SK_NC], bool (&live)[SK_NC], uint32_t (&out)[SK_NC])
+/* The descent of sk_rsi_len for SK_NC starts p[i] at once (live[i]: there is a candidate, first_e[i] the entry of
+ * its first CDS); out[i] = RSI length or 0. */
+__device__ __forceinline__ void sk_descend_nc(const AecSkimArgs &a, const uint32_t (&p)[SK_NC], const uint32_t (&first_e)[SK_NC],
+                                              bool (&live)[SK_NC], uint32_t (&out)[SK_NC])
 {
     const AecCfg &c = a.cfg;
     const uint32_t np = a.np, rsi = c.rsi;
@@ -206,7 +214,7 @@ __device__ __forceinline__ void sk_descend_nc(const AecSkimArgs &a, const uint32
     uint32_t q[SK_NC], rem[SK_NC];
 #pragma unroll
     for (int i = 0; i < SK_NC; i++) {
-        const uint32_t first = live[i] ? a.R[p[i]] : 0u;
+        const uint32_t first = live[i] ? first_e[i] : 0u;
         uint32_t b = sk_blk(first);
         if (b == 0u) b = rsi < 64u ? rsi : 64u;                 /* run-of-zero-segment at block 0 */
         live[i] = live[i] && first >= 0x1000u && b <= rsi;
@@ -267,56 +275,85 @@ aec_skim_rsi_kernel(const AecSkimArgs a)
     for (int round = 0; round < SK_ROUNDS; round++) {
         /* candidate i of this thread: consecutive threads take consecutive positions (coalesced R / H accesses) */
         const uint32_t base = (blockIdx.x * (uint32_t)SK_ROUNDS + (uint32_t)round) * (uint32_t)(SK_NC * SK_THREADS) + threadIdx.x;
-        uint32_t p[SK_NC], out[SK_NC];
+        uint32_t p[SK_NC], first_e[SK_NC], out[SK_NC];
         bool live[SK_NC];
 #pragma unroll
         for (int i = 0; i < SK_NC; i++) {
             p[i] = (base + (uint32_t)i * SK_THREADS) * step;
             live[i] = p[i] < a.nh_eff;
+            first_e[i] = live[i] ? a.R[p[i]] : 0u;
         }
-        sk_descend_nc(a, p, live, out);
+        sk_descend_nc(a, p, first_e, live, out);
 #pragma unroll
         for (int i = 0; i < SK_NC; i++)
             if (p[i] < a.nh_eff) a.H[p[i]] = out[i];
     }
 }
 
-/* The candidates only.  A CTA collects the marked positions of SK_CHUNK consecutive candidate slots in shared
- * memory -- in batches of up to SK_LIST, so that a window full of marks (fixed-length CDSs: chains that never
- * merge) still fits -- works out their RSI lengths SK_NC per thread like the dense pass, and appends the
- * positions that have one to the window's list (the long-jump passes run over that list). */
+/* The candidates only.  A CTA takes SK_CHUNK consecutive bit positions: it stages their stream words like the
+ * level-0 kernel does (the first CDS of an RSI carries the reference sample: its entry R is worked out here,
+ * for the candidates, instead of for every position), collects the marked positions in shared memory -- in
+ * batches, so that a window full of marks (fixed-length CDSs: chains that never merge) still fits -- works
+ * out their RSI lengths SK_NC per thread like the dense pass, and appends the positions that have one to the
+ * window's list (the long-jump passes run over that list). */
 constexpr uint32_t SK_CHUNK = 32768;
-constexpr uint32_t SK_LIST = 4096;
+constexpr uint32_t SK_LIST = 6144;
+constexpr uint32_t SK_CHUNK_WORDS = SK_CHUNK / 32u + 72u;   /* + the longest CDS (sk_lookahead_words <= 68) */
 __global__ void __launch_bounds__(SK_THREADS)
 aec_skim_rsi_sparse_kernel(const AecSkimArgs a)
 {
     if (a.state[2] & 1ull) return;
     if (!sk_sparse_now(a)) return;
+    const AecCfg &c = a.cfg;
+    __shared__ __align__(16) uint32_t s_w[SK_CHUNK_WORDS + 4];
+    __shared__ uint32_t s_pre[SK_CHUNK_WORDS + 4];
     __shared__ uint32_t s_list[SK_LIST];                /* the batch; its front is reused for the positions to be listed */
+    __shared__ uint32_t s_part[SK_THREADS / 32];
+    __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ uint32_t s_n, s_m;
     __shared__ unsigned long long s_at;
     const uint32_t tid = threadIdx.x;
-    const uint32_t sh = a.cfg.pad ? 3u : 0u;
-    const uint32_t slots = (a.nh_eff + (1u << sh) - 1u) >> sh;
-    const uint32_t slot0 = blockIdx.x * SK_CHUNK;
-    const uint32_t slot1 = slot0 + SK_CHUNK < slots ? slot0 + SK_CHUNK : slots;
-    constexpr uint32_t PER_PASS = SK_THREADS * 4u;      /* slots looked at between two checks of the batch's fill */
+    const uint32_t sh = c.pad ? 3u : 0u;
+    const uint32_t pos0 = blockIdx.x * SK_CHUNK;        /* window-relative */
+    if (pos0 >= a.nh_eff) return;
+    const uint32_t pos1 = pos0 + SK_CHUNK < a.nh_eff ? pos0 + SK_CHUNK : a.nh_eff;
+    const uint32_t nwords = SK_CHUNK / 32u + a.la_words;
+    sk_stage_words(a, pos0, nwords, s_w, s_pre, s_part, &s_mbar);
+    const uint64_t chunk_abs = a.wb + pos0;
+    const uint32_t limit = a.nbits > chunk_abs ? (uint32_t)min((unsigned long long)(a.nbits - chunk_abs), 0x7FFFFFFFull) : 0u;
+    constexpr uint32_t PER_PASS = SK_THREADS * 16u;     /* slots looked at between two checks of the batch's fill */
+    const uint32_t slot0 = pos0 >> sh, slot1 = (pos1 + (1u << sh) - 1u) >> sh;
     uint32_t next = slot0;
     while (next < slot1) {
         if (tid == 0) { s_n = 0u; s_m = 0u; }
         __syncthreads();
-        /* collect: whole passes of 1024 slots while the batch surely has room for another one */
+        /* collect: whole passes while the batch surely has room for another one */
         while (next < slot1) {
-            const uint32_t sl = next + tid * 4u;
-            if (sh == 0u && sl + 3u < slot1) {
-                const uint4 h = *reinterpret_cast<const uint4 *>(a.H + sl);     /* slot0 and nh_eff are multiples of 4 words apart: aligned */
-                if (h.x == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl;
-                if (h.y == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl + 1u;
-                if (h.z == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl + 2u;
-                if (h.w == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl + 3u;
+            if (sh == 0u) {
+                uint4 h[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {           /* four 16-byte loads in flight per thread */
+                    const uint32_t sl = next + ((uint32_t)k * SK_THREADS + tid) * 4u;
+                    h[k] = sl + 3u < slot1 ? *reinterpret_cast<const uint4 *>(a.H + sl) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t sl = next + ((uint32_t)k * SK_THREADS + tid) * 4u;
+                    if (sl + 3u < slot1) {
+                        if (h[k].x == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl;
+                        if (h[k].y == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl + 1u;
+                        if (h[k].z == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl + 2u;
+                        if (h[k].w == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl + 3u;
+                    } else {
+                        for (uint32_t t = 0; t < 4u; t++)
+                            if (sl + t < slot1 && a.H[sl + t] == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl + t;
+                    }
+                }
             } else {
-                for (uint32_t k = 0; k < 4u; k++)
-                    if (sl + k < slot1 && a.H[(sl + k) << sh] == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = (sl + k) << sh;
+                for (uint32_t k = 0; k < 16u; k++) {
+                    const uint32_t sl = next + k * SK_THREADS + tid;
+                    if (sl < slot1 && a.H[sl << sh] == SK_CAND) s_list[atomicAdd(&s_n, 1u)] = sl << sh;
+                }
             }
             next += PER_PASS;
             __syncthreads();
@@ -326,20 +363,23 @@ aec_skim_rsi_sparse_kernel(const AecSkimArgs a)
         __syncthreads();
         const uint32_t n = s_n;
         for (uint32_t base = 0; base < n; base += SK_NC * SK_THREADS) {
-            uint32_t p[SK_NC], out[SK_NC];
+            uint32_t p[SK_NC], first_e[SK_NC], out[SK_NC];
             bool live[SK_NC], have[SK_NC];
 #pragma unroll
             for (int i = 0; i < SK_NC; i++) {
                 const uint32_t k = base + (uint32_t)i * SK_THREADS + tid;
                 live[i] = have[i] = k < n;
                 p[i] = live[i] ? s_list[k] : 0u;
+                const uint32_t q = p[i] - pos0;
+                first_e[i] = (live[i] && q < limit) ? sk_entry(c, s_w, s_pre, nwords, q, limit, c.pp ? 1u : 0u) : 0u;
             }
             __syncthreads();                            /* this round's entries are read: the front of s_list takes the results */
-            sk_descend_nc(a, p, live, out);
+            sk_descend_nc(a, p, first_e, live, out);
 #pragma unroll
             for (int i = 0; i < SK_NC; i++) {
                 if (!have[i]) continue;
                 a.H[p[i]] = out[i];                     /* replaces the mark */
+                a.R[p[i]] = first_e[i];                 /* the group index wants it again */
                 if (out[i] && a.cand_list) s_list[atomicAdd(&s_m, 1u)] = p[i];
             }
         }
@@ -375,7 +415,11 @@ __global__ void aec_skim_walk_kernel(const AecSkimArgs a)
     while (sk_walk_step(c, br, a.nbits, a.wb, a.nh_eff, a.last, a.offsets, a.max_rsi, s,
                         [H](uint64_t rel) { return __ldcg(H + rel); }, a.grp_index, H8 != nullptr,
                         [H8](uint64_t rel) { return __ldcg(H8 + rel); }, sk_sparse_now(a),
-                        [&a, &c](uint64_t rel) { return sk_rsi_len(c, a.T, a.LV, a.np, (uint32_t)rel, __ldcg(a.R + rel)); })) { }
+                        [&a, &c, &br](uint64_t rel) {
+                            /* a start nobody marked has no R entry either: parse its first CDS, keep it for the group index */
+                            const uint32_t first = sk_first_entry_serial(c, br, a.wb + rel);
+                            a.R[rel] = first;
+                            return sk_rsi_len(c, a.T, a.LV, a.np, (uint32_t)rel, first); })) { }
     a.state[0] = s.pos; a.state[1] = s.found; a.state[2] = s.flags; a.state[3] = s.fast;
     if (sk_sparse_now(a) && sk_walk_wants_dense(s.slow, s.found - found0)) a.state[5] = 1ull;
 }
@@ -462,7 +506,7 @@ cudaError_t aec_skim_window_launch(const AecSkimArgs &args, cudaStream_t st)
     const uint32_t cand = a.cfg.pad ? (a.nh_eff + 7u) / 8u : a.nh_eff;
     const uint32_t per_cta = SK_THREADS * SK_NC * SK_ROUNDS;
     /* candidates first; the dense pass only runs when the walk has asked for it (or sparse is off) */
-    if (a.sparse) aec_skim_rsi_sparse_kernel<<<(cand + SK_CHUNK - 1u) / SK_CHUNK, SK_THREADS, 0, st>>>(a);
+    if (a.sparse) aec_skim_rsi_sparse_kernel<<<(a.nh_eff + SK_CHUNK - 1u) / SK_CHUNK, SK_THREADS, 0, st>>>(a);
     aec_skim_rsi_kernel<<<(cand + per_cta - 1u) / per_cta, SK_THREADS, 0, st>>>(a);
     if (a.H8) {
         /* H -> 2 RSIs -> 4 -> 8, between two buffers; the last result lands in the second one */

@@ -250,6 +250,19 @@ AEC_HD uint32_t sk_hdouble_listed(const uint32_t *H, const uint32_t *src, uint32
     return v2 ? v + v2 : 0u;
 }
 
+/* The entry of an RSI's first CDS (what R[p] holds) by parsing the stream at absolute bit `pos` the way the
+ * one-thread scan does: for starts nobody prepared an R entry for (sparse candidates compute R at marked
+ * positions only).  0 when the stream does not hold a whole CDS there; a run-of-zero-segment code comes out
+ * resolved for block 0 (sk_rsi_len and sk_group_entry resolve the 0 of the tables to the same count). */
+AEC_HD uint32_t sk_first_entry_serial(const AecCfg &c, BitRd &br, uint64_t pos)
+{
+    RsiDec st; st.pos = pos; st.zero_left = 0; st.status = DEC_OK;
+    if (!aec_skim_block(c, br, st, 0u)) return 0u;
+    const uint64_t len = st.pos - pos;
+    const uint32_t blk = 1u + st.zero_left;
+    return (len <= 0xFFFFFull && blk <= 0xFFFu) ? (((uint32_t)len << 12) | blk) : 0u;
+}
+
 /* One RSI of the walk: the serial part of the discovery.  Returns false when the walk ends.
  * state: pos, found, flags (1 ended, 2 data error), fast; slow = RSI lengths the walk had to work out itself. */
 struct SkWalk { uint64_t pos, found, flags, fast, slow; };

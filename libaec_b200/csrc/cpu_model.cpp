@@ -331,7 +331,8 @@ extern "C" int model_scan_offsets_grp(uint32_t n, uint32_t J, uint32_t rsi, uint
         const uint32_t np = (uint32_t)(nh + margin < rem ? nh + margin : rem);
         const uint32_t last = (wi + 1 == nwin) ? 1u : 0u;
         const uint32_t nh_eff = last ? np : (uint32_t)nh;
-        T.assign((size_t)LV * np, 0u); H.assign(np, 0u); Rv.assign(np, 0u);
+        const bool sparse = sparse_ok && !dense;
+        T.assign((size_t)LV * np, 0u); H.assign(np, 0u); Rv.assign(np, sparse ? 0xDEADBEEFu : 0u);   /* sparse: R exists at candidates only */
         for (uint32_t tile0 = 0; tile0 < np; tile0 += TILE) {           /* level-0 kernel, one CTA */
             const uint64_t word0 = (wb + tile0) >> 5;
             for (uint32_t i = 0; i <= nwords; i++) {
@@ -346,14 +347,14 @@ extern "C" int model_scan_offsets_grp(uint32_t n, uint32_t J, uint32_t rsi, uint
                 uint32_t t0 = 0, r0 = 0;
                 if (q < limit) {
                     t0 = sk_entry(c, w.data(), pre.data(), nwords, q, limit, 0u);
-                    r0 = c.pp ? sk_entry(c, w.data(), pre.data(), nwords, q, limit, 1u) : t0;
+                    r0 = (c.pp && !sparse) ? sk_entry(c, w.data(), pre.data(), nwords, q, limit, 1u) : t0;
                 }
-                T[tile0 + q] = t0; Rv[tile0 + q] = r0;
+                T[tile0 + q] = t0;
+                if (!sparse) Rv[tile0 + q] = r0;
             }
         }
         for (uint32_t j = 0; j + 1 < LV; j++)
             for (uint32_t p = 0; p < np; p++) T[(size_t)(j + 1) * np + p] = sk_double(T.data() + (size_t)j * np, np, p);
-        const bool sparse = sparse_ok && !dense;
         const uint32_t stp = c.pad ? 8u : 1u;
         std::vector<uint32_t> list;
         if (sparse) {
@@ -363,8 +364,24 @@ extern "C" int model_scan_offsets_grp(uint32_t n, uint32_t J, uint32_t rsi, uint
                 if (sk_jump(Tt[p])) { const uint32_t t = sk_mark_pos(c, p + sk_len(Tt[p])); if (t < nh_eff) H[t] = SK_CAND; }
                 if (sk_ros(T[p])) { const uint32_t t = sk_mark_pos(c, p + sk_len(T[p])); if (t < nh_eff) H[t] = SK_CAND; }
             }
+            /* aec_skim_rsi_sparse_kernel: a CTA stages the words of its chunk of positions and works out R for its candidates */
+            const uint32_t CH = 32768, cwords = CH / 32u + la;
+            std::vector<uint32_t> cw(cwords + 1), cpre(cwords + 2);
+            uint32_t staged = 0xFFFFFFFFu;
             for (uint32_t p = 0; p < nh_eff; p += stp) {
                 if (H[p] != SK_CAND) { H[p] = 0u; continue; }
+                const uint32_t ch0 = p / CH * CH;
+                if (staged != ch0) {
+                    const uint64_t word0 = (wb + ch0) >> 5;
+                    for (uint32_t i = 0; i <= cwords; i++) { const uint64_t x = word0 + i; cw[i] = x < total_words ? aec_bswap32(words[x]) : 0u; }
+                    cpre[0] = 0;
+                    for (uint32_t i = 0; i <= cwords; i++) cpre[i + 1] = cpre[i] + (i < cwords ? sk_popc(cw[i]) : 0u);
+                    staged = ch0;
+                }
+                const uint64_t ch_abs = wb + ch0;
+                const uint32_t climit = nbits > ch_abs ? (uint32_t)((nbits - ch_abs) < 0x7FFFFFFFull ? (nbits - ch_abs) : 0x7FFFFFFFull) : 0u;
+                const uint32_t q = p - ch0;
+                Rv[p] = q < climit ? sk_entry(c, cw.data(), cpre.data(), cwords, q, climit, c.pp ? 1u : 0u) : 0u;
                 H[p] = sk_rsi_len(c, T.data(), LV, np, p, Rv[p]);
                 g_marked++;
                 if (H[p]) list.push_back(p);
@@ -390,12 +407,15 @@ extern "C" int model_scan_offsets_grp(uint32_t n, uint32_t J, uint32_t rsi, uint
         }
         const uint32_t *H8p = g_skip8 ? Hb.data() : nullptr;
         const uint64_t f0 = s.found, slow0 = s.slow;
-        const uint32_t *Tp = T.data(), *Rp = Rv.data();
+        const uint32_t *Tp = T.data(); uint32_t *Rp = Rv.data();
         while (sk_walk_step(c, br, nbits, wb, nh_eff, last, offsets, max_rsi, s,
                             [Hp](uint64_t rel) { return Hp[rel]; }, grp, H8p != nullptr,
-                            [H8p](uint64_t rel) { return H8p[rel]; }, sparse_ok,
-                            [&c, Tp, Rp, LV, np](uint64_t rel) { return sk_rsi_len(c, Tp, LV, np, (uint32_t)rel, Rp[rel]); })) { }
-        if (sparse_ok && sk_walk_wants_dense(s.slow - slow0, s.found - f0)) dense = true;
+                            [H8p](uint64_t rel) { return H8p[rel]; }, sparse,
+                            [&c, &br, Tp, Rp, LV, np, wb, sparse](uint64_t rel) {
+                                /* a start nobody marked has no R entry either: parse its first CDS, keep it for the group index */
+                                if (sparse) Rp[rel] = sk_first_entry_serial(c, br, wb + rel);
+                                return sk_rsi_len(c, Tp, LV, np, (uint32_t)rel, Rp[rel]); })) { }
+        if (sparse && sk_walk_wants_dense(s.slow - slow0, s.found - f0)) dense = true;
         g_slow = s.slow;
         if (g_skip8)
             for (uint64_t r = f0; r < s.found; r++) sk_fill(Hp, wb, offsets, r, s.found);

@@ -16,7 +16,7 @@ j=json.loads(open("gpurun_out/r2_p_bench.json").read())
 print("value", j["value"])
 for k in ("e2e","e2e_indexed","e2e_pageable","pcie_copy_floor"): print(k, j[k]["value"], j[k]["ms_per_step"])
 PY
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:skim -c 200 --csv --log-file gpurun_out/r2_skim_sparse_launches.csv python profiles/tools/time_noindex.py c1 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -k regex:skim -c 200 --csv --log-file gpurun_out/r2_skim_sparse_launches.csv python profiles/tools/time_noindex.py c1 > /dev/null 2>&1
 python - <<'PY'
 import csv, collections
 rows = [r for r in csv.reader(open("gpurun_out/r2_skim_sparse_launches.csv")) if len(r) > 5 and r[0].isdigit()]
