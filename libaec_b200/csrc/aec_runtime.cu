@@ -871,10 +871,11 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
      * longer than the tables; three more passes give the length of eight RSIs in a row and the walk an
      * eighth of its steps.  Decided from what the caller expects: RSIs asked for per window of stream. */
     const double rsis_per_window = (double)max_rsi * (double)(nh < span ? nh : span) / (double)span;
-    /* Sparse candidates (aec_skim_core.cuh: SK_CAND) make the tables cheap enough for the walk to show: the long
-     * jumps, which then run over the list of candidates only, pay from a few hundred RSIs per window on. */
+    /* The walk costs about 0.8 us per RSI while table kernels run next to it, the tables of a window about
+     * 0.9 ms (1.15 ms dense), the long-jump passes 0.13 ms over the candidate list: measured break-even around 1000
+     * RSIs per window (profiles/r2_summary.md). */
     const bool sparse = ctx->scan_sparse && LV >= aec_skim_sparse_min_levels();
-    const bool skip8 = ctx->scan_skip8 == 1 || (ctx->scan_skip8 < 0 && rsis_per_window > (sparse ? 256.0 : 2500.0));
+    const bool skip8 = ctx->scan_skip8 == 1 || (ctx->scan_skip8 < 0 && rsis_per_window > (sparse ? 1000.0 : 1500.0));
     const size_t cand_cap = (sparse && skip8) ? (size_t)((np_max / 4u + 63u) & ~63ull) : 0;
     /* the levels, H and R (and two doubling buffers, and the list of candidates) */
     const size_t set_words = (size_t)(LV + 2u + (skip8 ? 2u : 0u)) * (size_t)np_max + cand_cap;
@@ -927,7 +928,8 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
             CK(cudaMemcpyAsync(&ctx->h_res[16 + 4 * s4], state, 32, cudaMemcpyDeviceToHost, ctx->s_walk), "memcpy(scan progress)");
             CK(cudaEventRecord(ctx->ev_prog[s4], ctx->s_walk), "cudaEventRecord");
         }
-        ctx->launches += LV + 2u + (sparse ? 2u : 0u) + (skip8 ? (sparse ? 7u : 4u) : 0u) + (d_grp ? 1u : 0u);
+        /* level 0, LV - 1 doubling passes, RSI lengths (+ begin and the candidates' pass), the long jumps, walk (+ fill), group index */
+        ctx->launches += 1u + (LV - 1u) + 1u + (sparse ? 2u : 0u) + (skip8 ? (sparse ? 7u : 4u) : 0u) + 1u + (d_grp ? 1u : 0u);
         if (prog && i >= 2) {
             /* The walk through the window two back has finished long ago; two windows of work are queued
              * behind it, so the device stays busy while the host hands that window's RSIs on (a copy to
