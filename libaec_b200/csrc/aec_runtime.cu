@@ -364,6 +364,7 @@ int pipe_abort(aecb200_ctx *ctx, int rc)
 {
     cudaStreamSynchronize(ctx->s_in);
     for (cudaStream_t st : ctx->s_idx) if (st) cudaStreamSynchronize(st);
+    if (ctx->s_walk) cudaStreamSynchronize(ctx->s_walk);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->s_out);
     return rc;
@@ -929,7 +930,7 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
             CK(cudaEventRecord(ctx->ev_prog[s4], ctx->s_walk), "cudaEventRecord");
         }
         /* level 0, LV - 1 doubling passes, RSI lengths (+ begin and the candidates' pass), the long jumps, walk (+ fill), group index */
-        ctx->launches += 1u + (LV - 1u) + 1u + (sparse ? 2u : 0u) + (skip8 ? (sparse ? 7u : 4u) : 0u) + 1u + (d_grp ? 1u : 0u);
+        ctx->launches += 1u + (LV - 1u) + 1u + (sparse ? 2u : 0u) + (skip8 ? (sparse ? 5u : 4u) : 0u) + 1u + (d_grp ? 1u : 0u);
         if (prog && i >= 2) {
             /* The walk through the window two back has finished long ago; two windows of work are queued
              * behind it, so the device stays busy while the host hands that window's RSIs on (a copy to

@@ -228,7 +228,8 @@ __device__ __forceinline__ void sk_descend_nc(const AecSkimArgs &a, const uint32
             do {
                 uint32_t e[SK_NC];
 #pragma unroll
-                for (int i = 0; i < SK_NC; i++) e[i] = (rem[i] && q[i] < np) ? __ldg(Tj + q[i]) : 0u;
+                for (int i = 0; i < SK_NC; i++)          /* 2^j CDSs stand for 2^j blocks at least: no look-up that cannot fit */
+                    e[i] = (rem[i] >= (1u << j) && q[i] < np) ? __ldg(Tj + q[i]) : 0u;
                 again = false;
 #pragma unroll
                 for (int i = 0; i < SK_NC; i++) {
@@ -439,10 +440,11 @@ aec_skim_hdouble_kernel(const AecSkimArgs a, const uint32_t *src, uint32_t *dst)
     }
 }
 
-/* the same over the window's list of candidates that have an RSI length: the buffers hold values at listed
- * positions only (the walk trusts them only where H is not 0) */
+/* Sparse candidates: the length of eight RSIs in a row for the window's list of candidates that have an RSI
+ * length, hop by hop through H (eight dependent look-ups per candidate, a million candidates in flight); the
+ * buffer holds values at listed positions only (the walk trusts it only where H is not 0). */
 __global__ void __launch_bounds__(SK_THREADS)
-aec_skim_hdouble_list_kernel(const AecSkimArgs a, const uint32_t *src, uint32_t *dst)
+aec_skim_hchase_list_kernel(const AecSkimArgs a, uint32_t *dst)
 {
     if (a.state[2] & 1ull) return;
     if (!sk_sparse_now(a)) return;
@@ -450,7 +452,7 @@ aec_skim_hdouble_list_kernel(const AecSkimArgs a, const uint32_t *src, uint32_t 
     if (n > a.cand_cap) n = a.cand_cap;
     for (uint64_t i = (uint64_t)blockIdx.x * SK_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * SK_THREADS) {
         const uint32_t p = a.cand_list[i];
-        dst[p] = sk_hdouble_listed(a.H, src, a.nh_eff, p);
+        dst[p] = sk_hchase(a.H, a.nh_eff, p);
     }
 }
 
@@ -517,9 +519,7 @@ cudaError_t aec_skim_window_launch(const AecSkimArgs &args, cudaStream_t st)
             uint32_t g3 = (a.cand_cap / 8u + SK_THREADS - 1u) / SK_THREADS;
             if (g3 > 4096u) g3 = 4096u;
             if (g3 < 1u) g3 = 1u;
-            aec_skim_hdouble_list_kernel<<<g3, SK_THREADS, 0, st>>>(a, a.H, a.H8 + a.np);
-            aec_skim_hdouble_list_kernel<<<g3, SK_THREADS, 0, st>>>(a, a.H8 + a.np, a.H8);
-            aec_skim_hdouble_list_kernel<<<g3, SK_THREADS, 0, st>>>(a, a.H8, a.H8 + a.np);
+            aec_skim_hchase_list_kernel<<<g3, SK_THREADS, 0, st>>>(a, a.H8 + a.np);
         }
         aec_skim_hdouble_kernel<<<g2, SK_THREADS, 0, st>>>(a, a.H, a.H8 + a.np);
         aec_skim_hdouble_kernel<<<g2, SK_THREADS, 0, st>>>(a, a.H8 + a.np, a.H8);

@@ -123,7 +123,7 @@ AEC_HD uint32_t sk_rsi_len(const AecCfg &c, const uint32_t *T, uint32_t LV, uint
         for (int j = (int)LV - 1; j >= 0; j--) {
             const uint32_t *Tj = T + (size_t)j * np;
             for (;;) {
-                if (q >= np) break;
+                if (q >= np || (1u << j) > rem) break;  /* 2^j CDSs stand for 2^j blocks at least: no need to look */
                 const uint32_t e = Tj[q];
                 if (!sk_jump(e) || sk_blk(e) > rem) break;
                 q += sk_len(e); rem -= sk_blk(e);
@@ -170,7 +170,7 @@ AEC_HD uint64_t sk_group_entry(const AecCfg &c, const uint32_t *T, const uint32_
         for (int j = (int)LV - 1; j >= 0; j--) {
             const uint32_t *Tj = T + (size_t)j * np;
             for (;;) {
-                if (q >= np) break;
+                if (q >= np || (1u << j) > rem) break;
                 const uint32_t e = Tj[q];
                 if (!sk_jump(e) || sk_blk(e) > rem) break;
                 q += sk_len(e); rem -= sk_blk(e);
@@ -239,17 +239,6 @@ AEC_HD uint32_t sk_hdouble(const uint32_t *src, uint32_t nh_eff, uint32_t p)
 
 AEC_HD uint32_t sk_mark_pos(const AecCfg &c, uint32_t t) { return c.pad ? ((t + 7u) & ~7u) : t; }
 
-/* the doubling step of the RSI lengths when only listed positions (H != 0) carry values in src */
-AEC_HD uint32_t sk_hdouble_listed(const uint32_t *H, const uint32_t *src, uint32_t nh_eff, uint32_t p)
-{
-    const uint32_t v = src[p];
-    if (v == 0u) return 0u;
-    const uint64_t q = (uint64_t)p + v;
-    if (q >= nh_eff || H[q] == 0u) return 0u;
-    const uint32_t v2 = src[q];
-    return v2 ? v + v2 : 0u;
-}
-
 /* The entry of an RSI's first CDS (what R[p] holds) by parsing the stream at absolute bit `pos` the way the
  * one-thread scan does: for starts nobody prepared an R entry for (sparse candidates compute R at marked
  * positions only).  0 when the stream does not hold a whole CDS there; a run-of-zero-segment code comes out
@@ -261,6 +250,20 @@ AEC_HD uint32_t sk_first_entry_serial(const AecCfg &c, BitRd &br, uint64_t pos)
     const uint64_t len = st.pos - pos;
     const uint32_t blk = 1u + st.zero_left;
     return (len <= 0xFFFFFull && blk <= 0xFFFu) ? (((uint32_t)len << 12) | blk) : 0u;
+}
+
+/* the length of SK_SKIP RSIs in a row from listed position p (H[p] != 0), hop by hop: 0 unless every one of them
+ * starts inside the part of the window that has lengths and has one (the same value three sk_hdouble steps give) */
+AEC_HD uint32_t sk_hchase(const uint32_t *H, uint32_t nh_eff, uint32_t p)
+{
+    uint64_t q = p;
+    for (uint32_t t = 0; t < SK_SKIP; t++) {
+        if (q >= nh_eff) return 0u;
+        const uint32_t h = H[q];
+        if (h == 0u) return 0u;
+        q += h;
+    }
+    return (q - p) <= 0xFFFFFFFFull ? (uint32_t)(q - p) : 0u;
 }
 
 /* One RSI of the walk: the serial part of the discovery.  Returns false when the walk ends.

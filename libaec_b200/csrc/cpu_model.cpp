@@ -395,10 +395,8 @@ extern "C" int model_scan_offsets_grp(uint32_t n, uint32_t J, uint32_t rsi, uint
         std::vector<uint32_t> Ha, Hb;
         if (g_skip8 && sparse) {
             /* the long-jump buffers hold values at listed positions only; everything else is stale */
-            Ha.assign(np, 0xDEADBEEFu); Hb.assign(np, 0xDEADBEEFu);
-            for (uint32_t p : list) Hb[p] = sk_hdouble_listed(Hp, H.data(), nh_eff, p);
-            for (uint32_t p : list) Ha[p] = sk_hdouble_listed(Hp, Hb.data(), nh_eff, p);
-            for (uint32_t p : list) Hb[p] = sk_hdouble_listed(Hp, Ha.data(), nh_eff, p);
+            Hb.assign(np, 0xDEADBEEFu);
+            for (uint32_t p : list) Hb[p] = sk_hchase(Hp, nh_eff, p);       /* aec_skim_hchase_list_kernel */
         } else if (g_skip8) {
             Ha.assign(np, 0u); Hb.assign(np, 0u);
             for (uint32_t p = 0; p < nh_eff; p += stp) Hb[p] = sk_hdouble(H.data(), nh_eff, p);
