@@ -9,8 +9,8 @@
  *
  *   1. aec_skim_level0_kernel   for EVERY bit position p of a window: if a coded data set (CDS) started
  *                               at p, how long would it be and how many blocks would it stand for
- *                               (T0[p]; R[p] = the same for the first CDS of an RSI, which carries the
- *                               reference sample).  One thread per position, the window's words and
+ *                               (T0[p]; with dense tables also R[p] = the same for the first CDS of an RSI,
+ *                               which carries the reference sample).  One thread per position, the window's words and
  *                               their running popcount staged in shared memory; a unary section is
  *                               skipped by rank/select on that popcount instead of bit by bit.
  *   2. aec_skim_double_kernel   T(j+1)[p] = T(j)[p] then T(j)[p + length]: the CDS chain from p after
@@ -19,17 +19,19 @@
  *                               then a greedy descent through the levels until exactly `rsi` blocks
  *                               are accounted for (run-of-zero-segment codes stand for "up to the end of
  *                               the 64-block segment" and are resolved here, where the block number is known).
- *      aec_skim_rsi_sparse_kernel  the same for the candidates only: an RSI starts where a chain of CDSs ends, and
+ *      aec_skim_rsi_sparse_kernel  R and H for the candidates only: an RSI starts where a chain of CDSs ends, and
  *                               the top-level chains of ALL positions end on a few per cent of them (the
  *                               doubling passes mark those in H, aec_skim_core.cuh: SK_CAND); the walk works
  *                               out the rare start that was not marked itself and turns the stream to dense
- *                               tables when that happens often.
+ *                               tables (aec_skim_rsi_kernel: every position) when that happens often.
+ *      aec_skim_hchase_list_kernel / aec_skim_hdouble_kernel  streams of many RSIs per window: the length of
+ *                               eight RSIs in a row, so that the walk takes an eighth of its steps.
  *   4. aec_skim_walk_kernel     the only serial part: one load of H per RSI from the stream's known
  *                               first bit; RSIs whose H is not available (truncated or corrupt stream,
  *                               a chain leaving the window) are skimmed CDS by CDS like the reference does.
  *
  * Everything up to the walk is independent of the entry point, so it runs on all SMs; windows bound
- * the table memory (4 bytes x (levels + 1) per stream bit).
+ * the table memory (4 bytes x (levels + 2 .. 4.25) per stream bit).
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -511,7 +513,9 @@ cudaError_t aec_skim_window_launch(const AecSkimArgs &args, cudaStream_t st)
     if (a.sparse) aec_skim_rsi_sparse_kernel<<<(a.nh_eff + SK_CHUNK - 1u) / SK_CHUNK, SK_THREADS, 0, st>>>(a);
     aec_skim_rsi_kernel<<<(cand + per_cta - 1u) / per_cta, SK_THREADS, 0, st>>>(a);
     if (a.H8) {
-        /* H -> 2 RSIs -> 4 -> 8, between two buffers; the last result lands in the second one */
+        /* dense tables: H -> 2 RSIs -> 4 -> 8, between two buffers, the last result lands in the second one;
+         * sparse candidates: eight hops per listed candidate, straight into the second one.  Both sets of
+         * kernels are launched; the window's latched mode lets one of them return at once. */
         uint32_t g2 = (cand + SK_THREADS - 1u) / SK_THREADS;
         if (g2 > 148u * 32u) g2 = 148u * 32u;
         if (a.sparse) {
