@@ -214,7 +214,7 @@ struct aecb200_ctx {
     /* RSI boundary discovery for streams without an index (aec_skim.cu) */
     DevBuf skim_tab;
     int scan_mode = 0;                   /* 0 auto, 1 always the one-thread scan, 2 always the parallel tables */
-    uint64_t scan_window_bits = 1ull << 25;
+    uint64_t scan_window_bits = 0;        /* 0: by stream size (scan_offsets_impl) */
     uint64_t scan_end = 0, scan_fast = 0;
     bool scan_grp = false;               /* the last scan also wrote the group index */
     uint64_t up_first_bits = 0;          /* un-indexed host decode: stream bits that were uploaded on `stream`; the rest is on s_in */
@@ -803,6 +803,22 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
                              uint64_t *d_rsi_offsets, size_t max_rsi, size_t *found, ScanProgress *prog,
                              uint64_t *d_grp = nullptr);
 
+/* Window size of the boundary discovery: a window costs about 0.15 ms whatever its size (launches, every
+ * kernel's tail), and the walk of window i overlaps the tables of window i+1 only when there are several: an
+ * eighth of the stream, between 2^24 and 2^26 bits (measured on the README workload: 2^25 19.4 ms, 2^26 17.9 ms;
+ * config 2, a 190 Mbit stream: 7.7 and 8.1 ms), unless the caller set one. */
+static uint64_t scan_window_bits_for(const aecb200_ctx *ctx, uint64_t span_bits)
+{
+    uint64_t nh = ctx->scan_window_bits;
+    if (nh == 0) {
+        nh = span_bits / 8ull;
+        if (nh < (1ull << 24)) nh = 1ull << 24;
+        if (nh > (1ull << 26)) nh = 1ull << 26;
+    }
+    nh = (nh + 127ull) & ~127ull;
+    return nh < 1024 ? 1024 : nh;
+}
+
 int aecb200_scan_offsets_device(aecb200_ctx *ctx, const aecb200_params *p,
                                 const void *d_in, size_t in_bytes, uint64_t start_bit,
                                 uint64_t *d_rsi_offsets, size_t max_rsi, size_t *found)
@@ -860,9 +876,9 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
      * every RSI starting inside the window can be followed to its end. */
     const uint32_t LV = aec_skim_levels(c);
     const uint64_t margin = aec_skim_margin_bits(c);
-    uint64_t nh = (ctx->scan_window_bits + 127ull) & ~127ull;
-    if (nh < 1024) nh = 1024;
     const uint64_t span = ((nbits - base) + 31ull) & ~31ull;
+    uint64_t nh = scan_window_bits_for(ctx, span);
+
     const uint64_t nwin = (span + nh - 1) / nh;
     const uint64_t np_max = nh + margin < span ? nh + margin : span;
     if (np_max >= 0x7FFFFFFFull) { snprintf(ctx->err, sizeof ctx->err, "scan window too large"); return AEC_CONF_ERROR; }
@@ -871,7 +887,8 @@ static int scan_offsets_impl(aecb200_ctx *ctx, const aecb200_params *p,
     /* Streams of many short RSIs (well-compressed data, small chunks): the one-load-per-RSI walk would take
      * longer than the tables; three more passes give the length of eight RSIs in a row and the walk an
      * eighth of its steps.  Decided from what the caller expects: RSIs asked for per window of stream. */
-    const double rsis_per_window = (double)max_rsi * (double)(nh < span ? nh : span) / (double)span;
+    /* RSIs expected per 2^25 bits of stream: the walk's cost against the tables' is a matter of RSI density */
+    const double rsis_per_window = (double)max_rsi * (double)(1ull << 25) / (double)span;
     /* The walk costs about 0.8 us per RSI while table kernels run next to it, the tables of a window about
      * 0.9 ms (1.15 ms dense), the long-jump passes 0.13 ms over the candidate list: measured break-even around 1000
      * RSIs per window (profiles/r2_summary.md). */
@@ -1301,7 +1318,7 @@ int aecb200_decode_host_resume(aecb200_ctx *ctx, const aecb200_params *p,
         size_t first = nbytes;
         ctx->up_first_bits = 0;
         if (!rsi_offsets && ctx->pipe_piece && nbytes > ((size_t)32 << 20) && pipe_prepare(ctx, 1) == AEC_OK) {
-            first = (size_t)((2 * ((ctx->scan_window_bits + 127ull) & ~127ull) + aec_skim_margin_bits(c)) / 8ull) + 65536;
+            first = (size_t)((2 * scan_window_bits_for(ctx, (uint64_t)nbytes * 8ull) + aec_skim_margin_bits(c)) / 8ull) + 65536;
             first &= ~(size_t)15;
             if (first >= nbytes) first = nbytes;
         }

@@ -42,7 +42,10 @@
 namespace {
 
 constexpr int SK_THREADS = 256;
-constexpr uint32_t SK_TILE = 8192;          /* bit positions per CTA of the level-0 kernel */
+#ifndef AEC_SK_TILE
+#define AEC_SK_TILE 8192
+#endif
+constexpr uint32_t SK_TILE = AEC_SK_TILE;   /* bit positions per CTA of the level-0 kernel */
 
 /* state[5] bit 0: the walk asked for dense tables (it runs on its own stream, next to the table kernels of the
  * following window).  A window latches the request once, before its first kernel, into bit 63 of its list
@@ -157,40 +160,49 @@ aec_skim_level0_kernel(const AecSkimArgs a)
     }
 }
 
-/* four consecutive positions per thread: one 16-byte load, four gathers in flight, one 16-byte store */
+/* SK_DP consecutive positions per thread: 16-byte loads, SK_DP gathers in flight, 16-byte stores */
+#ifndef AEC_SK_DP
+#define AEC_SK_DP 4
+#endif
+constexpr int SK_DP = AEC_SK_DP;
 __global__ void __launch_bounds__(SK_THREADS)
 aec_skim_double_kernel(const AecSkimArgs a, uint32_t level)
 {
     if (a.state[2] & 1ull) return;
-    const uint32_t p = (blockIdx.x * SK_THREADS + threadIdx.x) * 4u;      /* np is a multiple of 32 */
+    const uint32_t p = (blockIdx.x * SK_THREADS + threadIdx.x) * (uint32_t)SK_DP;      /* np is a multiple of 32 */
     if (p >= a.np) return;
     const uint32_t *src = a.T + (size_t)level * a.np;
     uint32_t *dst = a.T + (size_t)(level + 1u) * a.np;
-    const uint4 x = *reinterpret_cast<const uint4 *>(src + p);
-    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-    uint32_t y[4], r[4];
+    uint32_t xs[SK_DP], y[SK_DP], r[SK_DP];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int v = 0; v < SK_DP / 4; v++) {
+        const uint4 x = *reinterpret_cast<const uint4 *>(src + p + 4 * v);
+        xs[4 * v] = x.x; xs[4 * v + 1] = x.y; xs[4 * v + 2] = x.z; xs[4 * v + 3] = x.w;
+    }
+#pragma unroll
+    for (int i = 0; i < SK_DP; i++) {
         const uint32_t q = p + i + sk_len(xs[i]);
         y[i] = (sk_jump(xs[i]) && q < a.np) ? __ldg(src + q) : 0u;
     }
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < SK_DP; i++) {
         const uint32_t blk = sk_blk(xs[i]) + sk_blk(y[i]), len = sk_len(xs[i]) + sk_len(y[i]);
         r[i] = (sk_jump(y[i]) && blk <= 0xFFFu && len <= 0xFFFFFu) ? ((len << 12) | blk) : 0u;
     }
-    *reinterpret_cast<uint4 *>(dst + p) = make_uint4(r[0], r[1], r[2], r[3]);
+#pragma unroll
+    for (int v = 0; v < SK_DP / 4; v++)
+        *reinterpret_cast<uint4 *>(dst + p + 4 * v) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
     if (!sk_sparse_now(a)) return;
     /* candidates for RSI starts: behind a run-of-zero-segment code (level 0 is at hand in the first pass) and
      * where the chains of the top level end (the last pass has just worked them out) */
     if (level == 0u) {
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < SK_DP; i++)
             if (sk_ros(xs[i])) { const uint32_t t = sk_mark_pos(a.cfg, p + i + sk_len(xs[i])); if (t < a.nh_eff) a.H[t] = SK_CAND; }
     }
     if (level + 2u == a.LV) {
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < SK_DP; i++)
             if (sk_jump(r[i])) { const uint32_t t = sk_mark_pos(a.cfg, p + i + sk_len(r[i])); if (t < a.nh_eff) a.H[t] = SK_CAND; }
     }
 }
@@ -198,7 +210,10 @@ aec_skim_double_kernel(const AecSkimArgs a, uint32_t level)
 /* H[p] <- bits from p to the start of the next RSI when an RSI starts at p (0: not available).
  * Same walk as sk_rsi_len (aec_skim_core.cuh), NC candidates per thread in lock step so that their
  * table look-ups -- each a dependent, mostly uncached load -- are in flight together. */
-constexpr int SK_NC = 4;
+#ifndef AEC_SK_NC
+#define AEC_SK_NC 4
+#endif
+constexpr int SK_NC = AEC_SK_NC;
 #ifndef AEC_SK_ROUNDS
 #define AEC_SK_ROUNDS 2
 #endif
@@ -299,7 +314,10 @@ aec_skim_rsi_kernel(const AecSkimArgs a)
  * batches, so that a window full of marks (fixed-length CDSs: chains that never merge) still fits -- works
  * out their RSI lengths SK_NC per thread like the dense pass, and appends the positions that have one to the
  * window's list (the long-jump passes run over that list). */
-constexpr uint32_t SK_CHUNK = 32768;
+#ifndef AEC_SK_CHUNK
+#define AEC_SK_CHUNK 16384
+#endif
+constexpr uint32_t SK_CHUNK = AEC_SK_CHUNK;
 constexpr uint32_t SK_LIST = 6144;
 constexpr uint32_t SK_CHUNK_WORDS = SK_CHUNK / 32u + 72u;   /* + the longest CDS (sk_lookahead_words <= 68) */
 __global__ void __launch_bounds__(SK_THREADS)
@@ -504,7 +522,7 @@ cudaError_t aec_skim_window_launch(const AecSkimArgs &args, cudaStream_t st)
     const uint32_t smem = (((SK_TILE / 32u + a.la_words + 1u + 3u) & ~3u) + SK_TILE / 32u + a.la_words + 1u) * 4u;
     if (a.sparse) aec_skim_begin_kernel<<<1, 1, 0, st>>>(a);
     aec_skim_level0_kernel<<<(a.np + SK_TILE - 1u) / SK_TILE, SK_THREADS, smem, st>>>(a);
-    const uint32_t grid = (a.np / 4u + SK_THREADS - 1u) / SK_THREADS;
+    const uint32_t grid = (a.np / (uint32_t)SK_DP + SK_THREADS - 1u) / SK_THREADS;
     for (uint32_t j = 0; j + 1u < a.LV; j++)
         aec_skim_double_kernel<<<grid, SK_THREADS, 0, st>>>(a, j);
     const uint32_t cand = a.cfg.pad ? (a.nh_eff + 7u) / 8u : a.nh_eff;

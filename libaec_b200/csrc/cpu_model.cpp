@@ -365,7 +365,7 @@ extern "C" int model_scan_offsets_grp(uint32_t n, uint32_t J, uint32_t rsi, uint
                 if (sk_ros(T[p])) { const uint32_t t = sk_mark_pos(c, p + sk_len(T[p])); if (t < nh_eff) H[t] = SK_CAND; }
             }
             /* aec_skim_rsi_sparse_kernel: a CTA stages the words of its chunk of positions and works out R for its candidates */
-            const uint32_t CH = 32768, cwords = CH / 32u + la;
+            const uint32_t CH = 16384, cwords = CH / 32u + la;
             std::vector<uint32_t> cw(cwords + 1), cpre(cwords + 2);
             uint32_t staged = 0xFFFFFFFFu;
             for (uint32_t p = 0; p < nh_eff; p += stp) {
